@@ -1,0 +1,190 @@
+/* vivsim_b200 -- C ABI of the B200-native IB-LBM time step.
+ *
+ * The reference (haimingz/vivsim v2.0.0) is pure Python over jax.numpy and has no FFI of
+ * its own; its boundary is the set of pure functions in vivsim.lbm / lbm3d / ib / ib3d.
+ * Each entry point below replaces one of those functions (cited as reference file:line)
+ * or the composed step the reference's examples build from them.  This is what an XLA FFI
+ * custom call, a ctypes/cffi binding or any other host would bind.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller unless a parameter is named *_host;
+ *    fp32 fields, int32 indices, uint8 masks; SoA C order: f[q][x][y] / f[q][x][y][z];
+ *  - outputs are pre-allocated by the caller; nothing is allocated, freed or synchronised;
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *  - returns VSB_OK or a negative code; the message is in vsb_last_error() (thread-local);
+ *  - nothing throws across the ABI; calls are re-entrant per device;
+ *  - there is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef VIVSIM_B200_H
+#define VIVSIM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* vsb_stream_t; /* cudaStream_t */
+
+enum { VSB_OK = 0, VSB_ERR_INVALID = -1, VSB_ERR_CUDA = -2 };
+enum { VSB_COLL_BGK = 0, VSB_COLL_MRT = 1, VSB_COLL_KBC = 2, VSB_COLL_REG = 3 };
+enum { VSB_FORCE_NONE = 0, VSB_FORCE_EDM = 1, VSB_FORCE_GUO = 2 };
+enum { VSB_BC_NEE = 0, VSB_BC_NEBB = 1, VSB_BC_EQUILIBRIUM = 2, VSB_BC_BOUNCE_BACK = 3, VSB_BC_SPECULAR = 4,
+       VSB_POST_MASK = 5 };
+enum { VSB_WRAP_NONE = 0, VSB_WRAP_VELOCITY = 1, VSB_WRAP_PRESSURE = 2, VSB_WRAP_FORCE_CORRECTED = 3 };
+/* loc: x faces, y faces, z faces (reference lbm/lattice.py:64-109, lbm3d/lattice.py:64-125) */
+enum { VSB_LOC_LEFT = 0, VSB_LOC_RIGHT = 1, VSB_LOC_BOTTOM = 2, VSB_LOC_TOP = 3, VSB_LOC_BACK = 4, VSB_LOC_FRONT = 5 };
+enum { VSB_DELTA_PESKIN3 = 0, VSB_DELTA_PESKIN4 = 1, VSB_DELTA_COSINE4 = 2, VSB_DELTA_HAT2 = 3 };
+
+/* dim = 2 (D2Q9, nz ignored) or 3 (D3Q19). */
+typedef struct { int dim, nx, ny, nz; } VsbGrid;
+
+/* A wall quantity: per-face-cell device array (face shape = grid shape without the normal axis)
+ * when ptr != NULL, else the scalar `value` (reference lbm/boundary/_helpers.py:53-77). */
+typedef struct { const float* ptr; float value; } VsbWallValue;
+
+/* One post-streaming operation. */
+typedef struct {
+  int kind;            /* VSB_BC_* or VSB_POST_MASK */
+  int wrap;            /* VSB_WRAP_* (NEE / NEBB / EQUILIBRIUM only) */
+  int loc;             /* VSB_LOC_* */
+  VsbWallValue rho;    /* rho_wall (default 1)                                   */
+  VsbWallValue u[3];   /* ux_wall, uy_wall, uz_wall                              */
+  VsbWallValue g[3];   /* gx_wall ... (VSB_WRAP_FORCE_CORRECTED)                 */
+  const uint8_t* mask; /* VSB_POST_MASK: obstacle mask over the grid (1 = solid) */
+} VsbPostOp;
+
+int vsb_abi_version(void);
+const char* vsb_last_error(void);
+
+/* ---- D2Q9 / D3Q19 operators (one per reference function) ------------------------------ */
+
+/* streaming: lbm/basic.py:60-85, lbm3d/basic.py:52-87.  Periodic; bit-exact permutation. */
+int vsb_streaming(const VsbGrid* grid, const float* f, float* out, vsb_stream_t stream);
+/* get_macroscopic: lbm/basic.py:88-111, lbm3d/basic.py:90-106.  n_cells = any flattened spatial shape. */
+int vsb_macroscopic(int dim, int64_t n_cells, const float* f, float* rho, float* u, vsb_stream_t stream);
+/* get_equilibrium: lbm/basic.py:114-135, lbm3d/basic.py:109-130. */
+int vsb_equilibrium(int dim, int64_t n_cells, const float* rho, const float* u, float* feq, vsb_stream_t stream);
+/* collision_bgk / _mrt / _kbc / _reg: lbm/basic.py:138-156, lbm/collision/{mrt.py:66-88,kbc.py:10-59,reg.py:4-49}
+ * and the lbm3d twins.  op_host: Q*Q row-major HOST matrix for VSB_COLL_MRT (else NULL). */
+int vsb_collision(int dim, int64_t n_cells, int kind, double omega, const float* op_host, const float* f,
+                  const float* feq, float* out, vsb_stream_t stream);
+/* get_guo_forcing_term: lbm/forcing/guo.py:6-33, lbm3d/forcing/guo.py:13-38. */
+int vsb_guo_forcing_term(int dim, int64_t n_cells, const float* g, const float* u, float* out, vsb_stream_t stream);
+/* forcing_edm (kind EDM), forcing_guo_bgk (GUO, fop_host NULL), forcing_guo_mrt (GUO, fop_host Q*Q HOST matrix):
+ * lbm/forcing/edm.py:31, lbm/forcing/guo.py:38-57,82-107 and the lbm3d twins. */
+int vsb_forcing(int dim, int64_t n_cells, int kind, double omega, const float* fop_host, const float* f,
+                const float* g, const float* u, float* out, vsb_stream_t stream);
+/* One boundary / mask operation applied IN PLACE on post-streaming f.
+ * boundary_{nee,nebb,equilibrium} and their velocity / pressure / force_corrected wrappers:
+ *   lbm/boundary/{nee.py:19-65,nebb.py:20-62,eq.py:25-61,_helpers.py:80-239}, lbm3d/boundary/* twins;
+ * boundary_bounce_back / boundary_specular_reflection (need f_pre = pre-streaming f):
+ *   lbm/boundary/bb.py:15-95, lbm3d/boundary/bb.py:9-53;
+ * obstacle_bounce_back (VSB_POST_MASK): lbm/boundary/bb.py:98-110, lbm3d/boundary/bb.py:56-59. */
+int vsb_post_op(const VsbGrid* grid, const VsbPostOp* op, const float* f_pre, float* f, vsb_stream_t stream);
+/* boundary_characteristic: lbm/boundary/cbc.py:14-53, lbm3d/boundary/cbc.py:16-51.
+ * rho_out: face-shaped, u_out: (dim, face). */
+int vsb_boundary_characteristic(const VsbGrid* grid, int loc, const float* rho, const float* u, float* rho_out,
+                                float* u_out, vsb_stream_t stream);
+
+/* ---- immersed boundary (reference vivsim/ib, vivsim/ib3d) ------------------------------ */
+
+/* kernel_peskin_3pt / _4pt / kernel_cosine_4pt: ib/kernels.py:4-61 (+ 2-point hat, not in the reference). */
+int vsb_ib_delta(int kind, int64_t n, const float* r, float* out, vsb_stream_t stream);
+/* get_ib_stencil: ib/stencil.py:7-51 (dim 2, coords = (M,2) rows x,y; ny) and ib3d/stencil.py:7-59
+ * (dim 3, coords (M,3); ny, nz).  weights, indices: (M, (2*radius)^dim). */
+int vsb_ib_stencil(int dim, int kind, int radius, int64_t n_markers, const float* coords, int ny, int nz,
+                   float* weights, int32_t* indices, vsb_stream_t stream);
+/* interpolate: ib/stencil.py:54-78.  grid (C, n_cells) -> out (M, C). */
+int vsb_ib_interpolate(int n_comp, int64_t n_cells, const float* grid, int64_t n_markers, int n_stencil,
+                       const float* weights, const int32_t* indices, float* out, vsb_stream_t stream);
+/* spread: ib/stencil.py:81-110.  grid (C, n_cells) += scatter of values (M, C); atomics. */
+int vsb_ib_spread(int n_comp, int64_t n_cells, float* grid, int64_t n_markers, int n_stencil,
+                  const float* values, const float* weights, const int32_t* indices, vsb_stream_t stream);
+
+/* multi_direct_forcing with the stencil computed on the fly (ib/mdf.py:10-64 + ib/stencil.py:27-51 /
+ * ib3d/stencil.py:36-57), marker-parallel, on a window of the grid.
+ *   u_win         (dim, wnx, wny[, wnz]) velocity on the window (read)
+ *   g_win         same shape, ZEROED by the caller; receives spread(total marker force)
+ *   scratch       (max(n_iter-1,0), dim, window) ZEROED by the caller
+ *   markers0      (M, dim) marker coordinates; the body state adds its displacement
+ *   u_target      (M, dim) or NULL -> every marker targets the body velocity (body != NULL) or 0
+ *   ds            (M) when ds_ptr != NULL else the scalar ds_value
+ *   marker_u, marker_force (M, dim) work / output arrays (marker_force = +F; reaction = -F)
+ *   body          device VsbBodyState or NULL (fixed body at markers0, window origin = origin0)
+ * Launches n_iter kernels on `stream`. */
+typedef struct {
+  float d[3], v[3], a[3]; /* displacement, velocity, acceleration of the rigid body         */
+  float h[3];             /* last total hydrodynamic force on the body (sum of -F + added mass) */
+  float force_sum[3];     /* accumulator: sum over markers of +F (reset by the last MDF kernel's consumer) */
+  int origin[3];          /* current integer origin of the IB window (written by vsb_ib_window_moments) */
+} VsbBodyState;
+
+typedef struct {
+  int dim, delta_kind, n_iter, follow; /* follow: 0 fixed window, 1 trunc(origin0 + d) (2-D VIV example),
+                                          2 clip(floor(origin0 + d)) (3-D oscillating cylinder example) */
+  int64_t n_markers;
+  int win_origin0[3], win_size[3];     /* x, y, z order; unused trailing entries ignored for dim 2 */
+  int grid_size[3];
+  const float* markers0;
+  const float* u_target;
+  const float* ds_ptr;
+  float ds_value;
+  float* u_win;
+  float* g_win;
+  float* scratch;
+  float* marker_u;
+  float* marker_force;
+  VsbBodyState* body;
+} VsbMdfArgs;
+
+int vsb_ib_mdf(const VsbMdfArgs* args, vsb_stream_t stream);
+
+/* ---- fused time step ------------------------------------------------------------------- *
+ * State convention: `f_in` / `f_out` hold the POST-COLLISION populations S_n = collide(F_n),
+ * where F_n is the reference's carried state (post-streaming, post-boundary).  One call does
+ *     S_{n+1} = collide( post_ops( stream(S_n) ) )
+ * in one pass over the grid (pull streaming + moments + collision + forcing), followed, when
+ * post_ops is non-empty, by an ordered in-place fix-up of the wall lines.  With do_stream = 0
+ * the call is the prologue S_0 = collide(F_0); with do_collide = 0 it is the epilogue
+ * F_n = post_ops(stream(S_{n-1})).  (SURVEY.md 7 hard-part 1.)                              */
+typedef struct {
+  VsbGrid grid;          /* LOCAL array extent (including ghost layers when decomposed)       */
+  int collision;         /* VSB_COLL_*                                                        */
+  int forcing;           /* VSB_FORCE_*                                                       */
+  double omega;
+  const float* mrt_op_host;   /* Q*Q HOST, VSB_COLL_MRT                                        */
+  const float* mrt_fop_host;  /* Q*Q HOST, VSB_COLL_MRT + VSB_FORCE_GUO                        */
+  int do_stream, do_collide;
+  int row_begin, row_end;     /* range of the slowest axis (x) to update; row_end = 0 -> whole extent */
+  const float* f_in;
+  float* f_out;
+  float g_uniform[3];         /* uniform body force added everywhere                           */
+  const float* g_win;         /* optional force field on a window (dim, wnx, wny[, wnz])       */
+  int win_origin[3], win_size[3];
+  const VsbBodyState* body;   /* optional: window origin is read from body->origin             */
+  int n_post;
+  const VsbPostOp* post;      /* HOST array of ordered post-streaming operations (at most one
+                                 VSB_POST_MASK; it is also applied to interior cells in the fused pass) */
+  int vec;                    /* cells per thread along the contiguous axis: 0 = auto, 1, 2, 4 */
+} VsbStepArgs;
+
+int vsb_step(const VsbStepArgs* args, vsb_stream_t stream);
+
+/* Velocity of the streamed state on the IB window: u_win <- u(stream(f_in)) (feeds vsb_ib_mdf).  Uses grid, f_in,
+ * do_stream, win_size and the mask of `args`.  The window origin is win_origin0 (follow 0), trunc(win_origin0 + body->d)
+ * (follow 1) or clip(floor(win_origin0 + body->d)) (follow 2); it is written to body->origin when body != NULL.
+ * The window must not contain cells of a face that carries a boundary operation. */
+int vsb_ib_window_moments(const VsbStepArgs* args, int follow, const float win_origin0[3], float* u_win,
+                          VsbBodyState* body, vsb_stream_t stream);
+
+/* Device-resident Newmark-beta step for a translating rigid body (reference dyn.py:5-51,126-136 and the
+ * coupling of examples/2d/vortex_induced_vibration.py:135-137): h = -force_sum + a*added_mass;
+ * (a,v,d) <- newmark(a,v,d,h,m,k,c); force_sum <- 0.  n_dof = 2 or 3 translation components. */
+int vsb_body_newmark(VsbBodyState* body, int n_dof, double m, double k, double c, double added_mass,
+                     vsb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIVSIM_B200_H */

@@ -1,0 +1,97 @@
+"""CPU: the C-ABI library builds for sm_100a, loads, and exports every symbol include/vivsim_b200.h
+declares; host-side validation fails loudly (no CPU fallback)."""
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+HEADER = os.path.join(ROOT, "include", "vivsim_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from vivsim_b200 import _build, _lib
+    _build.build()
+    return _lib.lib()
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    return sorted(set(re.findall(r"^(?:int|const char\*)\s+(vsb_\w+)\s*\(", src, flags=re.M)))
+
+
+def test_header_symbols_exported(lib):
+    names = declared_symbols()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    from vivsim_b200 import _lib
+    assert sorted(_lib.EXPORTS) == names, "ctypes binding and header disagree"
+    assert lib.vsb_abi_version() == 1
+
+
+def test_struct_layouts_match_header(lib):
+    from vivsim_b200 import _lib
+    assert ctypes.sizeof(_lib.VsbBodyState) == 72
+    assert ctypes.sizeof(_lib.VsbGrid) == 16
+    assert ctypes.sizeof(_lib.VsbWallValue) == 16
+
+
+def test_validation_errors_without_gpu(lib):
+    from vivsim_b200 import _lib
+    g = _lib.VsbGrid(5, 4, 4, 1)
+    rc = lib.vsb_streaming(ctypes.byref(g), ctypes.c_void_p(16), ctypes.c_void_p(32), None)
+    assert rc == -1 and b"dim must be 2" in lib.vsb_last_error()
+    rc = lib.vsb_collision(2, ctypes.c_int64(4), 1, ctypes.c_double(1.0), None, ctypes.c_void_p(16), ctypes.c_void_p(16),
+                           ctypes.c_void_p(32), None)
+    assert rc == -1 and b"MRT needs op_host" in lib.vsb_last_error()
+
+
+def test_python_api_rejects_cpu_tensors(lib):
+    from vivsim_b200 import VsbError, lbm
+    with pytest.raises(VsbError):
+        lbm.streaming(torch.zeros(9, 4, 4))
+    with pytest.raises(TypeError):
+        lbm.streaming(np.zeros((9, 4, 4), dtype=np.float32))
+
+
+def test_mrt_operators_match_reference(lib, golden):
+    from vivsim_b200 import lbm, lbm3d
+    from vivsim_b200 import _api
+    from conftest import assert_close
+    g = golden["lattice"]
+    assert np.array_equal(_api._basis(2), g["d2q9_M"])
+    assert np.array_equal(_api._basis(3), g["d3q19_M"])
+    for om in (0.8, 1.7):
+        assert_close(lbm.get_mrt_collision_operator(om), g[f"d2q9_mrt_op_{om}"])
+        assert_close(lbm.get_mrt_forcing_operator(om), g[f"d2q9_mrt_fop_{om}"])
+        assert_close(lbm3d.get_mrt_collision_operator(om), g[f"d3q19_mrt_op_{om}"])
+        assert_close(lbm3d.get_mrt_forcing_operator(om), g[f"d3q19_mrt_fop_{om}"])
+
+
+def test_host_dyn_and_geometry(golden):
+    from vivsim_b200 import dyn, ib, ib3d
+    from conftest import assert_close
+    g = golden["dyn"]
+    for got, key in zip(dyn.newmark_2dof(g["a"], g["v"], g["d"], g["h"], 31.4, 0.8, 0.05), ("a", "v", "d")):
+        assert_close(got, g[f"nm_scalar_{key}"])
+    for got, key in zip(dyn.newmark(g["a"], g["v"], g["d"], g["h"], g["m"], g["k"], g["c"]), ("a", "v", "d")):
+        assert_close(got, g[f"nm_matrix_{key}"])
+    xm, ym = dyn.get_markers_coords_3dof(g["x0"], g["y0"], 6.0, 1.0, g["d3"])
+    assert_close(xm, g["c3x"]); assert_close(ym, g["c3y"])
+    assert_close(dyn.get_markers_velocity_3dof(xm, ym, 6.0, 1.0, g["d3"], g["v3"]), g["v3m"])
+    assert_close(dyn.get_force_to_obj(g["hm"]), g["force"])
+    assert_close(dyn.get_torque_to_obj(xm, ym, 6.0, 1.0, g["d3"], g["hm"]), g["torque"])
+    gi = golden["ib"]
+    coords = np.stack([gi["mx"], gi["my"]], axis=1)
+    assert_close(ib.get_ds(coords), gi["ds2_closed"]); assert_close(ib.get_ds(coords, closed=False), gi["ds2_open"])
+    assert_close(ib.get_area(coords), gi["area2"])
+    assert_close(ib3d.get_ds(gi["verts"], gi["faces"]), gi["ds3"])
+    assert_close(ib3d.get_volume(gi["verts"], gi["faces"]), gi["volume"])
+    assert_close(ib3d.get_surface_area(gi["verts"], gi["faces"]), gi["surf_area"])

@@ -1,0 +1,161 @@
+"""GPU: the fused stepper (vsb_step + IB kernels) against the reference recipes (golden fixtures),
+against the oracle over a 100-step horizon, and size-independent properties at larger sizes."""
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from conftest import assert_bitexact, assert_close
+from oracle import recipes
+
+pytestmark = pytest.mark.gpu
+
+NAMES = ["cavity", "cavity_kbc_topfirst", "poiseuille_bgk_edm", "poiseuille_bgk_guo", "poiseuille_mrt_guo",
+         "poiseuille_kbc_edm", "poiseuille_reg_edm", "cylinder_kbc_edm", "cylinder_c2", "text_mask", "sphere", "mrt3"]
+
+
+def N(x):
+    return x.detach().cpu().numpy()
+
+
+def run_stepper(spec, f0, n, **kw):
+    from vivsim_b200 import Stepper
+    st = Stepper(spec, **kw)
+    st.set_f(f0)
+    st.step(n)
+    return st
+
+
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("vec", [0, 1])
+def test_recipe_matches_reference(golden, name, vec):
+    g = golden["recipes"]
+    spec, f0, n, key = dict(cases.all_fluid_cases(g))[name]
+    st = run_stepper(spec, f0, n, vec=vec)
+    assert_close(N(st.get_f()), g[key], what=name)
+    if name == "cylinder_c2":
+        assert_close(-N(st.marker_force), g["c2_h_last"], what="marker force")
+    if name == "sphere":
+        assert_close(-N(st.marker_force), g["sphere_h_last"], what="marker force")
+
+
+def test_get_f_is_idempotent_and_steps_compose(golden):
+    g = golden["recipes"]
+    spec, f0, n, key = cases.cylinder(g, "kbc_edm")
+    from vivsim_b200 import Stepper
+    st = Stepper(spec).set_f(f0)
+    assert_bitexact(N(st.get_f()), f0, "get_f before stepping")
+    st.step(10); a = N(st.get_f()); b = N(st.get_f())
+    assert_bitexact(a, b, "get_f twice")
+    st.step(n - 10)
+    assert_close(N(st.get_f()), g[key], what="10 + 15 steps")
+    # reloading F_n and continuing equals continuing directly
+    st2 = Stepper(spec).set_f(a); st2.step(n - 10)
+    assert_close(N(st2.get_f()), g[key], what="reload + continue")
+
+
+def test_viv_moving_body_host_and_device(golden):
+    g = golden["recipes"]
+    spec, body, f0, (d, v, a), n = cases.viv(g)
+    from vivsim_b200 import Stepper
+    ref = g["viv_dvah"]
+    for mode in ("host", "device"):
+        bd = dict(body, d0=d, v0=v, a0=a, n_dof=2)
+        st = Stepper(spec, body=bd, dyn_mode=mode, follow=1).set_f(f0)
+        hist = []
+        for _ in range(n):
+            st.step(1)
+            hist.append(np.concatenate(st.body_state()))
+        hist = np.array(hist)
+        assert_close(N(st.get_f()), g["viv_f20"], what=f"viv f ({mode})")
+        for k, nm in enumerate(("d", "v", "a", "h")):
+            assert_close(hist[:, 2 * k:2 * k + 2], ref[:, 2 * k:2 * k + 2], rtol=1e-4, what=f"viv {nm} ({mode})")
+
+
+def test_hundred_step_horizon_vs_oracle():
+    """north_star: agreement within 1e-5 over a 100-step horizon (C2 recipe at reduced size)."""
+    spec = recipes.cylinder2d_spec(nx=96, ny=64, n_marker=64, radius=7.5, u0=0.08, nu=0.02, n_iter=5)
+    f0 = recipes.uniform_init(spec, noise=1e-3, seed=0)
+    f_ref, h_ref = recipes.run(spec, f0, 100)
+    st = run_stepper(spec, f0, 100)
+    assert_close(N(st.get_f()), f_ref, what="C2 100 steps")
+    # marker forces are (U - u_m) 2 ds, a difference of nearly equal numbers: fp32 summation-order noise in u_m
+    # (atomics here, einsum order in the oracle) is amplified, so the 100-step bound on forces is 5e-4 of the
+    # largest force; per-step force parity at 1e-5 is checked against the golden fixtures above
+    assert_close(-N(st.marker_force), h_ref, rtol=5e-4, what="marker forces after 100 steps")
+
+
+def test_hundred_step_horizon_3d_vs_oracle():
+    spec = recipes.sphere3d_spec(nx=40, ny=24, nz=24, diameter=8.0, u0=0.05, re=100.0, n_iter=3, subdivisions=2)
+    f0 = recipes.uniform_init(spec, noise=1e-3, seed=0)
+    f_ref, h_ref = recipes.run(spec, f0, 100)
+    st = run_stepper(spec, f0, 100)
+    assert_close(N(st.get_f()), f_ref, what="C3 100 steps")
+    assert_close(-N(st.marker_force), h_ref, rtol=5e-4, what="marker forces")
+
+
+@pytest.mark.parametrize("dim,shape", [(2, (64, 256)), (3, (12, 10, 64))])
+def test_vector_paths_bit_identical(dim, shape):
+    """vec = 1 / 2 / 4 only change how data moves, so results must be bit-identical;
+    a pure periodic streaming step through the fused kernel must equal the permutation."""
+    from vivsim_b200 import Stepper
+    import oracle.lbm, oracle.lbm3d
+    o = oracle.lbm if dim == 2 else oracle.lbm3d
+    spec = dict(dim=dim, shape=shape, collision="kbc", omega=1.7, forcing="edm", g=(1e-4,) * dim, post=[])
+    rng = np.random.default_rng(1)
+    u = (0.05 * rng.standard_normal((dim,) + shape)).astype(np.float32)
+    f0 = o.get_equilibrium(np.ones(shape, np.float32), u)
+    outs = []
+    for vec in (1, 2, 4):
+        st = Stepper(spec, vec=vec).set_f(f0); st.step(7)
+        outs.append(N(st.get_f()))
+    assert_bitexact(outs[1], outs[0], "vec2 vs vec1"); assert_bitexact(outs[2], outs[0], "vec4 vs vec1")
+    # epilogue alone = streaming permutation
+    st = Stepper(spec, vec=4).set_f(f0); st._kind = "S"
+    assert_bitexact(N(st.get_f()), o.streaming(f0), "fused pull == streaming permutation")
+
+
+def test_cuda_graph_matches_eager():
+    from vivsim_b200 import Stepper
+    spec = recipes.cylinder2d_spec(nx=128, ny=96, n_marker=96, radius=10.0, u0=0.08, nu=0.02, n_iter=5)
+    f0 = recipes.uniform_init(spec, noise=1e-3, seed=3)
+    a = Stepper(spec).set_f(f0); a.step(25)
+    b = Stepper(spec, use_graph=True).set_f(f0); b.step(12); b.step(13)
+    assert_close(N(b.get_f()), N(a.get_f()), rtol=1e-6, what="graph vs eager")
+
+
+def test_full_size_properties_c2():
+    """BASELINE config 1 at full size (1024^2, 512 markers): conservation-type properties that do not
+    need the oracle: mass change only through the open boundaries stays tiny, reaction force equals minus
+    the spread force, and the state stays finite."""
+    from vivsim_b200 import Stepper
+    spec = recipes.cylinder2d_spec()
+    f0 = torch.as_tensor(recipes.uniform_init(spec), device="cuda")
+    st = Stepper(spec, use_graph=True).set_f(f0)
+    st.step(50)
+    f = st.get_f()
+    assert torch.isfinite(f).all()
+    m0, m1 = float(f0.double().sum()), float(f.double().sum())
+    assert abs(m1 - m0) / m0 < 1e-4
+    g_sum = st._g_win.double().sum(dim=tuple(range(1, 3))).cpu().numpy()
+    f_sum = st.marker_force.double().sum(dim=0).cpu().numpy()
+    assert_close(g_sum, f_sum, rtol=1e-4, what="sum of spread force == sum of marker forces")
+
+
+def test_periodic_conservation_full_size_3d():
+    """D3Q19 at 128^3, periodic, MRT + Guo body force: mass conserved, momentum grows by g per step."""
+    from vivsim_b200 import Stepper
+    import oracle.lbm3d as o
+    shape = (128, 128, 128)
+    gx = 1e-5
+    spec = dict(dim=3, shape=shape, collision="mrt", omega=1.6, forcing="guo", g=(gx, 0.0, 0.0), post=[])
+    f0 = torch.as_tensor(o.get_equilibrium(np.ones(shape, np.float32), np.zeros((3,) + shape, np.float32)), device="cuda")
+    st = Stepper(spec).set_f(f0); st.step(20)
+    f = st.get_f().double()
+    ncell = float(np.prod(shape))
+    assert abs(float(f.sum()) - ncell) / ncell < 1e-6
+    from vivsim_b200 import lbm3d
+    rho, u = lbm3d.get_macroscopic(st.get_f())
+    # MRT leaves the momentum moments untouched (s = 0) and the Guo source adds exactly g per step
+    assert abs(float((rho * u[0]).double().mean()) - 20 * gx) < 0.01 * 20 * gx

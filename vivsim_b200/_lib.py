@@ -1,0 +1,143 @@
+"""ctypes binding of libvivsim_b200.so (the C ABI declared in include/vivsim_b200.h).
+
+There is no fallback: if the library is missing or the inputs are not CUDA tensors the call
+raises.  torch is used only for device memory and streams."""
+
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libvivsim_b200.so")
+
+OK = 0
+COLL = {"bgk": 0, "mrt": 1, "kbc": 2, "reg": 3}
+FORCE = {None: 0, "none": 0, "edm": 1, "guo": 2}
+BC = {"nee": 0, "nebb": 1, "equilibrium": 2, "bounce_back": 3, "specular_reflection": 4, "mask": 5}
+WRAP = {"": 0, "velocity": 1, "pressure": 2, "force_corrected": 3}
+LOC = {"left": 0, "right": 1, "bottom": 2, "top": 3, "back": 4, "front": 5}
+DELTA = {"peskin3": 0, "peskin4": 1, "cosine4": 2, "hat2": 3}
+
+EXPORTS = [
+    "vsb_abi_version", "vsb_last_error", "vsb_streaming", "vsb_macroscopic", "vsb_equilibrium", "vsb_collision",
+    "vsb_guo_forcing_term", "vsb_forcing", "vsb_post_op", "vsb_boundary_characteristic", "vsb_ib_delta",
+    "vsb_ib_stencil", "vsb_ib_interpolate", "vsb_ib_spread", "vsb_ib_mdf", "vsb_step", "vsb_ib_window_moments",
+    "vsb_body_newmark",
+]
+
+
+class VsbGrid(C.Structure):
+    _fields_ = [("dim", C.c_int), ("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int)]
+
+
+class VsbWallValue(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("value", C.c_float)]
+
+
+class VsbPostOp(C.Structure):
+    _fields_ = [("kind", C.c_int), ("wrap", C.c_int), ("loc", C.c_int), ("rho", VsbWallValue),
+                ("u", VsbWallValue * 3), ("g", VsbWallValue * 3), ("mask", C.c_void_p)]
+
+
+class VsbBodyState(C.Structure):
+    _fields_ = [("d", C.c_float * 3), ("v", C.c_float * 3), ("a", C.c_float * 3), ("h", C.c_float * 3),
+                ("force_sum", C.c_float * 3), ("origin", C.c_int * 3)]
+
+
+BODY_FLOATS = 15  # d, v, a, h, force_sum as fp32; then 3 int32 (origin)
+BODY_BYTES = C.sizeof(VsbBodyState)
+
+
+class VsbMdfArgs(C.Structure):
+    _fields_ = [("dim", C.c_int), ("delta_kind", C.c_int), ("n_iter", C.c_int), ("follow", C.c_int),
+                ("n_markers", C.c_int64), ("win_origin0", C.c_int * 3), ("win_size", C.c_int * 3),
+                ("grid_size", C.c_int * 3), ("markers0", C.c_void_p), ("u_target", C.c_void_p),
+                ("ds_ptr", C.c_void_p), ("ds_value", C.c_float), ("u_win", C.c_void_p), ("g_win", C.c_void_p),
+                ("scratch", C.c_void_p), ("marker_u", C.c_void_p), ("marker_force", C.c_void_p),
+                ("body", C.c_void_p)]
+
+
+class VsbStepArgs(C.Structure):
+    _fields_ = [("grid", VsbGrid), ("collision", C.c_int), ("forcing", C.c_int), ("omega", C.c_double),
+                ("mrt_op_host", C.c_void_p), ("mrt_fop_host", C.c_void_p), ("do_stream", C.c_int),
+                ("do_collide", C.c_int), ("row_begin", C.c_int), ("row_end", C.c_int), ("f_in", C.c_void_p),
+                ("f_out", C.c_void_p), ("g_uniform", C.c_float * 3), ("g_win", C.c_void_p),
+                ("win_origin", C.c_int * 3), ("win_size", C.c_int * 3), ("body", C.c_void_p),
+                ("n_post", C.c_int), ("post", C.POINTER(VsbPostOp)), ("vec", C.c_int)]
+
+
+_lib = None
+
+
+class VsbError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise VsbError(f"{LIB_PATH} is missing: run `python -m vivsim_b200._build` (there is no CPU fallback)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.vsb_last_error.restype = C.c_char_p
+        for name in EXPORTS:
+            getattr(_lib, name)  # AttributeError if the ABI and this binding diverge
+    return _lib
+
+
+def check(rc):
+    if rc != OK:
+        raise VsbError(lib().vsb_last_error().decode())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dev(t, dtype=torch.float32, name="tensor"):
+    """Validate a device operand and return it contiguous."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor on a CUDA device, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise VsbError(f"{name}: tensor is on {t.device}; vivsim_b200 has no CPU path")
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def host_matrix(m, q):
+    """Q x Q operator as a contiguous fp32 HOST array (accepts torch / numpy / nested lists)."""
+    if isinstance(m, torch.Tensor):
+        m = m.detach().cpu().numpy()
+    a = np.ascontiguousarray(np.asarray(m, dtype=np.float32))
+    if a.shape != (q, q):
+        raise ValueError(f"expected a ({q}, {q}) matrix, got {a.shape}")
+    return a
+
+
+def grid_of(shape):
+    if len(shape) == 2:
+        return VsbGrid(2, int(shape[0]), int(shape[1]), 1)
+    if len(shape) == 3:
+        return VsbGrid(3, int(shape[0]), int(shape[1]), int(shape[2]))
+    raise ValueError(f"spatial shape must have 2 or 3 dims, got {tuple(shape)}")
+
+
+def wall_value(v, face_shape, keep, name):
+    """Scalar or face-shaped array -> VsbWallValue (reference broadcast_wall_values)."""
+    if isinstance(v, torch.Tensor) and v.ndim > 0:
+        t = dev(v, name=name)
+        if tuple(t.shape) != tuple(face_shape):
+            raise ValueError(f"{name}: expected face shape {tuple(face_shape)}, got {tuple(t.shape)}")
+        keep.append(t)
+        return VsbWallValue(t.data_ptr(), 0.0)
+    if isinstance(v, np.ndarray) and v.ndim > 0:
+        raise TypeError(f"{name}: pass wall arrays as CUDA tensors")
+    return VsbWallValue(None, float(v))

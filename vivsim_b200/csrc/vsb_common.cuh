@@ -1,0 +1,280 @@
+// vivsim_b200 -- shared device code for the IB-LBM hot path (sm_100a).
+//
+// Layout: SoA fp32, C order.  D2Q9 f[q][x][y], D3Q19 f[q][x][y][z]; the
+// last spatial axis is contiguous.  Internally every field is addressed with three
+// array axes (n0, n1, n2), n2 contiguous; 2-D fields use n0 = 1 so that x -> axis 1 and
+// y -> axis 2.  Velocity component d (0..D-1) lives on array axis d + (3 - D).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vivsim_b200.h"
+
+namespace vsb {
+
+// ----------------------------------------------------------------------------- errors
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define VSB_REQUIRE(cond, ...)                    \
+  do {                                            \
+    if (!(cond)) {                                \
+      vsb::set_error(__VA_ARGS__);                \
+      return VSB_ERR_INVALID;                     \
+    }                                             \
+  } while (0)
+
+#define VSB_LAUNCH_CHECK(what)                                         \
+  do {                                                                 \
+    cudaError_t e__ = cudaGetLastError();                              \
+    if (e__ != cudaSuccess) return vsb::cuda_fail(e__, what);          \
+  } while (0)
+
+// ----------------------------------------------------------------------------- lattices
+// Direction numbering and weights: reference vivsim/lbm/lattice.py:43-63 (D2Q9) and
+// vivsim/lbm3d/lattice.py:43-63 (D3Q19).  Velocities are stored on the three array axes.
+template <int DIM> struct Lat;
+
+template <> struct Lat<2> {
+  static constexpr int D = 2, Q = 9, A0 = 1;  // A0: first array axis that carries a velocity component
+  __host__ __device__ static constexpr int c(int q, int a) {
+    constexpr int t[9][3] = {{0, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, -1, 0}, {0, 0, -1},
+                             {0, 1, 1}, {0, -1, 1}, {0, -1, -1}, {0, 1, -1}};
+    return t[q][a];
+  }
+  __host__ __device__ static constexpr float w(int q) { return q == 0 ? 4.0f / 9.0f : (q < 5 ? 1.0f / 9.0f : 1.0f / 36.0f); }
+  __host__ __device__ static constexpr int opp(int q) {
+    constexpr int t[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
+    return t[q];
+  }
+};
+
+template <> struct Lat<3> {
+  static constexpr int D = 3, Q = 19, A0 = 0;
+  __host__ __device__ static constexpr int c(int q, int a) {
+    constexpr int t[19][3] = {{0, 0, 0},  {1, 0, 0},  {-1, 0, 0},  {0, 1, 0},  {0, -1, 0}, {0, 0, 1},  {0, 0, -1},
+                              {1, 1, 0},  {-1, 1, 0}, {1, -1, 0},  {-1, -1, 0}, {1, 0, 1}, {-1, 0, 1}, {1, 0, -1},
+                              {-1, 0, -1}, {0, 1, 1}, {0, -1, 1},  {0, 1, -1},  {0, -1, -1}};
+    return t[q][a];
+  }
+  __host__ __device__ static constexpr float w(int q) { return q == 0 ? 1.0f / 3.0f : (q < 7 ? 1.0f / 18.0f : 1.0f / 36.0f); }
+  __host__ __device__ static constexpr int opp(int q) {
+    constexpr int t[19] = {0, 2, 1, 4, 3, 6, 5, 10, 9, 8, 7, 14, 13, 12, 11, 18, 17, 16, 15};
+    return t[q];
+  }
+};
+
+// Direction whose velocity is c(q) mirrored across the plane normal to `axis`.
+template <int DIM>
+__host__ __device__ constexpr int mirror_dir(int q, int axis) {
+  using L = Lat<DIM>;
+  for (int r = 0; r < L::Q; ++r) {
+    bool same = true;
+    for (int a = 0; a < 3; ++a) same = same && (L::c(r, a) == (a == axis ? -L::c(q, a) : L::c(q, a)));
+    if (same) return r;
+  }
+  return -1;
+}
+
+// ----------------------------------------------------------------------------- per-cell math
+// rho = sum f, u = sum c f / rho            (reference lbm/basic.py:107-110, lbm3d/basic.py:102-105)
+template <int DIM>
+__device__ __forceinline__ void moments(const float (&f)[Lat<DIM>::Q], float& rho, float (&u)[Lat<DIM>::D]) {
+  using L = Lat<DIM>;
+  float r = 0.f;
+#pragma unroll
+  for (int q = 0; q < L::Q; ++q) r += f[q];
+  rho = r;
+#pragma unroll
+  for (int d = 0; d < L::D; ++d) {
+    float pos = 0.f, neg = 0.f;
+#pragma unroll
+    for (int q = 0; q < L::Q; ++q) {
+      if (L::c(q, d + L::A0) > 0) pos += f[q];
+      if (L::c(q, d + L::A0) < 0) neg += f[q];
+    }
+    u[d] = (pos - neg) / r;
+  }
+}
+
+template <int DIM>
+__device__ __forceinline__ float dot_c(int q, const float (&v)[Lat<DIM>::D]) {
+  using L = Lat<DIM>;
+  float s = 0.f;
+#pragma unroll
+  for (int d = 0; d < L::D; ++d) {
+    const int c = L::c(q, d + L::A0);
+    if (c > 0) s += v[d];
+    if (c < 0) s -= v[d];
+  }
+  return s;
+}
+
+// feq_q = rho w_q (1 + 3 c.u + 4.5 (c.u)^2 - 1.5 u.u)   (lbm/basic.py:132-135, lbm3d/basic.py:121-130)
+template <int DIM>
+__device__ __forceinline__ void equilibrium(float rho, const float (&u)[Lat<DIM>::D], float (&feq)[Lat<DIM>::Q]) {
+  using L = Lat<DIM>;
+  float usq = 0.f;
+#pragma unroll
+  for (int d = 0; d < L::D; ++d) usq += u[d] * u[d];
+#pragma unroll
+  for (int q = 0; q < L::Q; ++q) {
+    const float cu = dot_c<DIM>(q, u);
+    feq[q] = rho * L::w(q) * (1.0f + 3.0f * cu + 4.5f * cu * cu - 1.5f * usq);
+  }
+}
+
+// G_q = w_q [3 (c_q - u).g + 9 (c_q.u)(c_q.g)]           (lbm/forcing/guo.py:21-33, lbm3d/forcing/guo.py:13-38)
+template <int DIM>
+__device__ __forceinline__ void guo_term(const float (&g)[Lat<DIM>::D], const float (&u)[Lat<DIM>::D],
+                                         float (&G)[Lat<DIM>::Q]) {
+  using L = Lat<DIM>;
+  float ug = 0.f;
+#pragma unroll
+  for (int d = 0; d < L::D; ++d) ug += u[d] * g[d];
+#pragma unroll
+  for (int q = 0; q < L::Q; ++q) {
+    const float cu = dot_c<DIM>(q, u), cg = dot_c<DIM>(q, g);
+    G[q] = L::w(q) * (3.0f * (cg - ug) + 9.0f * cu * cg);
+  }
+}
+
+// P fneq, P_qr = w_q/(2 cs^4) (c_q c_q - cs^2 I):(c_r c_r)   (lbm/collision/reg.py:23-47, lbm3d/collision/reg.py:10-41)
+template <int DIM>
+__device__ __forceinline__ void second_order_projection(const float (&fneq)[Lat<DIM>::Q], float (&out)[Lat<DIM>::Q]) {
+  using L = Lat<DIM>;
+  float pi[L::D][L::D];
+#pragma unroll
+  for (int a = 0; a < L::D; ++a)
+#pragma unroll
+    for (int b = a; b < L::D; ++b) {
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < L::Q; ++q) {
+        const int cc = L::c(q, a + L::A0) * L::c(q, b + L::A0);
+        if (cc > 0) s += fneq[q];
+        if (cc < 0) s -= fneq[q];
+      }
+      pi[a][b] = s;
+      pi[b][a] = s;
+    }
+  float tr = 0.f;
+#pragma unroll
+  for (int a = 0; a < L::D; ++a) tr += pi[a][a];
+#pragma unroll
+  for (int q = 0; q < L::Q; ++q) {
+    float s = 0.f;
+#pragma unroll
+    for (int a = 0; a < L::D; ++a)
+#pragma unroll
+      for (int b = 0; b < L::D; ++b) {
+        const int cc = L::c(q, a + L::A0) * L::c(q, b + L::A0);
+        if (cc > 0) s += pi[a][b];
+        if (cc < 0) s -= pi[a][b];
+      }
+    out[q] = L::w(q) * 4.5f * (s - tr * (1.0f / 3.0f));
+  }
+}
+
+// Relaxation constants prepared on the host exactly as Python evaluates them
+// (double arithmetic on the scalar, one rounding to fp32).
+struct Relax {
+  float omega, one_minus_omega, inv_omega, one_minus_inv_omega, guo_scale;
+};
+
+inline Relax make_relax(double omega) {
+  Relax r;
+  r.omega = (float)omega;
+  r.one_minus_omega = (float)(1.0 - omega);
+  r.inv_omega = (float)(1.0 / omega);
+  r.one_minus_inv_omega = (float)(1.0 - 1.0 / omega);
+  r.guo_scale = (float)(1.0 - 0.5 * omega);
+  return r;
+}
+
+template <int Q> struct Matrix { float a[Q * Q]; };
+
+// (1 - omega) f + omega feq                               (lbm/basic.py:156)
+template <int DIM>
+__device__ __forceinline__ void collide_bgk(float (&f)[Lat<DIM>::Q], const float (&feq)[Lat<DIM>::Q], const Relax& r) {
+#pragma unroll
+  for (int q = 0; q < Lat<DIM>::Q; ++q) f[q] = r.one_minus_omega * f[q] + r.omega * feq[q];
+}
+
+// feq + (1 - omega) P (f - feq)                           (lbm/collision/reg.py:49, lbm3d/collision/reg.py:60-62)
+template <int DIM>
+__device__ __forceinline__ void collide_reg(float (&f)[Lat<DIM>::Q], const float (&feq)[Lat<DIM>::Q], const Relax& r) {
+  constexpr int Q = Lat<DIM>::Q;
+  float fneq[Q], pr[Q];
+#pragma unroll
+  for (int q = 0; q < Q; ++q) fneq[q] = f[q] - feq[q];
+  second_order_projection<DIM>(fneq, pr);
+#pragma unroll
+  for (int q = 0; q < Q; ++q) f[q] = feq[q] + r.one_minus_omega * pr[q];
+}
+
+// Entropic KBC.  2-D: shear part from N = Pxx - Pyy and Pxy only (lbm/collision/kbc.py:37-44);
+// 3-D: shear part = full second-order projection (lbm3d/collision/kbc.py:29-31).  Mixing: kbc.py:47-59 / :32-42.
+template <int DIM>
+__device__ __forceinline__ void collide_kbc(float (&f)[Lat<DIM>::Q], const float (&feq)[Lat<DIM>::Q], const Relax& r) {
+  constexpr int Q = Lat<DIM>::Q;
+  float fneq[Q], sh[Q];
+#pragma unroll
+  for (int q = 0; q < Q; ++q) fneq[q] = f[q] - feq[q];
+  if constexpr (DIM == 2) {
+    const float n4 = (fneq[1] - fneq[2] + fneq[3] - fneq[4]) * 0.25f;
+    const float p4 = (fneq[5] - fneq[6] + fneq[7] - fneq[8]) * 0.25f;
+    sh[0] = 0.f;
+    sh[1] = n4; sh[2] = -n4; sh[3] = n4; sh[4] = -n4;
+    sh[5] = p4; sh[6] = -p4; sh[7] = p4; sh[8] = -p4;
+  } else {
+    second_order_projection<DIM>(fneq, sh);
+  }
+  float s_sh = 0.f, s_hh = 0.f;
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    const float hi = fneq[q] - sh[q];
+    const float inv = 1.0f / (feq[q] + 1e-20f);
+    s_sh += hi * sh[q] * inv;
+    s_hh += hi * hi * inv;
+  }
+  const float half_gamma = r.inv_omega - r.one_minus_inv_omega * s_sh / (s_hh + 1e-20f);
+#pragma unroll
+  for (int q = 0; q < Q; ++q) f[q] -= r.omega * (sh[q] + half_gamma * (fneq[q] - sh[q]));
+}
+
+// f + A (feq - f), A given                               (lbm/collision/mrt.py:88, lbm3d/collision/mrt.py:96-98)
+template <int DIM>
+__device__ __forceinline__ void collide_mrt(float (&f)[Lat<DIM>::Q], const float (&feq)[Lat<DIM>::Q],
+                                            const Matrix<Lat<DIM>::Q>& A) {
+  constexpr int Q = Lat<DIM>::Q;
+  float d[Q];
+#pragma unroll
+  for (int q = 0; q < Q; ++q) d[q] = feq[q] - f[q];
+#pragma unroll
+  for (int i = 0; i < Q; ++i) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < Q; ++j) s = fmaf(A.a[i * Q + j], d[j], s);
+    f[i] += s;
+  }
+}
+
+template <int DIM>
+__device__ __forceinline__ void matvec_add(float (&f)[Lat<DIM>::Q], const Matrix<Lat<DIM>::Q>& B,
+                                           const float (&G)[Lat<DIM>::Q]) {
+  constexpr int Q = Lat<DIM>::Q;
+#pragma unroll
+  for (int i = 0; i < Q; ++i) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < Q; ++j) s = fmaf(B.a[i * Q + j], G[j], s);
+    f[i] += s;
+  }
+}
+
+// ----------------------------------------------------------------------------- launch helpers
+inline unsigned blocks_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
+
+}  // namespace vsb

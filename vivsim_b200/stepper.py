@@ -1,0 +1,361 @@
+"""Fused IB-LBM time stepper: the hot path.
+
+The reference composes a step from separately-jitted functions (e.g.
+examples/2d/vortex_induced_vibration.py:96-148):
+
+    moments -> equilibrium -> collision -> [IB: window, stencil, multi-direct forcing, (Newmark)]
+            -> forcing -> streaming -> boundary conditions (in order) -> obstacle mask
+
+``Stepper`` takes a declarative description of that recipe (``spec``) and advances it with one
+fused pull-stream + moments + collision + forcing kernel per step (vsb_step), marker-parallel IB
+kernels (vsb_ib_window_moments, vsb_ib_mdf) and an ordered wall-layer fix-up.
+
+State convention (hard part 1).  The reference carries F_n (after streaming and
+boundary conditions).  Internally the stepper carries S_n = collide(F_n), so each step is a pure
+pull: S_{n+1} = collide(post(stream(S_n))).  ``set_f`` / ``get_f`` convert at the ends, so users
+only ever see the reference's F.
+
+spec keys (same dict the CPU oracle's ``oracle.recipes`` accepts)
+    dim 2|3, shape, collision "bgk"|"mrt"|"kbc"|"reg", omega, forcing None|"edm"|"guo",
+    g None | (gx, gy[, gz]) uniform | tensor (dim, *shape), mrt_op / mrt_fop optional Q x Q matrices,
+    ib None | dict(markers (M, dim), ds scalar|(M,), kernel, n_iter, u_target None|(M, dim), window (origin, size)),
+    post ordered list of (name, loc, kwargs) / ("mask", mask)
+"""
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _api, _lib as L, dyn as _dyn
+
+_WRAPS = ("velocity", "pressure", "force_corrected")
+
+
+def _parse_bc(name):
+    for w in _WRAPS:
+        if name.startswith(w + "_"):
+            return name[len(w) + 1:], w
+    return name, ""
+
+
+class Stepper:
+    def __init__(self, spec, device="cuda", rows=None, vec=0, body=None, dyn_mode="host", follow=1, use_graph=False):
+        """rows: (begin, end) range of the slowest axis that is physical domain (ghost layers outside; slab
+        decomposition).  body: dict(m, k, c, added_mass, n_dof=2, d0, v0, a0) for a moving rigid body coupled by
+        Newmark-beta; dyn_mode "host" (reference-faithful, one tiny D2H/H2D per step) or "device"
+        (vsb_body_newmark, graph-capturable).  follow: IB window rule for a moving body (1 trunc, 2 clip(floor))."""
+        L.lib()
+        if not torch.cuda.is_available():
+            raise L.VsbError("vivsim_b200.Stepper needs a CUDA device (there is no CPU fallback)")
+        self.device = torch.device(device)
+        self.spec = spec
+        self.dim = int(spec["dim"])
+        self.shape = tuple(int(n) for n in spec["shape"])
+        if self.dim not in (2, 3) or len(self.shape) != self.dim:
+            raise ValueError("spec['dim'] must be 2 or 3 and match len(spec['shape'])")
+        self.q = _api.Q[self.dim]
+        self.rows = (0, self.shape[0]) if rows is None else (int(rows[0]), int(rows[1]))
+        self.vec = int(vec)
+        self.use_graph = bool(use_graph)
+        self._keep = []
+        self._bufs = [torch.zeros((self.q,) + self.shape, device=self.device, dtype=torch.float32) for _ in range(2)]
+        self._cur = 0
+        self._kind = None          # 'F' (reference state) or 'S' (post-collision state)
+        self._tmp = None
+        self._graph = None
+        self.n_launch_per_step = 0
+
+        a = L.VsbStepArgs()
+        a.grid = L.grid_of(self.shape)
+        if spec["collision"] not in L.COLL:
+            raise ValueError(f"unknown collision {spec['collision']!r}")
+        a.collision = L.COLL[spec["collision"]]
+        forcing = spec.get("forcing")
+        if forcing not in L.FORCE:
+            raise ValueError(f"unknown forcing {forcing!r}")
+        a.forcing = L.FORCE[forcing]
+        a.omega = float(spec["omega"])
+        if spec["collision"] == "mrt":
+            op = spec.get("mrt_op")
+            self._op = L.host_matrix(op if op is not None else _api.mrt_operator(self.dim, a.omega), self.q)
+            a.mrt_op_host = self._op.ctypes.data
+            if forcing == "guo":
+                fop = spec.get("mrt_fop")
+                self._fop = L.host_matrix(fop if fop is not None else _api.mrt_operator(self.dim, a.omega, True), self.q)
+                a.mrt_fop_host = self._fop.ctypes.data
+        a.row_begin, a.row_end = self.rows
+        a.vec = self.vec
+
+        g = spec.get("g")
+        self._g_field = None
+        if g is not None and a.forcing:
+            if isinstance(g, torch.Tensor) and g.ndim == self.dim + 1:
+                self._g_field = L.dev(g, name="g")
+            else:
+                gv = [float(x) for x in np.asarray(g, dtype=np.float64).reshape(-1)]
+                if len(gv) != self.dim:
+                    raise ValueError("uniform g needs one value per dimension")
+                for d in range(self.dim):
+                    a.g_uniform[d] = gv[d]
+
+        # ---- immersed boundary
+        self.ib = spec.get("ib")
+        self.body = None
+        self._body_dev = None
+        if self.ib is not None:
+            if not a.forcing:
+                raise ValueError("an immersed boundary needs forcing='edm' or 'guo'")
+            if self._g_field is not None:
+                raise ValueError("a full force field and an IB window cannot be combined; add the field as uniform g")
+            self._init_ib(a, body, dyn_mode, follow)
+        elif self._g_field is not None:
+            a.g_win = self._g_field.data_ptr()
+            for d in range(self.dim):
+                a.win_origin[d] = 0
+                a.win_size[d] = self.shape[d]
+
+        # ---- ordered post-streaming operations
+        ops = []
+        for item in spec.get("post", ()):
+            if item[0] == "mask":
+                m = item[1]
+                m = torch.as_tensor(np.asarray(m), device=self.device) if not isinstance(m, torch.Tensor) else m.to(self.device)
+                op, _ = _api.make_post_op(self.dim, self.shape, "mask", keep=self._keep, mask=m)
+            else:
+                kind, wrap = _parse_bc(item[0])
+                kw = dict(item[2]) if len(item) > 2 else {}
+                for k_, v_ in list(kw.items()):
+                    if isinstance(v_, np.ndarray) and v_.ndim > 0:
+                        kw[k_] = torch.as_tensor(v_, device=self.device, dtype=torch.float32)
+                op, _ = _api.make_post_op(self.dim, self.shape, kind, item[1], wrap, keep=self._keep, **kw)
+                self._check_window_clear_of(item[1])
+            ops.append(op)
+        self._post = (L.VsbPostOp * max(len(ops), 1))(*ops)
+        a.n_post = len(ops)
+        a.post = self._post
+        self._args = a
+        self.n_launch_per_step = self._count_launches()
+
+    # ------------------------------------------------------------------ setup helpers
+    def _init_ib(self, a, body, dyn_mode, follow):
+        ib, dim, dev = self.ib, self.dim, self.device
+        markers = np.asarray(ib["markers"], dtype=np.float32)
+        if markers.ndim != 2 or markers.shape[1] != dim:
+            raise ValueError(f"ib['markers'] must have shape (M, {dim})")
+        origin, size = ib["window"]
+        self.win_origin0 = tuple(float(o) for o in origin)
+        self.win_size = tuple(int(n) for n in size)
+        for d in range(dim):
+            lo, n = int(np.floor(self.win_origin0[d])), self.win_size[d]
+            if n < 4 or lo < 0 or lo + n > self.shape[d]:
+                raise ValueError(f"IB window axis {d}: [{lo}, {lo + n}) must lie inside the grid [0, {self.shape[d]})")
+        if body is None:
+            rel = markers - np.floor(np.asarray(self.win_origin0, dtype=np.float32))
+            if (np.floor(rel).min(axis=0) < 1).any() or (np.floor(rel).max(axis=0) + 2 >= np.asarray(self.win_size)).any():
+                raise ValueError("every marker's 4-point stencil must lie inside the IB window (the reference leaves "
+                                 "out-of-range stencil indices undefined)")
+        self.n_markers = markers.shape[0]
+        self.n_iter = int(ib.get("n_iter", 5))
+        wshape = (dim,) + self.win_size
+        self._markers = torch.as_tensor(markers, device=dev)
+        self._u_win = torch.zeros(wshape, device=dev)
+        # g_win and the per-iteration scratch buffers live in one allocation so a single memset clears them
+        self._ib_zero = torch.zeros((self.n_iter,) + wshape, device=dev)
+        self._g_win = self._ib_zero[0]
+        self._marker_u = torch.zeros((self.n_markers, dim), device=dev)
+        self.marker_force = torch.zeros((self.n_markers, dim), device=dev)   # +F; reaction on the body is -F
+        tgt = ib.get("u_target")
+        self._u_target = None if tgt is None else torch.as_tensor(np.asarray(tgt, dtype=np.float32), device=dev)
+        ds = ib["ds"]
+        self._ds = None
+        m = L.VsbMdfArgs()
+        m.dim, m.delta_kind, m.n_iter = dim, L.DELTA[ib.get("kernel", "peskin4")], self.n_iter
+        m.n_markers = self.n_markers
+        if np.ndim(ds) > 0:
+            self._ds = torch.as_tensor(np.asarray(ds, dtype=np.float32), device=dev)
+            if self._ds.shape != (self.n_markers,):
+                raise ValueError("ib['ds'] must be a scalar or have shape (M,)")
+            m.ds_ptr = self._ds.data_ptr()
+        else:
+            m.ds_value = float(ds)
+        for d in range(dim):
+            m.win_origin0[d] = int(np.floor(self.win_origin0[d]))
+            m.win_size[d] = self.win_size[d]
+            m.grid_size[d] = self.shape[d]
+            a.win_origin[d] = m.win_origin0[d]
+            a.win_size[d] = self.win_size[d]
+        m.markers0 = self._markers.data_ptr()
+        m.u_target = self._u_target.data_ptr() if self._u_target is not None else None
+        m.u_win = self._u_win.data_ptr()
+        m.g_win = self._g_win.data_ptr()
+        m.scratch = self._ib_zero[1].data_ptr() if self.n_iter > 1 else None
+        m.marker_u = self._marker_u.data_ptr()
+        m.marker_force = self.marker_force.data_ptr()
+        a.g_win = self._g_win.data_ptr()
+        self.follow = 0
+        if body is not None:
+            self.body = dict(body)
+            self.dyn_mode = dyn_mode
+            if dyn_mode not in ("host", "device"):
+                raise ValueError("dyn_mode must be 'host' or 'device'")
+            self.follow = int(follow)
+            self.n_dof = int(body.get("n_dof", 2))
+            self._body_dev = torch.zeros(L.BODY_BYTES // 4, device=dev, dtype=torch.float32)
+            self._body_pin = torch.zeros(L.BODY_BYTES // 4, dtype=torch.float32).pin_memory()
+            st = self._body_pin.numpy()
+            st[0:self.n_dof] = np.asarray(body.get("d0", np.zeros(self.n_dof)), dtype=np.float32)
+            st[3:3 + self.n_dof] = np.asarray(body.get("v0", np.zeros(self.n_dof)), dtype=np.float32)
+            st[6:6 + self.n_dof] = np.asarray(body.get("a0", np.zeros(self.n_dof)), dtype=np.float32)
+            self._body_dev.copy_(self._body_pin, non_blocking=True)
+            m.body = self._body_dev.data_ptr()
+            m.follow = self.follow
+            a.body = self._body_dev.data_ptr()
+        self._mdf = m
+        self._origin0_c = (C.c_float * 3)(*(list(self.win_origin0) + [0.0] * (3 - dim)))
+
+    def _check_window_clear_of(self, loc):
+        if self.ib is None:
+            return
+        axis, low = L.LOC[loc] // 2, L.LOC[loc] % 2 == 0
+        lo = int(np.floor(self.win_origin0[axis]))
+        hi = lo + self.win_size[axis]
+        rb, re = (self.rows if axis == 0 else (0, self.shape[axis]))
+        if (low and lo <= rb) or (not low and hi >= re):
+            raise ValueError(f"the IB window touches the '{loc}' wall layer, which carries a boundary operation")
+
+    def _count_launches(self):
+        n = 1
+        if self._args.n_post:
+            n_bc = sum(1 for i in range(self._args.n_post) if self._post[i].kind != L.BC["mask"])
+            if n_bc:
+                n += 2 + self._args.n_post
+        if self.ib is not None:
+            n += 1 + self.n_iter + (1 if self.body is not None and self.dyn_mode == "device" else 0)
+        return n
+
+    # ------------------------------------------------------------------ state access
+    def set_f(self, f):
+        """Load the reference-convention state F (post-streaming, post-boundary populations)."""
+        f = torch.as_tensor(np.asarray(f), device=self.device) if not isinstance(f, torch.Tensor) else f.to(self.device)
+        if tuple(f.shape) != (self.q,) + self.shape:
+            raise ValueError(f"f must have shape {(self.q,) + self.shape}, got {tuple(f.shape)}")
+        self._bufs[self._cur].copy_(f.to(torch.float32))
+        self._kind = "F"
+        return self
+
+    def get_f(self):
+        """Return F_n, the state the reference carries after n steps (a new tensor)."""
+        self._require_state()
+        if self._kind == "F":
+            return self._bufs[self._cur].clone()
+        out = torch.empty_like(self._bufs[0])
+        self._launch(self._bufs[self._cur], out, do_stream=1, do_collide=0)
+        return out
+
+    @property
+    def state(self):
+        """The internal buffer (S_n after the first step, F_0 before).  For halo exchange and tests."""
+        return self._bufs[self._cur]
+
+    def body_state(self):
+        """(d, v, a, h) of the rigid body as NumPy arrays (synchronises)."""
+        st = self._body_dev.cpu().numpy()
+        n = self.n_dof
+        return st[0:n].copy(), st[3:3 + n].copy(), st[6:6 + n].copy(), st[9:9 + n].copy()
+
+    def _require_state(self):
+        if self._kind is None:
+            raise L.VsbError("no state loaded: call set_f(f) first")
+
+    # ------------------------------------------------------------------ stepping
+    def _launch(self, src, dst, do_stream, do_collide):
+        a = self._args
+        a.f_in, a.f_out = src.data_ptr(), dst.data_ptr()
+        a.do_stream, a.do_collide = do_stream, do_collide
+        lib, st = L.lib(), L.stream()
+        if self.ib is not None and do_collide:
+            self._ib_zero.zero_()
+            L.check(lib.vsb_ib_window_moments(C.byref(a), self.follow, self._origin0_c, L.ptr(self._u_win),
+                                              C.c_void_p(self._body_dev.data_ptr()) if self._body_dev is not None else None,
+                                              st))
+            L.check(lib.vsb_ib_mdf(C.byref(self._mdf), st))
+            if self.body is not None:
+                self._newmark(st)
+        L.check(lib.vsb_step(C.byref(a), st))
+
+    def _newmark(self, st):
+        b = self.body
+        if self.dyn_mode == "device":
+            L.check(L.lib().vsb_body_newmark(C.c_void_p(self._body_dev.data_ptr()), self.n_dof, C.c_double(b["m"]),
+                                             C.c_double(b["k"]), C.c_double(b["c"]), C.c_double(b["added_mass"]), st))
+            return
+        # host ODE as in the reference recipe: h = sum(-F) + a * added_mass ; Newmark-beta
+        self._body_pin.copy_(self._body_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        s = self._body_pin.numpy()
+        n = self.n_dof
+        d, v, acc = s[0:n].copy(), s[3:3 + n].copy(), s[6:6 + n].copy()
+        h = (-s[12:12 + n] + acc * np.float32(b["added_mass"])).astype(np.float32)
+        a2, v2, d2 = _dyn.newmark(acc, v, d, h, b["m"], b["k"], b["c"])
+        s[0:n], s[3:3 + n], s[6:6 + n], s[9:9 + n] = d2, v2, a2, h
+        s[12:15] = 0
+        self._body_dev.copy_(self._body_pin, non_blocking=True)
+
+    def _advance(self):
+        src, dst = self._bufs[self._cur], self._bufs[1 - self._cur]
+        self._launch(src, dst, do_stream=1, do_collide=1)
+        self._cur = 1 - self._cur
+
+    def step(self, n=1):
+        """Advance n reference time steps."""
+        self._require_state()
+        n = int(n)
+        if n <= 0:
+            return self
+        if self._kind == "F":   # prologue: S_0 = collide(F_0)
+            src, dst = self._bufs[self._cur], self._bufs[1 - self._cur]
+            self._launch(src, dst, do_stream=0, do_collide=1)
+            self._cur = 1 - self._cur
+            self._kind = "S"
+            n -= 1
+        graphable = self.use_graph and not (self.body is not None and self.dyn_mode == "host")
+        if graphable and n >= 2:
+            if self._graph is None:
+                self._capture()
+            if self._graph_cur != self._cur:   # the graph was recorded starting from the other buffer
+                self._advance()
+                n -= 1
+            while n >= 2:
+                self._graph.replay()
+                n -= 2
+        for _ in range(n):
+            self._advance()
+        return self
+
+    def _capture(self):
+        """Record two consecutive steps (A->B, B->A) in one CUDA graph."""
+        torch.cuda.synchronize()
+        keep = [b.clone() for b in self._bufs]
+        ib_keep = None
+        if self.ib is not None:
+            ib_keep = [t.clone() for t in (self._marker_u, self.marker_force)] + (
+                [self._body_dev.clone()] if self._body_dev is not None else [])
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):   # warm-up outside capture
+            self._advance(); self._advance()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        self._graph_cur = self._cur
+        with torch.cuda.graph(g):
+            self._advance(); self._advance()
+        torch.cuda.synchronize()
+        for b, k in zip(self._bufs, keep):   # capture does not execute, but the warm-up did: restore
+            b.copy_(k)
+        if ib_keep is not None:
+            self._marker_u.copy_(ib_keep[0]); self.marker_force.copy_(ib_keep[1])
+            if self._body_dev is not None:
+                self._body_dev.copy_(ib_keep[2])
+        self._graph = g
