@@ -307,6 +307,15 @@ class Stepper:
         self._launch(src, dst, do_stream=1, do_collide=1)
         self._cur = 1 - self._cur
 
+    def advance_raw(self, n=1):
+        """Enqueue n fused steps on the current stream with no graph handling (for callers that capture
+        their own CUDA graph).  Needs the internal post-collision state, i.e. at least one step() before."""
+        if self._kind != "S":
+            raise L.VsbError("advance_raw needs the internal state: call set_f(f) and step(1) first")
+        for _ in range(int(n)):
+            self._advance()
+        return self
+
     def step(self, n=1):
         """Advance n reference time steps."""
         self._require_state()
