@@ -86,6 +86,7 @@ __device__ __forceinline__ void moments(const float (&f)[Lat<DIM>::Q], float& rh
 #pragma unroll
   for (int q = 0; q < L::Q; ++q) r += f[q];
   rho = r;
+  const float inv = 1.0f / r;   // one IEEE division; u = m * (1/rho) differs from m / rho by at most 1 ulp
 #pragma unroll
   for (int d = 0; d < L::D; ++d) {
     float pos = 0.f, neg = 0.f;
@@ -94,7 +95,7 @@ __device__ __forceinline__ void moments(const float (&f)[Lat<DIM>::Q], float& rh
       if (L::c(q, d + L::A0) > 0) pos += f[q];
       if (L::c(q, d + L::A0) < 0) neg += f[q];
     }
-    u[d] = (pos - neg) / r;
+    u[d] = (pos - neg) * inv;
   }
 }
 
@@ -235,7 +236,7 @@ __device__ __forceinline__ void collide_kbc(float (&f)[Lat<DIM>::Q], const float
 #pragma unroll
   for (int q = 0; q < Q; ++q) {
     const float hi = fneq[q] - sh[q];
-    const float inv = 1.0f / (feq[q] + 1e-20f);
+    const float inv = __fdividef(1.0f, feq[q] + 1e-20f);   // MUFU.RCP, <= 2 ulp
     s_sh += hi * sh[q] * inv;
     s_hh += hi * hi * inv;
   }

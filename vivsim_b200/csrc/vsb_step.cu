@@ -72,30 +72,37 @@ __device__ __forceinline__ int wrap(int i, int n) {
   return i;
 }
 
-// Force on one cell: uniform part + window field.  coord[] are array-axis coordinates.
+// Force window lookup, split so that the part that does not depend on the contiguous coordinate is done once
+// per thread: `base` is the flat window index of (c0, c1, 0) and `rows_inside` tells whether the leading
+// coordinates fall inside the window.
 template <int DIM>
-__device__ __forceinline__ void cell_force(const StepParams<DIM>& p, const int (&worg)[3], int c0, int c1, int c2,
-                                           float (&g)[Lat<DIM>::D]) {
+__device__ __forceinline__ void window_rows(const StepParams<DIM>& p, const int (&worg)[3], int c0, int c1,
+                                            bool& rows_inside, int& base) {
+  using L = Lat<DIM>;
+  rows_inside = p.gwin != nullptr;
+  base = 0;
+  const int coord[3] = {c0, c1, 0};
+#pragma unroll
+  for (int d = 0; d < L::D - 1; ++d) {
+    const int rel = coord[d + L::A0] - worg[d];
+    rows_inside = rows_inside && (unsigned)rel < (unsigned)p.wsz[d];
+    base = (base + rel) * p.wsz[d + 1];
+  }
+}
+
+template <int DIM>
+__device__ __forceinline__ void cell_force(const StepParams<DIM>& p, const int (&worg)[3], bool rows_inside, int base,
+                                           int c2, float (&g)[Lat<DIM>::D]) {
   using L = Lat<DIM>;
 #pragma unroll
   for (int d = 0; d < L::D; ++d) g[d] = p.g0[d];
-  if (p.gwin) {
-    const int coord[3] = {c0, c1, c2};
-    long long widx = 0;
-    bool inside = true;
+  const int rel = c2 - worg[L::D - 1];
+  if (rows_inside && (unsigned)rel < (unsigned)p.wsz[L::D - 1]) {
+    int wcells = 1;
 #pragma unroll
-    for (int d = 0; d < L::D; ++d) {
-      const int rel = coord[d + L::A0] - worg[d];
-      inside = inside && rel >= 0 && rel < p.wsz[d];
-      widx = widx * p.wsz[d] + rel;
-    }
-    if (inside) {
-      long long wcells = 1;
+    for (int d = 0; d < L::D; ++d) wcells *= p.wsz[d];
 #pragma unroll
-      for (int d = 0; d < L::D; ++d) wcells *= p.wsz[d];
-#pragma unroll
-      for (int d = 0; d < L::D; ++d) g[d] += p.gwin[d * wcells + widx];
-    }
+    for (int d = 0; d < L::D; ++d) g[d] += p.gwin[d * wcells + base + rel];
   }
 }
 
@@ -108,6 +115,11 @@ __device__ __forceinline__ void collide_cell(float (&f)[Lat<DIM>::Q], const floa
   using L = Lat<DIM>;
   float rho, u[L::D], feq[L::Q];
   moments<DIM>(f, rho, u);
+  // a zero force contributes exactly nothing (u + 0, f + w*0): skip the work -- bit-identical
+  bool has_g = false;
+#pragma unroll
+  for (int d = 0; d < L::D; ++d) has_g = has_g || (g[d] != 0.f);
+  if (!has_g) forcing = VSB_FORCE_NONE;
   if (forcing == VSB_FORCE_GUO) {
 #pragma unroll
     for (int d = 0; d < L::D; ++d) u[d] += g[d] * 0.5f / rho;
@@ -209,10 +221,13 @@ __global__ void __launch_bounds__(256) k_step(const StepParams<DIM> p, const Mrt
   if (p.do_collide) {
     int worg[3] = {p.worg[0], p.worg[1], p.worg[2]};
     if (p.gwin && p.body) { worg[0] = p.body->origin[0]; worg[1] = p.body->origin[1]; worg[2] = p.body->origin[2]; }
+    bool rows_inside;
+    int wbase;
+    window_rows<DIM>(p, worg, i0, i1, rows_inside, wbase);
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
       float g[L::D];
-      cell_force<DIM>(p, worg, i0, i1, i2 + k, g);
+      cell_force<DIM>(p, worg, rows_inside, wbase, i2 + k, g);
       collide_cell<DIM, COLL>(f[k], g, p.forcing, p.rx, mm);
     }
   }
@@ -295,7 +310,10 @@ __global__ void k_lines_collide(const StepParams<DIM> p, const MrtMats<DIM, COLL
   for (int q = 0; q < L::Q; ++q) f[q] = p.fout[q * ncell + cell];
   int worg[3] = {p.worg[0], p.worg[1], p.worg[2]};
   if (p.gwin && p.body) { worg[0] = p.body->origin[0]; worg[1] = p.body->origin[1]; worg[2] = p.body->origin[2]; }
-  cell_force<DIM>(p, worg, c[0], c[1], c[2], g);
+  bool rows_inside;
+  int wbase;
+  window_rows<DIM>(p, worg, c[0], c[1], rows_inside, wbase);
+  cell_force<DIM>(p, worg, rows_inside, wbase, c[2], g);
   collide_cell<DIM, COLL>(f, g, p.forcing, p.rx, mm);
 #pragma unroll
   for (int q = 0; q < L::Q; ++q) p.fout[q * ncell + cell] = f[q];

@@ -1,0 +1,214 @@
+"""Slab domain decomposition across GPUs with halo exchange over NCCL / NVLink.
+
+Replaces the reference's ``vivsim/multidevice.py`` (``stream_cross_devices``: four ``lax.ppermute`` of
+the three populations that cross each cut, 2-D only, no caller).  Design from the physics:
+
+* the global grid is cut along x, the slowest axis, so the layer ``f[q, x_edge]`` of every population is
+  one contiguous block (NY floats in 2-D, NY*NZ in 3-D): no pack / unpack kernels are needed;
+* every rank stores its slab with one ghost layer on each side, local shape ``(nx_local + 2, NY[, NZ])``,
+  physical rows ``[1, nx_local + 1)``;
+* after each fused step only the populations moving across a cut are exchanged with the two ring
+  neighbours (periodic wrap): ``c_x = +1`` populations go right, ``c_x = -1`` go left -- 3 of 9 in D2Q9,
+  5 of 19 in D3Q19 -- as one batch of NCCL send/recv pairs (``ncclGroupStart/End``);
+* wall boundary operations on the x faces are applied by the rank that owns that face; y / z faces and the
+  obstacle mask are applied by every rank on its rows; an immersed body is owned by the rank whose slab
+  contains its window, and the total IB force is combined with a small all-reduce.
+
+The exchange is written on torch tensors, so the same code runs on CPU tensors over gloo (tests) and on
+CUDA tensors over NCCL (production).  There is no data-path collective besides the neighbour exchange.
+"""
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+RIGHT_MOVING = {2: (1, 5, 8), 3: (1, 7, 9, 11, 13)}   # c_x = +1  (lbm/lattice.py:58, lbm3d/lattice.py:43-58)
+LEFT_MOVING = {2: (3, 7, 6), 3: (2, 8, 10, 12, 14)}   # c_x = -1
+
+
+class Slab:
+    """Geometry of one rank's slab of a global grid cut along x."""
+
+    def __init__(self, global_shape, rank, world):
+        self.global_shape = tuple(int(n) for n in global_shape)
+        self.dim = len(self.global_shape)
+        self.rank, self.world = int(rank), int(world)
+        nx = self.global_shape[0]
+        if nx % self.world:
+            raise ValueError(f"NX = {nx} must be divisible by the number of ranks ({self.world})")
+        self.nx_local = nx // self.world
+        if self.nx_local < 4:
+            raise ValueError("each slab needs at least 4 x-layers")
+        self.x0 = self.rank * self.nx_local                       # global x of local row 1
+        self.local_shape = (self.nx_local + 2,) + self.global_shape[1:]
+        self.rows = (1, self.nx_local + 1)
+        self.left = (self.rank - 1) % self.world
+        self.right = (self.rank + 1) % self.world
+        self.owns_left_wall = self.rank == 0
+        self.owns_right_wall = self.rank == self.world - 1
+
+    def to_local_x(self, x_global):
+        return x_global - self.x0 + 1
+
+    def scatter(self, field_global):
+        """Local slab (with ghost layers filled periodically) of a global array whose axis 1 is x."""
+        nx = self.global_shape[0]
+        idx = (np.arange(self.x0 - 1, self.x0 + self.nx_local + 1)) % nx
+        if isinstance(field_global, torch.Tensor):
+            return field_global.index_select(1, torch.as_tensor(idx, device=field_global.device)).contiguous()
+        return np.ascontiguousarray(np.take(field_global, idx, axis=1))
+
+    def halo_bytes_per_step(self):
+        face = int(np.prod(self.global_shape[1:]))
+        return 2 * len(RIGHT_MOVING[self.dim]) * face * 4
+
+
+def exchange_halo(state, slab, group=None):
+    """Fill the ghost layers of ``state`` (Q, nx_local + 2, ...) from the ring neighbours.
+
+    Row ``nx_local`` (last physical) of the right-moving populations goes to the right neighbour's ghost
+    row 0; row 1 of the left-moving populations goes to the left neighbour's ghost row ``nx_local + 1``.
+    Returns the list of outstanding requests (already waited on for world == 1)."""
+    n = slab.nx_local
+    if slab.world == 1:
+        for q in RIGHT_MOVING[slab.dim]:
+            state[q, 0].copy_(state[q, n])
+        for q in LEFT_MOVING[slab.dim]:
+            state[q, n + 1].copy_(state[q, 1])
+        return []
+    ops = []
+    for q in RIGHT_MOVING[slab.dim]:
+        ops.append(dist.P2POp(dist.isend, state[q, n], slab.right, group))
+        ops.append(dist.P2POp(dist.irecv, state[q, 0], slab.left, group))
+    for q in LEFT_MOVING[slab.dim]:
+        ops.append(dist.P2POp(dist.isend, state[q, 1], slab.left, group))
+        ops.append(dist.P2POp(dist.irecv, state[q, n + 1], slab.right, group))
+    return dist.batch_isend_irecv(ops)
+
+
+def wait_all(reqs):
+    for r in reqs:
+        r.wait()
+
+
+def localize_spec(spec, slab, local_ib=None):
+    """Per-rank step description: local extent with ghost layers, x-face operations only on the owning rank,
+    immersed body (``spec['ib']`` or ``local_ib(slab)``, global coordinates) shifted to local coordinates."""
+    out = dict(spec)
+    out["shape"] = slab.local_shape
+    post = []
+    for item in spec.get("post", ()):
+        if item[0] == "mask":
+            m = item[1]
+            m = m.detach().cpu().numpy() if isinstance(m, torch.Tensor) else np.asarray(m)
+            post.append(("mask", slab.scatter(m[None])[0]))
+            continue
+        loc = item[1]
+        if loc == "left" and not slab.owns_left_wall:
+            continue
+        if loc == "right" and not slab.owns_right_wall:
+            continue
+        kw = dict(item[2]) if len(item) > 2 else {}
+        for k, v in kw.items():
+            if hasattr(v, "ndim") and v.ndim > 0 and loc not in ("left", "right"):
+                arr = v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+                kw[k] = slab.scatter(arr[None])[0]          # face arrays of y / z faces run along x
+        post.append((item[0], loc, kw))
+    out["post"] = post
+    ib = local_ib(slab) if local_ib is not None else spec.get("ib")
+    out["ib"] = None
+    if ib is not None:
+        (ox, *orest), size = ib["window"]
+        lo, hi = int(np.floor(ox)), int(np.floor(ox)) + int(size[0])
+        inside = lo >= slab.x0 + 2 and hi <= slab.x0 + slab.nx_local - 2
+        overlaps = hi > slab.x0 and lo < slab.x0 + slab.nx_local
+        if overlaps and not inside:
+            raise ValueError(f"the IB window x-range [{lo}, {hi}) must lie at least 2 layers inside one slab "
+                             f"(rank {slab.rank} owns [{slab.x0}, {slab.x0 + slab.nx_local})); markers near a cut "
+                             "need a wider exchange that is not implemented")
+        if inside:
+            loc_ib = dict(ib)
+            markers = np.array(ib["markers"], dtype=np.float32, copy=True)
+            markers[:, 0] = markers[:, 0] - np.float32(slab.x0) + np.float32(1)
+            loc_ib["markers"] = markers
+            loc_ib["window"] = ((slab.to_local_x(ox),) + tuple(orest), tuple(size))
+            out["ib"] = loc_ib
+    g = spec.get("g")
+    if isinstance(g, torch.Tensor) and g.ndim == slab.dim + 1:
+        out["g"] = slab.scatter(g)
+    return out
+
+
+class SlabStepper:
+    """One rank's part of a slab-decomposed simulation: a ``Stepper`` on the local extent plus the halo
+    exchange after every step.  Collective: every rank must call ``step`` with the same count."""
+
+    def __init__(self, spec, rank=None, world=None, group=None, local_ib=None, body=None, overlap=True, **kw):
+        from .stepper import Stepper
+        self.group = group
+        if world is None:
+            world = dist.get_world_size(group) if dist.is_initialized() else 1
+            rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.slab = Slab(spec["shape"], rank, world)
+        self.local_spec = localize_spec(spec, self.slab, local_ib)
+        has_body = self.local_spec["ib"] is not None
+        self.stepper = Stepper(self.local_spec, rows=self.slab.rows, body=body if has_body else None, **kw)
+        self.owns_body = has_body
+        self.overlap = bool(overlap)
+        self._comm = torch.cuda.Stream() if self.overlap and self.slab.world > 1 else None
+
+    # -- state in / out (reference convention F)
+    def set_f_global(self, f_global):
+        self.stepper.set_f(self.slab.scatter(f_global))
+        return self
+
+    def set_f_local(self, f_local_with_ghosts):
+        self.stepper.set_f(f_local_with_ghosts)
+        return self
+
+    def get_f_local(self):
+        """Physical rows of F_n on this rank, shape (Q, nx_local, ...)."""
+        return self.stepper.get_f()[:, 1:-1].contiguous()
+
+    def gather_f(self):
+        """Global F_n on every rank (all-gather along x) -- for tests and I/O."""
+        loc = self.get_f_local()
+        if self.slab.world == 1:
+            return loc
+        parts = [torch.empty_like(loc) for _ in range(self.slab.world)]
+        dist.all_gather(parts, loc, group=self.group)
+        return torch.cat(parts, dim=1)
+
+    def total_force(self):
+        """Sum over all bodies / ranks of the hydrodynamic force on the bodies (small all-reduce)."""
+        st = self.stepper
+        dim = st.dim
+        h = (-st.marker_force.sum(dim=0)) if self.owns_body else torch.zeros(dim, device=st.device)
+        if self.slab.world > 1:
+            dist.all_reduce(h, group=self.group)
+        return h
+
+    # -- stepping
+    def _exchange(self):
+        st = self.stepper
+        if self._comm is None:
+            wait_all(exchange_halo(st.state, self.slab, self.group))
+            return
+        # issue the exchange on a side stream so that it only orders against the kernels that produced the
+        # edge layers; the main stream waits for it before the next step reads the ghost layers
+        self._comm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._comm):
+            wait_all(exchange_halo(st.state, self.slab, self.group))
+        torch.cuda.current_stream().wait_stream(self._comm)
+
+    def step(self, n=1):
+        st = self.stepper
+        st._require_state()
+        for _ in range(int(n)):
+            if st._kind == "F":
+                # the F state came with periodic ghost layers (scatter) or the caller filled them
+                st.step(1)          # prologue S_0 = collide(F_0) on the physical rows
+            else:
+                st.advance_raw(1)
+            self._exchange()
+        return self
