@@ -102,6 +102,29 @@ int vsb_ib_interpolate(int n_comp, int64_t n_cells, const float* grid, int64_t n
 int vsb_ib_spread(int n_comp, int64_t n_cells, float* grid, int64_t n_markers, int n_stencil,
                   const float* values, const float* weights, const int32_t* indices, vsb_stream_t stream);
 
+/* ---- rigid body state (device resident) ------------------------------------------------ *
+ * The IB window follows a moving body.  Its integer origin for the step with parity p (0/1, alternating every
+ * step) is origin2[p]; it is produced by the body update of the PREVIOUS step (vsb_body_newmark / vsb_ib_fused,
+ * or the host in host-ODE mode), so that all kernels of one step can run concurrently while the update writes
+ * the other slot. */
+typedef struct {
+  float d[3], v[3], a[3]; /* displacement, velocity, acceleration of the rigid body                       */
+  float h[3];             /* last total hydrodynamic force on the body: sum over markers of -F + a*added_mass */
+  float force_sum[3];     /* accumulator: sum over markers of +F; cleared by the body update             */
+  int origin2[2][3];      /* integer IB-window origin for step parity 0 / 1                               */
+} VsbBodyState;
+
+/* Structural parameters and window rule of a translating rigid body (reference dyn.py:5-51 with gamma = 1/2,
+ * beta = 1/4, dt = 1; coupling of examples/2d/vortex_induced_vibration.py:104-105,135-137). */
+typedef struct {
+  int n_dof;              /* 1..3 translation components; 0 = fixed body (no update)                       */
+  int follow;             /* window rule: 0 fixed, 1 trunc(origin0 + d) (2-D VIV example :104-105),
+                             2 clip(floor(origin0 + d)) (examples/3d/oscillating_cylinder.py:241-243)       */
+  float origin0[3];       /* window origin for d = 0                                                       */
+  int grid_size[3], win_size[3];
+  double m, k, c, added_mass;
+} VsbBodyParams;
+
 /* multi_direct_forcing with the stencil computed on the fly (ib/mdf.py:10-64 + ib/stencil.py:27-51 /
  * ib3d/stencil.py:36-57), marker-parallel, on a window of the grid.
  *   u_win         (dim, wnx, wny[, wnz]) velocity on the window (read)
@@ -111,21 +134,12 @@ int vsb_ib_spread(int n_comp, int64_t n_cells, float* grid, int64_t n_markers, i
  *   u_target      (M, dim) or NULL -> every marker targets the body velocity (body != NULL) or 0
  *   ds            (M) when ds_ptr != NULL else the scalar ds_value
  *   marker_u, marker_force (M, dim) work / output arrays (marker_force = +F; reaction = -F)
- *   body          device VsbBodyState or NULL (fixed body at markers0, window origin = origin0)
+ *   body          device VsbBodyState or NULL (fixed body at markers0, window origin = win_origin0)
  * Launches n_iter kernels on `stream`. */
 typedef struct {
-  float d[3], v[3], a[3]; /* displacement, velocity, acceleration of the rigid body         */
-  float h[3];             /* last total hydrodynamic force on the body (sum of -F + added mass) */
-  float force_sum[3];     /* accumulator: sum over markers of +F (reset by the last MDF kernel's consumer) */
-  int origin[3];          /* current integer origin of the IB window (written by vsb_ib_window_moments) */
-} VsbBodyState;
-
-typedef struct {
-  int dim, delta_kind, n_iter, follow; /* follow: 0 fixed window, 1 trunc(origin0 + d) (2-D VIV example),
-                                          2 clip(floor(origin0 + d)) (3-D oscillating cylinder example) */
+  int dim, delta_kind, n_iter, parity;
   int64_t n_markers;
   int win_origin0[3], win_size[3];     /* x, y, z order; unused trailing entries ignored for dim 2 */
-  int grid_size[3];
   const float* markers0;
   const float* u_target;
   const float* ds_ptr;
@@ -162,27 +176,42 @@ typedef struct {
   float g_uniform[3];         /* uniform body force added everywhere                           */
   const float* g_win;         /* optional force field on a window (dim, wnx, wny[, wnz])       */
   int win_origin[3], win_size[3];
-  const VsbBodyState* body;   /* optional: window origin is read from body->origin             */
+  const VsbBodyState* body;   /* optional: window origin is read from body->origin2[parity]    */
+  int parity;
   int n_post;
   const VsbPostOp* post;      /* HOST array of ordered post-streaming operations (at most one
                                  VSB_POST_MASK; it is also applied to interior cells in the fused pass) */
   int vec;                    /* cells per thread along the contiguous axis: 0 = auto, 1, 2, 4 */
+  int band;                   /* 0: all rows; 1: all rows except the x-range of the force window;
+                                 2: only that x-range (lets the bulk run concurrently with the IB kernels) */
+  int edges;                  /* 0: ordered wall fix-up inside vsb_step; 1: none -- the caller runs
+                                 vsb_edge_fused and the fused pass leaves those wall layers untouched */
 } VsbStepArgs;
 
 int vsb_step(const VsbStepArgs* args, vsb_stream_t stream);
 
-/* Velocity of the streamed state on the IB window: u_win <- u(stream(f_in)) (feeds vsb_ib_mdf).  Uses grid, f_in,
- * do_stream, win_size and the mask of `args`.  The window origin is win_origin0 (follow 0), trunc(win_origin0 + body->d)
- * (follow 1) or clip(floor(win_origin0 + body->d)) (follow 2); it is written to body->origin when body != NULL.
- * The window must not contain cells of a face that carries a boundary operation. */
-int vsb_ib_window_moments(const VsbStepArgs* args, int follow, const float win_origin0[3], float* u_win,
-                          VsbBodyState* body, vsb_stream_t stream);
+/* Wall layers in ONE kernel per face: pull the streamed populations of the wall cell (and of the adjacent fluid
+ * cell when the operation reads it), apply the face operation, collide, store.  Valid when the face operations are
+ * independent of each other: all on faces normal to one non-contiguous axis, at least 3 layers apart.
+ * vsb_edge_fused_supported returns 1 in that case, else 0 (use edges = 0). */
+int vsb_edge_fused_supported(const VsbStepArgs* args);
+int vsb_edge_fused(const VsbStepArgs* args, vsb_stream_t stream);
 
-/* Device-resident Newmark-beta step for a translating rigid body (reference dyn.py:5-51,126-136 and the
- * coupling of examples/2d/vortex_induced_vibration.py:135-137): h = -force_sum + a*added_mass;
- * (a,v,d) <- newmark(a,v,d,h,m,k,c); force_sum <- 0.  n_dof = 2 or 3 translation components. */
-int vsb_body_newmark(VsbBodyState* body, int n_dof, double m, double k, double c, double added_mass,
-                     vsb_stream_t stream);
+/* Velocity of the streamed state on the IB window: u_win <- u(stream(f_in)) (feeds vsb_ib_mdf).  Uses grid, f_in,
+ * do_stream, win_origin / body + parity, win_size and the mask of `args`.  The window must not contain cells of a
+ * face that carries a boundary operation. */
+int vsb_ib_window_moments(const VsbStepArgs* args, float* u_win, vsb_stream_t stream);
+
+/* Body update on the device: h = -force_sum + a*added_mass; (a,v,d) <- newmark(a,v,d,h,m,k,c); force_sum <- 0;
+ * origin2[parity ^ 1] <- window origin for the next step.  `parity` is the parity of the step being completed. */
+int vsb_body_newmark(VsbBodyState* body, const VsbBodyParams* params, int parity, vsb_stream_t stream);
+
+/* The whole immersed-boundary part of one step in ONE kernel (single CTA, scratch in shared memory):
+ * velocity at the stencil points from the streamed state, all multi-direct-forcing iterations, the force field
+ * written to mdf->g_win (every window cell, no memset needed), the body update of vsb_body_newmark.
+ * Only when the window fits shared memory: dim * window_cells * 4 B <= 200 KB (vsb_ib_fused_supported). */
+int vsb_ib_fused_supported(const VsbMdfArgs* mdf);
+int vsb_ib_fused(const VsbStepArgs* args, const VsbMdfArgs* mdf, const VsbBodyParams* params, vsb_stream_t stream);
 
 #ifdef __cplusplus
 }

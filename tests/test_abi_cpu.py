@@ -28,7 +28,7 @@ def declared_symbols():
 
 def test_header_symbols_exported(lib):
     names = declared_symbols()
-    assert len(names) >= 18
+    assert len(names) >= 22
     for n in names:
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
     from vivsim_b200 import _lib
@@ -38,7 +38,7 @@ def test_header_symbols_exported(lib):
 
 def test_struct_layouts_match_header(lib):
     from vivsim_b200 import _lib
-    assert ctypes.sizeof(_lib.VsbBodyState) == 72
+    assert ctypes.sizeof(_lib.VsbBodyState) == 84
     assert ctypes.sizeof(_lib.VsbGrid) == 16
     assert ctypes.sizeof(_lib.VsbWallValue) == 16
 

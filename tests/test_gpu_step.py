@@ -122,7 +122,8 @@ def test_cuda_graph_matches_eager():
     f0 = recipes.uniform_init(spec, noise=1e-3, seed=3)
     a = Stepper(spec).set_f(f0); a.step(25)
     b = Stepper(spec, use_graph=True).set_f(f0); b.step(12); b.step(13)
-    assert_close(N(b.get_f()), N(a.get_f()), rtol=1e-6, what="graph vs eager")
+    # spreading uses fp32 atomics, so two runs agree to rounding, not bit for bit
+    assert_close(N(b.get_f()), N(a.get_f()), rtol=1e-5, what="graph vs eager")
 
 
 def test_full_size_properties_c2():
@@ -171,11 +172,55 @@ def test_slab_stepper_single_rank_matches_plain_stepper():
     f0 = recipes.uniform_init(spec, noise=1e-3, seed=0)
     a = Stepper(spec).set_f(f0); a.step(12)
     b = SlabStepper(spec, rank=0, world=1).set_f_global(f0); b.step(12)
-    assert_bitexact(N(b.gather_f()), N(a.get_f()), "slab(1 rank) vs plain")
-    assert_bitexact(N(b.stepper.marker_force), N(a.marker_force), "marker forces")
+    # the IB spread uses fp32 atomics: agreement to rounding; without the body the match is bit-exact
+    assert_close(N(b.gather_f()), N(a.get_f()), what="slab(1 rank) vs plain")
+    assert_close(N(b.stepper.marker_force), N(a.marker_force), rtol=1e-4, what="marker forces")
+    spec2 = dict(spec, ib=None, forcing=None)
+    a = Stepper(spec2).set_f(f0); a.step(12)
+    b = SlabStepper(spec2, rank=0, world=1).set_f_global(f0); b.step(12)
+    assert_bitexact(N(b.gather_f()), N(a.get_f()), "slab(1 rank) vs plain, no body")
 
 
 def _mask(shape):
     m = np.zeros(shape, dtype=bool)
     m[70:74, 20:30] = True
     return m
+
+
+@pytest.mark.parametrize("name", ["cylinder_c2", "cylinder_kbc_edm", "sphere", "text_mask", "cavity"])
+def test_scheduling_variants_agree(golden, name):
+    """Fused-IB / fused-wall / concurrent-stream paths against the plain sequential multi-kernel path."""
+    from vivsim_b200 import Stepper
+    g = golden["recipes"]
+    spec, f0, n, key = dict(cases.all_fluid_cases(g))[name]
+    base = Stepper(spec, fuse_ib=False, fuse_edges=False, overlap=False).set_f(f0); base.step(n)
+    ref = N(base.get_f())
+    assert_close(ref, g[key], what=f"{name} sequential path")
+    for kw in (dict(fuse_ib=True, fuse_edges=False, overlap=False), dict(fuse_ib=False, fuse_edges=True, overlap=False),
+               dict(fuse_ib=True, fuse_edges=True, overlap=True), dict(fuse_ib=False, fuse_edges=True, overlap=True)):
+        st = Stepper(spec, **kw).set_f(f0); st.step(n)
+        assert_close(N(st.get_f()), g[key], what=f"{name} {kw}")
+        if spec.get("ib") is None:
+            assert_bitexact(N(st.get_f()), ref, f"{name} {kw} (no atomics involved)")
+
+
+def test_moving_window_follows_body():
+    """A body driven across several cells: the IB window origin must track trunc(origin0 + d) on every path."""
+    from vivsim_b200 import Stepper, configs
+    spec, body = configs.viv_cylinder_2d(nx=160, ny=96, n_marker=64, radius=8.0, u0=0.08, nu=0.02, n_iter=2)
+    body = dict(body, v0=(0.25, -0.15), k=0.0)          # coasting body: ~0.25 cells per step
+    f0 = configs.uniform_state(spec, noise=1e-3)
+    outs = []
+    for kw in (dict(dyn_mode="host"), dict(dyn_mode="device"), dict(dyn_mode="device", fuse_ib=False, overlap=False),
+               dict(dyn_mode="device", use_graph=True)):
+        st = Stepper(spec, body=dict(body), **kw).set_f(f0)
+        st.step(30)
+        d, v, a, h = st.body_state()
+        org = st.window_origin()
+        o0 = spec["ib"]["window"][0]
+        assert org == (int(np.float32(o0[0]) + d[0]), int(np.float32(o0[1]) + d[1])), (kw, org, d)
+        assert abs(d[0]) > 4
+        outs.append((N(st.get_f()), d))
+    for f, d in outs[1:]:
+        assert_close(f, outs[0][0], what="moving body paths agree")
+        assert_close(d, outs[0][1], rtol=1e-4, what="displacement")

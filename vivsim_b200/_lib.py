@@ -24,7 +24,7 @@ EXPORTS = [
     "vsb_abi_version", "vsb_last_error", "vsb_streaming", "vsb_macroscopic", "vsb_equilibrium", "vsb_collision",
     "vsb_guo_forcing_term", "vsb_forcing", "vsb_post_op", "vsb_boundary_characteristic", "vsb_ib_delta",
     "vsb_ib_stencil", "vsb_ib_interpolate", "vsb_ib_spread", "vsb_ib_mdf", "vsb_step", "vsb_ib_window_moments",
-    "vsb_body_newmark",
+    "vsb_body_newmark", "vsb_edge_fused", "vsb_edge_fused_supported", "vsb_ib_fused", "vsb_ib_fused_supported",
 ]
 
 
@@ -43,17 +43,22 @@ class VsbPostOp(C.Structure):
 
 class VsbBodyState(C.Structure):
     _fields_ = [("d", C.c_float * 3), ("v", C.c_float * 3), ("a", C.c_float * 3), ("h", C.c_float * 3),
-                ("force_sum", C.c_float * 3), ("origin", C.c_int * 3)]
+                ("force_sum", C.c_float * 3), ("origin2", (C.c_int * 3) * 2)]
 
 
-BODY_FLOATS = 15  # d, v, a, h, force_sum as fp32; then 3 int32 (origin)
-BODY_BYTES = C.sizeof(VsbBodyState)
+BODY_BYTES = C.sizeof(VsbBodyState)   # 15 fp32 + 6 int32 = 84 bytes
+
+
+class VsbBodyParams(C.Structure):
+    _fields_ = [("n_dof", C.c_int), ("follow", C.c_int), ("origin0", C.c_float * 3), ("grid_size", C.c_int * 3),
+                ("win_size", C.c_int * 3), ("m", C.c_double), ("k", C.c_double), ("c", C.c_double),
+                ("added_mass", C.c_double)]
 
 
 class VsbMdfArgs(C.Structure):
-    _fields_ = [("dim", C.c_int), ("delta_kind", C.c_int), ("n_iter", C.c_int), ("follow", C.c_int),
+    _fields_ = [("dim", C.c_int), ("delta_kind", C.c_int), ("n_iter", C.c_int), ("parity", C.c_int),
                 ("n_markers", C.c_int64), ("win_origin0", C.c_int * 3), ("win_size", C.c_int * 3),
-                ("grid_size", C.c_int * 3), ("markers0", C.c_void_p), ("u_target", C.c_void_p),
+                ("markers0", C.c_void_p), ("u_target", C.c_void_p),
                 ("ds_ptr", C.c_void_p), ("ds_value", C.c_float), ("u_win", C.c_void_p), ("g_win", C.c_void_p),
                 ("scratch", C.c_void_p), ("marker_u", C.c_void_p), ("marker_force", C.c_void_p),
                 ("body", C.c_void_p)]
@@ -64,8 +69,9 @@ class VsbStepArgs(C.Structure):
                 ("mrt_op_host", C.c_void_p), ("mrt_fop_host", C.c_void_p), ("do_stream", C.c_int),
                 ("do_collide", C.c_int), ("row_begin", C.c_int), ("row_end", C.c_int), ("f_in", C.c_void_p),
                 ("f_out", C.c_void_p), ("g_uniform", C.c_float * 3), ("g_win", C.c_void_p),
-                ("win_origin", C.c_int * 3), ("win_size", C.c_int * 3), ("body", C.c_void_p),
-                ("n_post", C.c_int), ("post", C.POINTER(VsbPostOp)), ("vec", C.c_int)]
+                ("win_origin", C.c_int * 3), ("win_size", C.c_int * 3), ("body", C.c_void_p), ("parity", C.c_int),
+                ("n_post", C.c_int), ("post", C.POINTER(VsbPostOp)), ("vec", C.c_int), ("band", C.c_int),
+                ("edges", C.c_int)]
 
 
 _lib = None

@@ -1,50 +1,12 @@
 // Post-streaming operations on domain faces: NEE / NEBB / equilibrium (+ velocity, pressure,
 // force-corrected wrappers), bounce-back / specular reflection, obstacle mask, characteristic BC.
 // One thread per face cell; all in place on the post-streaming populations.  SURVEY.md 8a rows a10-a16.
-#include "vsb_common.cuh"
+#include "vsb_bc.cuh"
 #include "vsb_internal.h"
 
 namespace vsb {
 
 constexpr int kBlock = 128;
-
-struct WallVals {
-  VsbWallValue rho, u[3], g[3];
-};
-
-__device__ __forceinline__ float wv(const VsbWallValue& v, long long k) { return v.ptr ? v.ptr[k] : v.value; }
-
-template <int DIM>
-__host__ __device__ constexpr int find_dir(int c0, int c1, int c2) {
-  using L = Lat<DIM>;
-  for (int q = 0; q < L::Q; ++q)
-    if (L::c(q, 0) == c0 && L::c(q, 1) == c1 && L::c(q, 2) == c2) return q;
-  return -1;
-}
-
-// Geometry of one face in array-axis terms.  LOC as VSB_LOC_*.
-template <int DIM, int LOC> struct FaceGeom {
-  using L = Lat<DIM>;
-  static constexpr int AX = LOC / 2 + L::A0;          // array axis normal to the face
-  static constexpr int SIGN = (LOC % 2 == 0) ? 1 : -1; // inward normal direction along AX
-  static constexpr int ND = AX - L::A0;               // velocity component normal to the face
-  static constexpr int TA = (AX == 0) ? 1 : 0;        // remaining array axes, ascending
-  static constexpr int TB = (AX == 2) ? 1 : 2;
-  __host__ __device__ static constexpr int cn(int q) { return L::c(q, AX) * SIGN; }  // >0: enters the fluid
-};
-
-// sum_{zero} f + 2 sum_{out} f      (lbm/boundary/_helpers.py:135-145, lbm3d/boundary/_helpers.py:35-43)
-template <int DIM, int LOC>
-__device__ __forceinline__ float rho_numerator(const float (&fw)[Lat<DIM>::Q]) {
-  using G = FaceGeom<DIM, LOC>;
-  float zero = 0.f, out = 0.f;
-#pragma unroll
-  for (int q = 0; q < Lat<DIM>::Q; ++q) {
-    if (G::cn(q) == 0) zero += fw[q];
-    if (G::cn(q) < 0) out += fw[q];
-  }
-  return zero + 2.0f * out;
-}
 
 template <int DIM, int LOC>
 __global__ void k_face_bc(float* __restrict__ f, int n0, int n1, int n2, int wall_layer, int kind, int wrap, WallVals w) {
@@ -67,73 +29,19 @@ __global__ void k_face_bc(float* __restrict__ f, int n0, int n1, int n2, int wal
   float fw[Q], fn[Q];
 #pragma unroll
   for (int q = 0; q < Q; ++q) fw[q] = f[q * ncell + cw];
-  const bool need_nb = (kind == VSB_BC_NEE) || (wrap == VSB_WRAP_PRESSURE);
-  if (need_nb) {
+  if (bc_needs_neighbor(kind, wrap)) {
 #pragma unroll
     for (int q = 0; q < Q; ++q) fn[q] = f[q * ncell + cn];
+  } else {
+#pragma unroll
+    for (int q = 0; q < Q; ++q) fn[q] = 0.f;
   }
-
-  float rho_w = wv(w.rho, k), uw[D];
+  float uw[D], gw[D];
 #pragma unroll
-  for (int d = 0; d < D; ++d) uw[d] = wv(w.u[d], k);
-
-  if (wrap == VSB_WRAP_VELOCITY) {
-    // rho_w = numerator / (1 - u_n)                (lbm/boundary/_helpers.py:80-95, lbm3d/.../_helpers.py:58-63)
-    rho_w = rho_numerator<DIM, LOC>(fw) / (1.0f - (float)G::SIGN * uw[G::ND]);
-  } else if (wrap == VSB_WRAP_PRESSURE) {
-    // u_n from rho_w; tangential velocity from the adjacent fluid layer
-    // (lbm/boundary/_helpers.py:98-132 ; lbm3d/boundary/_helpers.py:66-78)
-    const float un = (float)G::SIGN * (1.0f - rho_numerator<DIM, LOC>(fw) / rho_w);
-    float rho_nb, u_nb[D];
-    moments<DIM>(fn, rho_nb, u_nb);
+  for (int d = 0; d < D; ++d) { uw[d] = wv(w.u[d], k); gw[d] = wv(w.g[d], k); }
+  apply_face_bc<DIM, LOC>(fw, fn, kind, wrap, wv(w.rho, k), uw, gw);
 #pragma unroll
-    for (int d = 0; d < D; ++d) uw[d] = u_nb[d];
-    uw[G::ND] = un;
-  } else if (wrap == VSB_WRAP_FORCE_CORRECTED) {
-    // u_w -= g_w / (2 rho_w)                        (lbm/boundary/_helpers.py:156-177)
-#pragma unroll
-    for (int d = 0; d < D; ++d) uw[d] -= wv(w.g[d], k) * 0.5f / rho_w;
-  }
-
-  if (kind == VSB_BC_EQUILIBRIUM) {            // lbm/boundary/eq.py:45-56
-    float fe[Q];
-    equilibrium<DIM>(rho_w, uw, fe);
-#pragma unroll
-    for (int q = 0; q < Q; ++q) f[q * ncell + cw] = fe[q];
-  } else if (kind == VSB_BC_NEE) {             // lbm/boundary/nee.py:43-60
-    float fe[Q], fen[Q], rho_nb, u_nb[D];
-    equilibrium<DIM>(rho_w, uw, fe);
-    moments<DIM>(fn, rho_nb, u_nb);
-    equilibrium<DIM>(rho_nb, u_nb, fen);
-#pragma unroll
-    for (int q = 0; q < Q; ++q) f[q * ncell + cw] = fe[q] + (fn[q] - fen[q]);
-  } else if (kind == VSB_BC_NEBB) {
-    if constexpr (DIM == 2) {
-      // Zou/He with transverse correction          (lbm/boundary/nebb.py:41-58)
-      constexpr int TAX = (G::AX == 1) ? 2 : 1;  // tangential array axis
-      constexpr int TD = TAX - L::A0;
-      constexpr int cN[3] = {0, G::AX == 1 ? G::SIGN : 0, G::AX == 2 ? G::SIGN : 0};
-      constexpr int cT[3] = {0, TAX == 1 ? 1 : 0, TAX == 2 ? 1 : 0};
-      constexpr int in0 = find_dir<2>(0, cN[1], cN[2]);
-      constexpr int in1 = find_dir<2>(0, cN[1] + G::SIGN * cT[1], cN[2] + G::SIGN * cT[2]);
-      constexpr int in2 = find_dir<2>(0, cN[1] - G::SIGN * cT[1], cN[2] - G::SIGN * cT[2]);
-      constexpr int t0 = find_dir<2>(0, cT[1], cT[2]), t1 = find_dir<2>(0, -cT[1], -cT[2]);
-      const float un = (float)G::SIGN * uw[G::ND], ut = (float)G::SIGN * uw[TD];
-      const float shear = 0.5f * (fw[t0] - fw[t1]) * (float)G::SIGN;
-      const float normal = (1.0f / 6.0f) * un * rho_w;
-      const float tang = 0.5f * ut * rho_w;
-      f[in0 * ncell + cw] = fw[L::opp(in0)] + (2.0f / 3.0f) * un * rho_w;
-      f[in1 * ncell + cw] = fw[L::opp(in1)] - shear + normal + tang;
-      f[in2 * ncell + cw] = fw[L::opp(in2)] + shear + normal - tang;
-    } else {
-      // f_in = f_opp(in) + feq_in - feq_opp(in)    (lbm3d/boundary/nebb.py:16-32)
-      float fe[Q];
-      equilibrium<DIM>(rho_w, uw, fe);
-#pragma unroll
-      for (int q = 0; q < Q; ++q)
-        if (G::cn(q) > 0) f[q * ncell + cw] = fw[L::opp(q)] + fe[q] - fe[L::opp(q)];
-    }
-  }
+  for (int q = 0; q < Q; ++q) f[q * ncell + cw] = fw[q];
 }
 
 // bounce-back / specular reflection: needs the PRE-streaming populations on the wall.
@@ -153,36 +61,14 @@ __global__ void k_face_reflect(const float* __restrict__ f_pre, float* __restric
   idx[G::AX] = wall_layer;
   const long long ncell = (long long)n0 * n1 * n2;
   const long long cw = ((long long)idx[0] * n1 + idx[1]) * n2 + idx[2];
-  float uw[D];
+  float fw[Q], pre[Q], uw[D];
+#pragma unroll
+  for (int q = 0; q < Q; ++q) { fw[q] = f[q * ncell + cw]; pre[q] = f_pre[q * ncell + cw]; }
 #pragma unroll
   for (int d = 0; d < D; ++d) uw[d] = wv(w.u[d], k);
-  if constexpr (DIM == 2) {
-    // in_k <- pre[out_k] + {2/3 un, 1/6 (un+ut), 1/6 (un-ut)}; rho = 1 assumed   (lbm/boundary/bb.py:43-53,82-95)
-    constexpr int TAX = (G::AX == 1) ? 2 : 1;
-    constexpr int TD = TAX - L::A0;
-    constexpr int cN[3] = {0, G::AX == 1 ? G::SIGN : 0, G::AX == 2 ? G::SIGN : 0};
-    constexpr int cT[3] = {0, TAX == 1 ? 1 : 0, TAX == 2 ? 1 : 0};
-    constexpr int in0 = find_dir<2>(0, cN[1], cN[2]);
-    constexpr int in1 = find_dir<2>(0, cN[1] + G::SIGN * cT[1], cN[2] + G::SIGN * cT[2]);
-    constexpr int in2 = find_dir<2>(0, cN[1] - G::SIGN * cT[1], cN[2] - G::SIGN * cT[2]);
-    const float un = (float)G::SIGN * uw[G::ND], ut = (float)G::SIGN * uw[TD];
-    const float v0 = f_pre[L::opp(in0) * ncell + cw] + (2.0f / 3.0f) * un;
-    const float v1 = f_pre[L::opp(in1) * ncell + cw] + (1.0f / 6.0f) * (un + ut);
-    const float v2 = f_pre[L::opp(in2) * ncell + cw] + (1.0f / 6.0f) * (un - ut);
-    f[in0 * ncell + cw] = v0;
-    f[(specular ? in2 : in1) * ncell + cw] = v1;
-    f[(specular ? in1 : in2) * ncell + cw] = v2;
-  } else {
-    // in <- pre[mirror(in)] + 2 w rho_w (c_in.u_w)/cs^2, rho_w = sum_q pre; specular == bounce-back
-    // in the reference                                                        (lbm3d/boundary/bb.py:9-53)
-    float pre[Q], rho = 0.f;
+  apply_face_reflect<DIM, LOC>(fw, pre, specular, uw);
 #pragma unroll
-    for (int q = 0; q < Q; ++q) { pre[q] = f_pre[q * ncell + cw]; rho += pre[q]; }
-#pragma unroll
-    for (int q = 0; q < Q; ++q)
-      if (G::cn(q) > 0)
-        f[q * ncell + cw] = pre[mirror_dir<3>(q, G::AX)] + 2.0f * L::w(q) * rho * dot_c<DIM>(q, uw) * 3.0f;
-  }
+  for (int q = 0; q < Q; ++q) f[q * ncell + cw] = fw[q];
 }
 
 // obstacle_bounce_back: masked cells f_q <- f_opp(q)          (lbm/boundary/bb.py:110, lbm3d/boundary/bb.py:59)

@@ -275,6 +275,27 @@ __device__ __forceinline__ void matvec_add(float (&f)[Lat<DIM>::Q], const Matrix
   }
 }
 
+// ----------------------------------------------------------------------------- IB delta kernels
+// ib/kernels.py:4-61 (+ the 2-point hat, which the reference names in its README but does not define)
+__device__ __forceinline__ float delta(int kind, float r) {
+  const float a = fabsf(r);
+  switch (kind) {
+    case VSB_DELTA_PESKIN3:
+      if (a > 1.5f) return 0.f;
+      if (a < 0.5f) return (1.0f + sqrtf(1.0f - 3.0f * a * a)) / 3.0f;
+      return (5.0f - 3.0f * a - sqrtf(-2.0f + 6.0f * a - 3.0f * a * a)) / 6.0f;
+    case VSB_DELTA_PESKIN4:
+      if (a > 2.0f) return 0.f;
+      if (a < 1.0f) return (3.0f - 2.0f * a + sqrtf(1.0f + 4.0f * a - 4.0f * a * a)) * 0.125f;
+      return (5.0f - 2.0f * a - sqrtf(-7.0f + 12.0f * a - 4.0f * a * a)) * 0.125f;
+    case VSB_DELTA_COSINE4:
+      if (a > 2.0f) return 0.f;
+      return (1.0f + cosf(3.14159265358979323846f * a * 0.5f)) * 0.25f;
+    default:  // VSB_DELTA_HAT2
+      return fmaxf(0.f, 1.0f - a);
+  }
+}
+
 // ----------------------------------------------------------------------------- launch helpers
 inline unsigned blocks_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
 

@@ -2,32 +2,11 @@
 // spread, and marker-parallel multi-direct forcing with the stencil evaluated on the fly.
 // A group of lanes owns one marker; its stencil points are spread over the lanes and reduced
 // with warp shuffles; spreading uses fp32 atomics (REDG) into window-sized buffers.
-#include "vsb_common.cuh"
-#include "vsb_internal.h"
+#include "vsb_step.cuh"
 
 namespace vsb {
 
 constexpr int kBlock = 128;
-
-// ib/kernels.py:4-61 (+ the 2-point hat, which the reference names in its README but does not define)
-__device__ __forceinline__ float delta(int kind, float r) {
-  const float a = fabsf(r);
-  switch (kind) {
-    case VSB_DELTA_PESKIN3:
-      if (a > 1.5f) return 0.f;
-      if (a < 0.5f) return (1.0f + sqrtf(1.0f - 3.0f * a * a)) / 3.0f;
-      return (5.0f - 3.0f * a - sqrtf(-2.0f + 6.0f * a - 3.0f * a * a)) / 6.0f;
-    case VSB_DELTA_PESKIN4:
-      if (a > 2.0f) return 0.f;
-      if (a < 1.0f) return (3.0f - 2.0f * a + sqrtf(1.0f + 4.0f * a - 4.0f * a * a)) * 0.125f;
-      return (5.0f - 2.0f * a - sqrtf(-7.0f + 12.0f * a - 4.0f * a * a)) * 0.125f;
-    case VSB_DELTA_COSINE4:
-      if (a > 2.0f) return 0.f;
-      return (1.0f + cosf(3.14159265358979323846f * a * 0.5f)) * 0.25f;
-    default:  // VSB_DELTA_HAT2
-      return fmaxf(0.f, 1.0f - a);
-  }
-}
 
 __global__ void k_delta(int kind, long long n, const float* __restrict__ r, float* __restrict__ out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -86,7 +65,7 @@ __global__ void k_spread(int ncomp, long long ncell, float* __restrict__ grid, l
 
 // ----------------------------------------------------------------------------- fused MDF stage
 struct MdfParams {
-  int delta_kind, n_iter, stage, follow;
+  int delta_kind, n_iter, stage, parity;
   long long n_markers;
   int origin0[3], wsize[3];
   const float* markers0;
@@ -133,7 +112,7 @@ __global__ void k_mdf_stage(MdfParams p) {
     for (int d = 0; d < DIM; ++d) {
       float pos = p.markers0[m * DIM + d];
       int org = p.origin0[d];
-      if (p.body) { pos += p.body->d[d]; org = p.body->origin[d]; }
+      if (p.body) { pos += p.body->d[d]; org = p.body->origin2[p.parity][d]; }
       x[d] = pos - (float)org;   // window-local coordinate, as in the reference's marker_x - ib_x0
       base[d] = (int)floorf(x[d]);
     }
@@ -214,22 +193,9 @@ __global__ void k_mdf_stage(MdfParams p) {
   }
 }
 
-// h = -force_sum + a * added_mass ; Newmark-beta ; force_sum = 0      (dyn.py:27-51,136; VIV example :135-137)
-__global__ void k_body_newmark(VsbBodyState* b, int n_dof, float denom, float k, float c, float added_mass) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  const float gamma = 0.5f, beta = 0.25f, dt = 1.0f;
-  const float c1 = gamma * dt, c2 = beta * dt * dt;
-  for (int i = 0; i < n_dof; ++i) {
-    const float h = -b->force_sum[i] + b->a[i] * added_mass;
-    const float v1 = b->v[i] + dt * (1.0f - gamma) * b->a[i];
-    const float d1 = b->d[i] + dt * b->v[i] + dt * dt * (0.5f - beta) * b->a[i];
-    const float a_next = (h - c * v1 - k * d1) / denom;  // denom = m + c1 c + c2 k, evaluated in double on the host
-    b->h[i] = h;
-    b->a[i] = a_next;
-    b->v[i] = c1 * a_next + v1;
-    b->d[i] = c2 * a_next + d1;
-  }
-  for (int i = 0; i < 3; ++i) b->force_sum[i] = 0.f;
+// body update by one thread (see body_update in vsb_step.cuh)
+__global__ void k_body_newmark(VsbBodyState* b, BodyUpdate u, int parity) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) body_update(b, u, parity);
 }
 
 }  // namespace vsb
@@ -295,7 +261,7 @@ int vsb_ib_mdf(const VsbMdfArgs* a, vsb_stream_t stream) {
   for (int d = 0; d < a->dim; ++d) VSB_REQUIRE(a->win_size[d] >= 4, "IB window must be at least 4 cells wide");
   if (a->n_markers == 0) return VSB_OK;
   MdfParams p;
-  p.delta_kind = a->delta_kind; p.n_iter = a->n_iter; p.follow = a->follow; p.n_markers = a->n_markers;
+  p.delta_kind = a->delta_kind; p.n_iter = a->n_iter; p.parity = a->parity & 1; p.n_markers = a->n_markers;
   for (int d = 0; d < 3; ++d) { p.origin0[d] = a->win_origin0[d]; p.wsize[d] = a->win_size[d]; }
   p.markers0 = a->markers0; p.u_target = a->u_target; p.ds_ptr = a->ds_ptr; p.ds_value = a->ds_value;
   p.u_win = a->u_win; p.g_win = a->g_win; p.scratch = a->scratch; p.marker_u = a->marker_u;
@@ -311,11 +277,13 @@ int vsb_ib_mdf(const VsbMdfArgs* a, vsb_stream_t stream) {
   return VSB_OK;
 }
 
-int vsb_body_newmark(VsbBodyState* body, int n_dof, double m, double k, double c, double added_mass, vsb_stream_t stream) {
-  VSB_REQUIRE(body != nullptr, "vsb_body_newmark: null body");
-  VSB_REQUIRE(n_dof >= 1 && n_dof <= 3, "n_dof must be 1..3, got %d", n_dof);
-  k_body_newmark<<<1, 32, 0, (cudaStream_t)stream>>>(body, n_dof, (float)(m + 0.5 * c + 0.25 * k), (float)k, (float)c,
-                                                     (float)added_mass);
+int vsb_body_newmark(VsbBodyState* body, const VsbBodyParams* params, int parity, vsb_stream_t stream) {
+  VSB_REQUIRE(body != nullptr && params != nullptr, "vsb_body_newmark: null argument");
+  VSB_REQUIRE(params->n_dof >= 1 && params->n_dof <= 3, "n_dof must be 1..3, got %d", params->n_dof);
+  VSB_REQUIRE(params->follow >= 0 && params->follow <= 2, "follow must be 0, 1 or 2");
+  int dim = 3;
+  if (params->grid_size[2] <= 1) dim = 2;
+  k_body_newmark<<<1, 32, 0, (cudaStream_t)stream>>>(body, make_body_update(*params, dim), parity & 1);
   VSB_LAUNCH_CHECK("vsb_body_newmark");
   return VSB_OK;
 }

@@ -8,39 +8,12 @@
 // missing element comes from the neighbouring lane by warp shuffle; only lanes at a warp or row
 // edge issue one extra scalar load (which also performs the periodic wrap).  Shifts along the
 // other axes only change the row that is read, so every access stays aligned and coalesced.
-#include <utility>
+#include <algorithm>
 
-#include "vsb_common.cuh"
-#include "vsb_internal.h"
+#include "vsb_bc.cuh"
+#include "vsb_step.cuh"
 
 namespace vsb {
-
-// compile-time loop: body(std::integral_constant<int, I>) for I in [0, N)
-template <class F, int... I>
-__device__ __forceinline__ void static_for_impl(F&& body, std::integer_sequence<int, I...>) {
-  (body(std::integral_constant<int, I>{}), ...);
-}
-template <int N, class F>
-__device__ __forceinline__ void static_for(F&& body) {
-  static_for_impl(body, std::make_integer_sequence<int, N>{});
-}
-
-template <int DIM> struct StepParams {
-  int n0, n1, n2;
-  int r_begin, r_end;   // rows of array axis A0 (the slowest real axis) to update
-  const float* fin;
-  float* fout;
-  int do_stream, do_collide, forcing;
-  Relax rx;
-  float g0[3];
-  const float* gwin;
-  int worg[3], wsz[3];
-  const VsbBodyState* body;
-  const uint8_t* mask;
-};
-
-template <int DIM, bool USED> struct MrtMats { Matrix<Lat<DIM>::Q> A, B; };
-template <int DIM> struct MrtMats<DIM, false> {};
 
 template <int VEC> struct VecT;
 template <> struct VecT<1> { using type = float; };
@@ -66,104 +39,38 @@ __device__ __forceinline__ void store_vec(float* __restrict__ p, const float (&v
   *reinterpret_cast<T*>(p) = t;
 }
 
-__device__ __forceinline__ int wrap(int i, int n) {
-  i += (i < 0) ? n : 0;
-  i -= (i >= n) ? n : 0;
-  return i;
-}
-
-// Force window lookup, split so that the part that does not depend on the contiguous coordinate is done once
-// per thread: `base` is the flat window index of (c0, c1, 0) and `rows_inside` tells whether the leading
-// coordinates fall inside the window.
-template <int DIM>
-__device__ __forceinline__ void window_rows(const StepParams<DIM>& p, const int (&worg)[3], int c0, int c1,
-                                            bool& rows_inside, int& base) {
-  using L = Lat<DIM>;
-  rows_inside = p.gwin != nullptr;
-  base = 0;
-  const int coord[3] = {c0, c1, 0};
-#pragma unroll
-  for (int d = 0; d < L::D - 1; ++d) {
-    const int rel = coord[d + L::A0] - worg[d];
-    rows_inside = rows_inside && (unsigned)rel < (unsigned)p.wsz[d];
-    base = (base + rel) * p.wsz[d + 1];
-  }
-}
-
-template <int DIM>
-__device__ __forceinline__ void cell_force(const StepParams<DIM>& p, const int (&worg)[3], bool rows_inside, int base,
-                                           int c2, float (&g)[Lat<DIM>::D]) {
-  using L = Lat<DIM>;
-#pragma unroll
-  for (int d = 0; d < L::D; ++d) g[d] = p.g0[d];
-  const int rel = c2 - worg[L::D - 1];
-  if (rows_inside && (unsigned)rel < (unsigned)p.wsz[L::D - 1]) {
-    int wcells = 1;
-#pragma unroll
-    for (int d = 0; d < L::D; ++d) wcells *= p.wsz[d];
-#pragma unroll
-    for (int d = 0; d < L::D; ++d) g[d] += p.gwin[d * wcells + base + rel];
-  }
-}
-
-// moments -> (Guo velocity shift) -> equilibrium -> collision -> forcing, on one cell in registers.
-// Order of operations: examples/2d/poiseuille_channel.py:80-148 (EDM uses the uncorrected velocity,
-// Guo shifts u by g/(2 rho) before the equilibrium).
-template <int DIM, int COLL>
-__device__ __forceinline__ void collide_cell(float (&f)[Lat<DIM>::Q], const float (&g)[Lat<DIM>::D], int forcing,
-                                             const Relax& rx, const MrtMats<DIM, COLL == VSB_COLL_MRT>& mm) {
-  using L = Lat<DIM>;
-  float rho, u[L::D], feq[L::Q];
-  moments<DIM>(f, rho, u);
-  // a zero force contributes exactly nothing (u + 0, f + w*0): skip the work -- bit-identical
-  bool has_g = false;
-#pragma unroll
-  for (int d = 0; d < L::D; ++d) has_g = has_g || (g[d] != 0.f);
-  if (!has_g) forcing = VSB_FORCE_NONE;
-  if (forcing == VSB_FORCE_GUO) {
-#pragma unroll
-    for (int d = 0; d < L::D; ++d) u[d] += g[d] * 0.5f / rho;
-  }
-  equilibrium<DIM>(rho, u, feq);
-  if constexpr (COLL == VSB_COLL_BGK) collide_bgk<DIM>(f, feq, rx);
-  if constexpr (COLL == VSB_COLL_KBC) collide_kbc<DIM>(f, feq, rx);
-  if constexpr (COLL == VSB_COLL_REG) collide_reg<DIM>(f, feq, rx);
-  if constexpr (COLL == VSB_COLL_MRT) collide_mrt<DIM>(f, feq, mm.A);
-  if (forcing != VSB_FORCE_NONE) {
-    float G[L::Q];
-    guo_term<DIM>(g, u, G);
-    if (forcing == VSB_FORCE_EDM) {
-#pragma unroll
-      for (int q = 0; q < L::Q; ++q) f[q] += G[q];
-    } else {
-      if constexpr (COLL == VSB_COLL_MRT) {
-        matvec_add<DIM>(f, mm.B, G);
-      } else {
-#pragma unroll
-        for (int q = 0; q < L::Q; ++q) f[q] += G[q] * rx.guo_scale;
-      }
-    }
-  }
-}
-
 template <int DIM, int COLL, int VEC>
 __global__ void __launch_bounds__(256) k_step(const StepParams<DIM> p, const MrtMats<DIM, COLL == VSB_COLL_MRT> mm) {
   using L = Lat<DIM>;
   constexpr int Q = L::Q;
   const int nv = p.n2 / VEC;
-  const long long rows = (DIM == 2) ? (long long)(p.r_end - p.r_begin) : (long long)(p.r_end - p.r_begin) * p.n1;
+  int worg[3];
+  window_origin<DIM>(p, worg);
+  // rows of the slowest axis handled by this launch: all of [r_begin, r_end), or only / all but the x-range of
+  // the force window (band), so that the bulk can run while the IB kernels still produce the window's force
+  const int band_lo = max(p.r_begin, worg[0]), band_hi = min(p.r_end, worg[0] + p.wsz[0]);
+  const int row0 = (p.band == 2) ? band_lo : p.r_begin;
+  const int nrow = (p.band == 2) ? max(band_hi - band_lo, 0) : p.r_end - p.r_begin;
+  const long long rows = (DIM == 2) ? (long long)nrow : (long long)nrow * p.n1;
   const long long total = rows * nv;
   long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = gid < total;
-  if (!active) gid = total - 1;  // keep the lane in the shuffles with valid addresses; it stores nothing
+  bool active = gid < total;
+  if (!active) gid = 0;          // the lane stays in the shuffles; it loads and stores nothing
   const int j = (int)(gid % nv);
   const long long row = gid / nv;
-  const int i0 = (DIM == 2) ? 0 : p.r_begin + (int)(row / p.n1);
-  const int i1 = (DIM == 2) ? p.r_begin + (int)row : (int)(row % p.n1);
+  const int i0 = (DIM == 2) ? 0 : row0 + (int)(row / p.n1);
+  const int i1 = (DIM == 2) ? row0 + (int)row : (int)(row % p.n1);
   const int i2 = j * VEC;
   const int lane = threadIdx.x & 31;
   const long long ncell = (long long)p.n0 * p.n1 * p.n2;
   const long long cell = ((long long)i0 * p.n1 + i1) * p.n2 + i2;
+  {
+    const int ix = (DIM == 2) ? i1 : i0;
+    if (p.band == 1 && ix >= band_lo && ix < band_hi) active = false;
+    const int coord[2] = {i0, i1};
+    for (int e = 0; e < p.n_skip; ++e)   // wall layers owned by the fused wall kernel
+      if (coord[p.skip_axis[e]] == p.skip_layer[e]) active = false;
+  }
 
   float f[VEC][Q];
   if (p.do_stream) {
@@ -174,29 +81,34 @@ __global__ void __launch_bounds__(256) k_step(const StepParams<DIM> p, const Mrt
       const int s1 = wrap(i1 - L::c(q, 1), p.n1);
       const float* __restrict__ src = p.fin + q * ncell + ((long long)s0 * p.n1 + s1) * p.n2;
       if constexpr (VEC == 1) {
-        f[0][q] = __ldg(src + wrap(i2 - c2, p.n2));
+        f[0][q] = active ? __ldg(src + wrap(i2 - c2, p.n2)) : 1.0f;
       } else {
         float v[VEC];
-        load_vec<VEC>(src + i2, v);
+        if (active) {
+          load_vec<VEC>(src + i2, v);
+        } else {
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) v[k] = 1.0f;
+        }
         if constexpr (c2 == 0) {
 #pragma unroll
           for (int k = 0; k < VEC; ++k) f[k][q] = v[k];
         } else if constexpr (c2 > 0) {  // new[i2 + k] = old[i2 + k - 1]
           float left = __shfl_up_sync(0xffffffffu, v[VEC - 1], 1);
-          if (lane == 0 || j == 0) left = __ldg(src + (i2 == 0 ? p.n2 - 1 : i2 - 1));
+          if (active && (lane == 0 || j == 0)) left = __ldg(src + (i2 == 0 ? p.n2 - 1 : i2 - 1));
           f[0][q] = left;
 #pragma unroll
           for (int k = 1; k < VEC; ++k) f[k][q] = v[k - 1];
         } else {                        // new[i2 + k] = old[i2 + k + 1]
           float right = __shfl_down_sync(0xffffffffu, v[0], 1);
-          if (lane == 31 || j == nv - 1) right = __ldg(src + (i2 + VEC == p.n2 ? 0 : i2 + VEC));
+          if (active && (lane == 31 || j == nv - 1)) right = __ldg(src + (i2 + VEC == p.n2 ? 0 : i2 + VEC));
           f[VEC - 1][q] = right;
 #pragma unroll
           for (int k = 0; k < VEC - 1; ++k) f[k][q] = v[k + 1];
         }
       }
     });
-    if (p.mask) {  // obstacle_bounce_back on the streamed populations (lbm/boundary/bb.py:110)
+    if (p.mask && active) {  // obstacle_bounce_back on the streamed populations (lbm/boundary/bb.py:110)
 #pragma unroll
       for (int k = 0; k < VEC; ++k) {
         if (p.mask[cell + k]) {
@@ -212,15 +124,18 @@ __global__ void __launch_bounds__(256) k_step(const StepParams<DIM> p, const Mrt
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
       float v[VEC];
-      load_vec<VEC>(p.fin + q * ncell + cell, v);
+      if (active) {
+        load_vec<VEC>(p.fin + q * ncell + cell, v);
+      } else {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) v[k] = 1.0f;
+      }
 #pragma unroll
       for (int k = 0; k < VEC; ++k) f[k][q] = v[k];
     }
   }
 
-  if (p.do_collide) {
-    int worg[3] = {p.worg[0], p.worg[1], p.worg[2]};
-    if (p.gwin && p.body) { worg[0] = p.body->origin[0]; worg[1] = p.body->origin[1]; worg[2] = p.body->origin[2]; }
+  if (p.do_collide && active) {
     bool rows_inside;
     int wbase;
     window_rows<DIM>(p, worg, i0, i1, rows_inside, wbase);
@@ -308,8 +223,8 @@ __global__ void k_lines_collide(const StepParams<DIM> p, const MrtMats<DIM, COLL
   float f[L::Q], g[L::D];
 #pragma unroll
   for (int q = 0; q < L::Q; ++q) f[q] = p.fout[q * ncell + cell];
-  int worg[3] = {p.worg[0], p.worg[1], p.worg[2]};
-  if (p.gwin && p.body) { worg[0] = p.body->origin[0]; worg[1] = p.body->origin[1]; worg[2] = p.body->origin[2]; }
+  int worg[3];
+  window_origin<DIM>(p, worg);
   bool rows_inside;
   int wbase;
   window_rows<DIM>(p, worg, c[0], c[1], rows_inside, wbase);
@@ -321,28 +236,14 @@ __global__ void k_lines_collide(const StepParams<DIM> p, const MrtMats<DIM, COLL
 
 // u on the IB window from the streamed (and masked) state: feeds vsb_ib_mdf.
 template <int DIM>
-__global__ void k_window_moments(const StepParams<DIM> p, int follow, float o0x, float o0y, float o0z, float* __restrict__ u_win,
-                                 VsbBodyState* body) {
+__global__ void k_window_moments(const StepParams<DIM> p, float* __restrict__ u_win) {
   using L = Lat<DIM>;
-  const float o0[3] = {o0x, o0y, o0z};
-  int org[3] = {0, 0, 0};
-  const int n[3] = {p.n0, p.n1, p.n2};
-#pragma unroll
-  for (int d = 0; d < L::D; ++d) {
-    const float shifted = o0[d] + ((body && follow) ? body->d[d] : 0.f);
-    if (follow == 2) {   // clip(floor(.)): examples/3d/oscillating_cylinder.py:241-243
-      int o = (int)floorf(shifted);
-      o = max(0, min(o, n[d + L::A0] - p.wsz[d]));
-      org[d] = o;
-    } else {             // astype(int32): examples/2d/vortex_induced_vibration.py:104-105
-      org[d] = (int)shifted;
-    }
-  }
+  int org[3];
+  window_origin<DIM>(p, org);
   long long wcells = 1;
 #pragma unroll
   for (int d = 0; d < L::D; ++d) wcells *= p.wsz[d];
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t == 0 && body) { body->origin[0] = org[0]; body->origin[1] = org[1]; body->origin[2] = org[2]; }
   if (t >= wcells) return;
   int rel[3] = {0, 0, 0};
   long long r = t;
@@ -351,31 +252,77 @@ __global__ void k_window_moments(const StepParams<DIM> p, int follow, float o0x,
   int c[3] = {0, 0, 0};
 #pragma unroll
   for (int d = 0; d < L::D; ++d) c[d + L::A0] = org[d] + rel[d];
-  const long long ncell = (long long)p.n0 * p.n1 * p.n2;
-  float f[L::Q];
-#pragma unroll
-  for (int q = 0; q < L::Q; ++q) {
-    const int s0 = p.do_stream ? wrap(c[0] - L::c(q, 0), p.n0) : c[0];
-    const int s1 = p.do_stream ? wrap(c[1] - L::c(q, 1), p.n1) : c[1];
-    const int s2 = p.do_stream ? wrap(c[2] - L::c(q, 2), p.n2) : c[2];
-    f[q] = p.fin[q * ncell + ((long long)s0 * p.n1 + s1) * p.n2 + s2];
-  }
-  if (p.do_stream && p.mask && p.mask[((long long)c[0] * p.n1 + c[1]) * p.n2 + c[2]]) {
-    float tq[L::Q];
-#pragma unroll
-    for (int q = 0; q < L::Q; ++q) tq[q] = f[q];
-#pragma unroll
-    for (int q = 0; q < L::Q; ++q) f[q] = tq[L::opp(q)];
-  }
-  float rho, u[L::D];
+  float f[L::Q], rho, u[L::D];
+  pull_cell<DIM>(p, c[0], c[1], c[2], f, true);
   moments<DIM>(f, rho, u);
 #pragma unroll
   for (int d = 0; d < L::D; ++d) u_win[d * wcells + t] = u[d];
 }
 
+// Wall layer of one face in one kernel: pull, face operation, (mask), collide, store.  Only for face operations
+// that are independent of each other (see vsb_edge_fused_supported), so no ordering between launches is needed.
+template <int DIM, int COLL, int LOC>
+__global__ void k_edge_fused(const StepParams<DIM> p, const MrtMats<DIM, COLL == VSB_COLL_MRT> mm, int wall_layer, int kind,
+                             int wrap_kind, WallVals w, int mask_before) {
+  using L = Lat<DIM>;
+  using G = FaceGeom<DIM, LOC>;
+  constexpr int Q = L::Q, D = L::D;
+  const int n[3] = {p.n0, p.n1, p.n2};
+  const long long nface = (long long)n[G::TA] * n[G::TB];
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nface) return;
+  int c[3];
+  c[G::TA] = (int)(k / n[G::TB]);
+  c[G::TB] = (int)(k % n[G::TB]);
+  c[G::AX] = wall_layer;
+  if (c[L::A0] < p.r_begin || c[L::A0] >= p.r_end) return;
+  const long long ncell = (long long)p.n0 * p.n1 * p.n2;
+  const long long cell = ((long long)c[0] * p.n1 + c[1]) * p.n2 + c[2];
+  float fw[Q], fn[Q];
+  pull_cell<DIM>(p, c[0], c[1], c[2], fw, mask_before != 0);
+  if (bc_needs_neighbor(kind, wrap_kind)) {
+    int cn[3] = {c[0], c[1], c[2]};
+    cn[G::AX] += G::SIGN;
+    pull_cell<DIM>(p, cn[0], cn[1], cn[2], fn, mask_before != 0);
+  } else {
+#pragma unroll
+    for (int q = 0; q < Q; ++q) fn[q] = 0.f;
+  }
+  float uw[D], gw[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) { uw[d] = wv(w.u[d], k); gw[d] = wv(w.g[d], k); }
+  if (kind == VSB_BC_BOUNCE_BACK || kind == VSB_BC_SPECULAR) {
+    float pre[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) pre[q] = p.fin[q * ncell + cell];
+    apply_face_reflect<DIM, LOC>(fw, pre, kind == VSB_BC_SPECULAR ? 1 : 0, uw);
+  } else {
+    apply_face_bc<DIM, LOC>(fw, fn, kind, wrap_kind, wv(w.rho, k), uw, gw);
+  }
+  if (!mask_before && p.mask && p.mask[cell]) {
+    float t[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) t[q] = fw[q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) fw[q] = t[L::opp(q)];
+  }
+  if (p.do_collide) {
+    int worg[3];
+    window_origin<DIM>(p, worg);
+    bool rows_inside;
+    int wbase;
+    float g[D];
+    window_rows<DIM>(p, worg, c[0], c[1], rows_inside, wbase);
+    cell_force<DIM>(p, worg, rows_inside, wbase, c[2], g);
+    collide_cell<DIM, COLL>(fw, g, p.forcing, p.rx, mm);
+  }
+#pragma unroll
+  for (int q = 0; q < Q; ++q) p.fout[q * ncell + cell] = fw[q];
+}
+
 // ----------------------------------------------------------------------------- host side
 template <int DIM>
-static int fill_params(const VsbStepArgs& a, StepParams<DIM>& p) {
+int fill_params(const VsbStepArgs& a, StepParams<DIM>& p) {
   grid_axes(a.grid, p.n0, p.n1, p.n2);
   VSB_REQUIRE(p.n0 > 0 && p.n1 > 0 && p.n2 > 0, "vsb_step: bad grid");
   const int nrows = (DIM == 2) ? p.n1 : p.n0;
@@ -389,8 +336,12 @@ static int fill_params(const VsbStepArgs& a, StepParams<DIM>& p) {
   VSB_REQUIRE(a.forcing >= VSB_FORCE_NONE && a.forcing <= VSB_FORCE_GUO, "vsb_step: unknown forcing %d", a.forcing);
   p.rx = make_relax(a.omega);
   for (int d = 0; d < 3; ++d) { p.g0[d] = a.g_uniform[d]; p.worg[d] = a.win_origin[d]; p.wsz[d] = a.win_size[d]; }
-  p.gwin = a.g_win; p.body = a.body; p.mask = nullptr;
+  p.gwin = a.g_win; p.body = a.body; p.parity = a.parity & 1; p.mask = nullptr;
   if (a.g_win) for (int d = 0; d < DIM; ++d) VSB_REQUIRE(a.win_size[d] > 0, "vsb_step: empty force window");
+  VSB_REQUIRE(a.band >= 0 && a.band <= 2, "vsb_step: band must be 0, 1 or 2");
+  VSB_REQUIRE(a.band == 0 || a.win_size[0] > 0, "vsb_step: band mode needs a force window");
+  p.band = a.band;
+  p.n_skip = 0;
   int n_mask = 0;
   for (int i = 0; i < a.n_post; ++i)
     if (a.post[i].kind == VSB_POST_MASK) { p.mask = a.post[i].mask; ++n_mask; }
@@ -398,27 +349,139 @@ static int fill_params(const VsbStepArgs& a, StepParams<DIM>& p) {
   VSB_REQUIRE(n_mask == 0 || p.mask, "vsb_step: mask op without a mask");
   return VSB_OK;
 }
+template int fill_params<2>(const VsbStepArgs&, StepParams<2>&);
+template int fill_params<3>(const VsbStepArgs&, StepParams<3>&);
 
 template <int DIM, int COLL>
-static int step_impl(const VsbStepArgs& a, cudaStream_t s) {
-  constexpr bool MRT = (COLL == VSB_COLL_MRT);
-  constexpr int Q = Lat<DIM>::Q;
-  StepParams<DIM> p;
-  if (int rc = fill_params<DIM>(a, p)) return rc;
-  MrtMats<DIM, MRT> mm;
-  if constexpr (MRT) {
-    VSB_REQUIRE(a.mrt_op_host || !a.do_collide, "vsb_step: MRT collision needs mrt_op_host");
-    VSB_REQUIRE(a.forcing != VSB_FORCE_GUO || a.mrt_fop_host || !a.do_collide, "vsb_step: MRT + Guo forcing needs mrt_fop_host");
+static void fill_mats(const VsbStepArgs& a, MrtMats<DIM, COLL == VSB_COLL_MRT>& mm) {
+  if constexpr (COLL == VSB_COLL_MRT) {
+    constexpr int Q = Lat<DIM>::Q;
     for (int i = 0; i < Q * Q; ++i) {
       mm.A.a[i] = a.mrt_op_host ? a.mrt_op_host[i] : 0.f;
       mm.B.a[i] = a.mrt_fop_host ? a.mrt_fop_host[i] : 0.f;
+    }
+  }
+}
+
+static int check_mrt(const VsbStepArgs& a) {
+  if (a.collision != VSB_COLL_MRT || !a.do_collide) return VSB_OK;
+  VSB_REQUIRE(a.mrt_op_host, "vsb_step: MRT collision needs mrt_op_host");
+  VSB_REQUIRE(a.forcing != VSB_FORCE_GUO || a.mrt_fop_host, "vsb_step: MRT + Guo forcing needs mrt_fop_host");
+  return VSB_OK;
+}
+
+// Wall layer (array axis, layer index) of a face operation for this launch's row range.
+template <int DIM>
+static void wall_of(const StepParams<DIM>& p, int loc, int& ax, int& wall, int& extent) {
+  const int n[3] = {p.n0, p.n1, p.n2};
+  ax = loc / 2 + Lat<DIM>::A0;
+  const int lo = (ax == Lat<DIM>::A0) ? p.r_begin : 0, hi = (ax == Lat<DIM>::A0) ? p.r_end : n[ax];
+  wall = (loc % 2 == 0) ? lo : hi - 1;
+  extent = hi - lo;
+}
+
+// Face operations are independent when they sit on faces normal to ONE non-contiguous array axis (so wall cells of
+// different operations never coincide and no operation reads a layer another one writes).
+template <int DIM>
+static bool edges_independent(const VsbStepArgs& a, const StepParams<DIM>& p, int& mask_before) {
+  int axis = -1, n_bc = 0, first_mask = -1, last_bc = -1, first_bc = -1;
+  bool seen[6] = {false, false, false, false, false, false};
+  for (int i = 0; i < a.n_post; ++i) {
+    const VsbPostOp& op = a.post[i];
+    if (op.kind == VSB_POST_MASK) { first_mask = i; continue; }
+    if (op.loc < 0 || op.loc >= 2 * DIM || seen[op.loc]) return false;
+    seen[op.loc] = true;
+    int ax, wall, extent;
+    wall_of<DIM>(p, op.loc, ax, wall, extent);
+    if (ax == 2 || extent < 4) return false;
+    if (axis >= 0 && ax != axis) return false;
+    axis = ax;
+    if (first_bc < 0) first_bc = i;
+    last_bc = i;
+    ++n_bc;
+  }
+  if (n_bc == 0) return false;
+  mask_before = 0;
+  if (first_mask >= 0) {
+    if (first_mask < first_bc) mask_before = 1;
+    else if (first_mask > last_bc) mask_before = 0;
+    else return false;
+  }
+  return true;
+}
+
+template <int DIM, int COLL, int LOC>
+static int launch_edge(const StepParams<DIM>& p, const MrtMats<DIM, COLL == VSB_COLL_MRT>& mm, const VsbPostOp& op,
+                       int mask_before, cudaStream_t s) {
+  using G = FaceGeom<DIM, LOC>;
+  const int n[3] = {p.n0, p.n1, p.n2};
+  int ax, wall, extent;
+  wall_of<DIM>(p, op.loc, ax, wall, extent);
+  WallVals w;
+  w.rho = op.rho;
+  for (int d = 0; d < 3; ++d) { w.u[d] = op.u[d]; w.g[d] = op.g[d]; }
+  const long long nface = (long long)n[G::TA] * n[G::TB];
+  k_edge_fused<DIM, COLL, LOC><<<blocks_for(nface, 128), 128, 0, s>>>(p, mm, wall, op.kind, op.wrap, w, mask_before);
+  VSB_LAUNCH_CHECK("vsb_edge_fused");
+  return VSB_OK;
+}
+
+template <int DIM, int COLL>
+static int edge_impl(const VsbStepArgs& a, cudaStream_t s, bool query_only, int* supported) {
+  StepParams<DIM> p;
+  if (int rc = fill_params<DIM>(a, p)) return rc;
+  int mask_before = 0;
+  const bool ok = a.do_stream && edges_independent<DIM>(a, p, mask_before);
+  if (supported) *supported = ok ? 1 : 0;
+  if (query_only) return VSB_OK;
+  VSB_REQUIRE(ok, "vsb_edge_fused: the face operations are not independent; use the ordered fix-up (edges = 0)");
+  if (int rc = check_mrt(a)) return rc;
+  MrtMats<DIM, COLL == VSB_COLL_MRT> mm;
+  fill_mats<DIM, COLL>(a, mm);
+  for (int i = 0; i < a.n_post; ++i) {
+    const VsbPostOp& op = a.post[i];
+    if (op.kind == VSB_POST_MASK) continue;
+    int rc = VSB_OK;
+    if constexpr (DIM == 2) {
+      rc = op.loc == 0 ? launch_edge<2, COLL, 0>(p, mm, op, mask_before, s) : launch_edge<2, COLL, 1>(p, mm, op, mask_before, s);
+    } else {
+      switch (op.loc) {
+        case 0: rc = launch_edge<3, COLL, 0>(p, mm, op, mask_before, s); break;
+        case 1: rc = launch_edge<3, COLL, 1>(p, mm, op, mask_before, s); break;
+        case 2: rc = launch_edge<3, COLL, 2>(p, mm, op, mask_before, s); break;
+        default: rc = launch_edge<3, COLL, 3>(p, mm, op, mask_before, s); break;
+      }
+    }
+    if (rc) return rc;
+  }
+  return VSB_OK;
+}
+
+template <int DIM, int COLL>
+static int step_impl(const VsbStepArgs& a, cudaStream_t s) {
+  StepParams<DIM> p;
+  if (int rc = fill_params<DIM>(a, p)) return rc;
+  if (int rc = check_mrt(a)) return rc;
+  MrtMats<DIM, COLL == VSB_COLL_MRT> mm;
+  fill_mats<DIM, COLL>(a, mm);
+  const bool have_ops = a.n_post > 0 && a.do_stream;
+  if (a.edges == 1 && have_ops) {
+    int mask_before = 0;
+    VSB_REQUIRE(edges_independent<DIM>(a, p, mask_before), "vsb_step: edges = 1 needs independent face operations");
+    for (int i = 0; i < a.n_post; ++i) {
+      if (a.post[i].kind == VSB_POST_MASK) continue;
+      int ax, wall, extent;
+      wall_of<DIM>(p, a.post[i].loc, ax, wall, extent);
+      VSB_REQUIRE(p.n_skip < 2, "vsb_step: too many wall layers");
+      p.skip_axis[p.n_skip] = ax; p.skip_layer[p.n_skip] = wall; ++p.n_skip;
     }
   }
   int vec = a.vec;
   if (vec == 0) vec = (DIM == 2) ? 4 : 2;
   while (vec > 1 && (p.n2 % vec != 0 || ((uintptr_t)a.f_in % (4 * vec)) || ((uintptr_t)a.f_out % (4 * vec)))) vec >>= 1;
   VSB_REQUIRE(vec == 1 || vec == 2 || vec == 4, "vsb_step: vec must be 0, 1, 2 or 4");
-  const long long rows = (DIM == 2) ? (long long)(p.r_end - p.r_begin) : (long long)(p.r_end - p.r_begin) * p.n1;
+  const int nrow = (p.band == 2) ? std::min(p.wsz[0], p.r_end - p.r_begin) : p.r_end - p.r_begin;
+  const long long rows = (DIM == 2) ? (long long)nrow : (long long)nrow * p.n1;
   const long long total = rows * (p.n2 / vec);
   constexpr int kBlock = 256;
   const unsigned nb = blocks_for(total, kBlock);
@@ -427,7 +490,8 @@ static int step_impl(const VsbStepArgs& a, cudaStream_t s) {
   else k_step<DIM, COLL, 1><<<nb, kBlock, 0, s>>>(p, mm);
   VSB_LAUNCH_CHECK("vsb_step (fused kernel)");
 
-  if (a.n_post == 0 || !a.do_stream) return VSB_OK;
+  if (!have_ops || a.edges == 1) return VSB_OK;
+  VSB_REQUIRE(a.band == 0, "vsb_step: the ordered wall fix-up (edges = 0) cannot be combined with band modes");
   // layers touched by face operations: wall layer and adjacent fluid layer of each face
   LineSet ls;
   ls.n = 0;
@@ -436,11 +500,10 @@ static int step_impl(const VsbStepArgs& a, cudaStream_t s) {
     const VsbPostOp& op = a.post[i];
     if (op.kind == VSB_POST_MASK) continue;
     VSB_REQUIRE(op.loc >= 0 && op.loc < 2 * DIM, "vsb_step: loc %d is not a face of a %d-D grid", op.loc, DIM);
-    const int ax = op.loc / 2 + Lat<DIM>::A0;
-    const bool low = (op.loc % 2 == 0);
-    const int lo = (ax == Lat<DIM>::A0) ? p.r_begin : 0, hi = (ax == Lat<DIM>::A0) ? p.r_end : n[ax];
-    VSB_REQUIRE(hi - lo >= 2, "vsb_step: fewer than 2 layers along the normal of face %d", op.loc);
-    const int layers[2] = {low ? lo : hi - 1, low ? lo + 1 : hi - 2};
+    int ax, wall, extent;
+    wall_of<DIM>(p, op.loc, ax, wall, extent);
+    VSB_REQUIRE(extent >= 2, "vsb_step: fewer than 2 layers along the normal of face %d", op.loc);
+    const int layers[2] = {wall, wall + ((op.loc % 2 == 0) ? 1 : -1)};
     for (int l = 0; l < 2; ++l) {
       bool seen = false;
       for (int e = 0; e < ls.n; ++e) seen = seen || (ls.axis[e] == ax && ls.layer[e] == layers[l]);
@@ -473,28 +536,30 @@ static int step_impl(const VsbStepArgs& a, cudaStream_t s) {
 }
 
 template <int DIM>
-static int step_dispatch(const VsbStepArgs& a, cudaStream_t s) {
+static int step_dispatch(const VsbStepArgs& a, cudaStream_t s, int what, int* supported) {
+  // what: 0 step, 1 fused wall kernel, 2 query support of the fused wall kernel
   switch (a.collision) {
-    case VSB_COLL_BGK: return step_impl<DIM, VSB_COLL_BGK>(a, s);
-    case VSB_COLL_MRT: return step_impl<DIM, VSB_COLL_MRT>(a, s);
-    case VSB_COLL_KBC: return step_impl<DIM, VSB_COLL_KBC>(a, s);
-    case VSB_COLL_REG: return step_impl<DIM, VSB_COLL_REG>(a, s);
+    case VSB_COLL_BGK: return what ? edge_impl<DIM, VSB_COLL_BGK>(a, s, what == 2, supported) : step_impl<DIM, VSB_COLL_BGK>(a, s);
+    case VSB_COLL_MRT: return what ? edge_impl<DIM, VSB_COLL_MRT>(a, s, what == 2, supported) : step_impl<DIM, VSB_COLL_MRT>(a, s);
+    case VSB_COLL_KBC: return what ? edge_impl<DIM, VSB_COLL_KBC>(a, s, what == 2, supported) : step_impl<DIM, VSB_COLL_KBC>(a, s);
+    case VSB_COLL_REG: return what ? edge_impl<DIM, VSB_COLL_REG>(a, s, what == 2, supported) : step_impl<DIM, VSB_COLL_REG>(a, s);
     default: VSB_REQUIRE(false, "vsb_step: unknown collision %d", a.collision);
   }
 }
 
 template <int DIM>
-static int window_impl(const VsbStepArgs& a, int follow, const float* o0, float* u_win, VsbBodyState* body, cudaStream_t s) {
+static int window_impl(const VsbStepArgs& a, float* u_win, cudaStream_t s) {
   StepParams<DIM> p;
   VsbStepArgs b = a;
   if (!b.f_out) b.f_out = u_win;  // unused by this kernel; only has to differ from f_in
+  b.band = 0;
   if (int rc = fill_params<DIM>(b, p)) return rc;
   long long wcells = 1;
   for (int d = 0; d < DIM; ++d) {
     VSB_REQUIRE(a.win_size[d] > 0, "vsb_ib_window_moments: empty window");
     wcells *= a.win_size[d];
   }
-  k_window_moments<DIM><<<blocks_for(wcells, 128), 128, 0, s>>>(p, follow, o0[0], o0[1], o0[2], u_win, body);
+  k_window_moments<DIM><<<blocks_for(wcells, 128), 128, 0, s>>>(p, u_win);
   VSB_LAUNCH_CHECK("vsb_ib_window_moments");
   return VSB_OK;
 }
@@ -503,24 +568,39 @@ static int window_impl(const VsbStepArgs& a, int follow, const float* o0, float*
 
 using namespace vsb;
 
+static int check_step_args(const VsbStepArgs* args, const char* who) {
+  VSB_REQUIRE(args != nullptr, "%s: null args", who);
+  VSB_REQUIRE(args->grid.dim == 2 || args->grid.dim == 3, "dim must be 2 or 3, got %d", args->grid.dim);
+  VSB_REQUIRE(args->n_post >= 0 && (args->n_post == 0 || args->post), "%s: bad post list", who);
+  return VSB_OK;
+}
+
 extern "C" {
 
 int vsb_step(const VsbStepArgs* args, vsb_stream_t stream) {
-  VSB_REQUIRE(args != nullptr, "vsb_step: null args");
-  VSB_REQUIRE(args->grid.dim == 2 || args->grid.dim == 3, "dim must be 2 or 3, got %d", args->grid.dim);
-  VSB_REQUIRE(args->n_post >= 0 && (args->n_post == 0 || args->post), "vsb_step: bad post list");
+  if (int rc = check_step_args(args, "vsb_step")) return rc;
   VSB_REQUIRE(args->do_stream || args->do_collide, "vsb_step: nothing to do");
-  return args->grid.dim == 2 ? step_dispatch<2>(*args, (cudaStream_t)stream) : step_dispatch<3>(*args, (cudaStream_t)stream);
+  return args->grid.dim == 2 ? step_dispatch<2>(*args, (cudaStream_t)stream, 0, nullptr)
+                             : step_dispatch<3>(*args, (cudaStream_t)stream, 0, nullptr);
 }
 
-int vsb_ib_window_moments(const VsbStepArgs* args, int follow, const float win_origin0[3], float* u_win, VsbBodyState* body,
-                          vsb_stream_t stream) {
-  VSB_REQUIRE(args && win_origin0 && u_win, "vsb_ib_window_moments: null argument");
+int vsb_edge_fused(const VsbStepArgs* args, vsb_stream_t stream) {
+  if (int rc = check_step_args(args, "vsb_edge_fused")) return rc;
+  return args->grid.dim == 2 ? step_dispatch<2>(*args, (cudaStream_t)stream, 1, nullptr)
+                             : step_dispatch<3>(*args, (cudaStream_t)stream, 1, nullptr);
+}
+
+int vsb_edge_fused_supported(const VsbStepArgs* args) {
+  if (check_step_args(args, "vsb_edge_fused_supported")) return 0;
+  int ok = 0;
+  const int rc = args->grid.dim == 2 ? step_dispatch<2>(*args, nullptr, 2, &ok) : step_dispatch<3>(*args, nullptr, 2, &ok);
+  return rc == VSB_OK ? ok : 0;
+}
+
+int vsb_ib_window_moments(const VsbStepArgs* args, float* u_win, vsb_stream_t stream) {
+  VSB_REQUIRE(args && u_win, "vsb_ib_window_moments: null argument");
   VSB_REQUIRE(args->grid.dim == 2 || args->grid.dim == 3, "dim must be 2 or 3, got %d", args->grid.dim);
-  VSB_REQUIRE(follow >= 0 && follow <= 2, "follow must be 0, 1 or 2");
-  VSB_REQUIRE(follow == 0 || body, "a moving window needs a body state");
-  return args->grid.dim == 2 ? window_impl<2>(*args, follow, win_origin0, u_win, body, (cudaStream_t)stream)
-                             : window_impl<3>(*args, follow, win_origin0, u_win, body, (cudaStream_t)stream);
+  return args->grid.dim == 2 ? window_impl<2>(*args, u_win, (cudaStream_t)stream) : window_impl<3>(*args, u_win, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,204 @@
+// Device code shared by the fused step kernels (vsb_step.cu) and the fused IB kernel (vsb_ibfused.cu).
+#pragma once
+
+#include <utility>
+
+#include "vsb_common.cuh"
+#include "vsb_internal.h"
+
+namespace vsb {
+
+// compile-time loop: body(std::integral_constant<int, I>) for I in [0, N)
+template <class F, int... I>
+__device__ __forceinline__ void static_for_impl(F&& body, std::integer_sequence<int, I...>) {
+  (body(std::integral_constant<int, I>{}), ...);
+}
+template <int N, class F>
+__device__ __forceinline__ void static_for(F&& body) {
+  static_for_impl(body, std::make_integer_sequence<int, N>{});
+}
+
+template <int DIM> struct StepParams {
+  int n0, n1, n2;
+  int r_begin, r_end;   // rows of array axis A0 (the slowest real axis) to update
+  const float* fin;
+  float* fout;
+  int do_stream, do_collide, forcing;
+  Relax rx;
+  float g0[3];
+  const float* gwin;
+  int worg[3], wsz[3];
+  const VsbBodyState* body;
+  int parity;
+  const uint8_t* mask;
+  int band;             // 0 all rows, 1 skip the window's x-range, 2 only the window's x-range
+  int n_skip;           // wall layers (normal to a non-contiguous axis) left to the fused wall kernel
+  int skip_axis[2], skip_layer[2];
+};
+
+template <int DIM, bool USED> struct MrtMats { Matrix<Lat<DIM>::Q> A, B; };
+template <int DIM> struct MrtMats<DIM, false> {};
+
+__device__ __forceinline__ int wrap(int i, int n) {
+  i += (i < 0) ? n : 0;
+  i -= (i >= n) ? n : 0;
+  return i;
+}
+
+// Integer origin of the force / IB window for this step.
+template <int DIM>
+__device__ __forceinline__ void window_origin(const StepParams<DIM>& p, int (&worg)[3]) {
+  if (p.body) {
+    worg[0] = p.body->origin2[p.parity][0]; worg[1] = p.body->origin2[p.parity][1]; worg[2] = p.body->origin2[p.parity][2];
+  } else {
+    worg[0] = p.worg[0]; worg[1] = p.worg[1]; worg[2] = p.worg[2];
+  }
+}
+
+// Window origin rule for a displaced body (host and device):
+//   follow 1: astype(int32) truncation      (examples/2d/vortex_induced_vibration.py:104-105)
+//   follow 2: clip(floor(.), 0, N - size)   (examples/3d/oscillating_cylinder.py:241-243)
+__host__ __device__ inline int origin_rule(int follow, float origin0, float d, int grid_n, int win_n) {
+  const float shifted = origin0 + (follow ? d : 0.f);
+  if (follow == 2) {
+    int o = (int)floorf(shifted);
+    o = o < 0 ? 0 : o;
+    return o > grid_n - win_n ? grid_n - win_n : o;
+  }
+  return (int)shifted;
+}
+
+// Body update: h = -force_sum + a*added_mass; Newmark-beta (gamma 1/2, beta 1/4, dt 1); next window origin.
+// (dyn.py:27-51,136; examples/2d/vortex_induced_vibration.py:135-137)      One thread.
+struct BodyUpdate {
+  int n_dof, follow, dim;
+  float origin0[3];
+  int grid_size[3], win_size[3];
+  float denom, k, c, added_mass;   // denom = m + c/2 + k/4 evaluated in double on the host
+};
+
+inline BodyUpdate make_body_update(const VsbBodyParams& bp, int dim) {
+  BodyUpdate u;
+  u.n_dof = bp.n_dof; u.follow = bp.follow; u.dim = dim;
+  for (int d = 0; d < 3; ++d) { u.origin0[d] = bp.origin0[d]; u.grid_size[d] = bp.grid_size[d]; u.win_size[d] = bp.win_size[d]; }
+  u.denom = (float)(bp.m + 0.5 * bp.c + 0.25 * bp.k);
+  u.k = (float)bp.k; u.c = (float)bp.c; u.added_mass = (float)bp.added_mass;
+  return u;
+}
+
+__device__ __forceinline__ void body_update(VsbBodyState* b, const BodyUpdate& u, int parity) {
+  for (int i = 0; i < u.n_dof; ++i) {
+    const float h = -b->force_sum[i] + b->a[i] * u.added_mass;
+    const float v1 = b->v[i] + 0.5f * b->a[i];
+    const float d1 = b->d[i] + b->v[i] + 0.25f * b->a[i];
+    const float a_next = (h - u.c * v1 - u.k * d1) / u.denom;
+    b->h[i] = h;
+    b->a[i] = a_next;
+    b->v[i] = 0.5f * a_next + v1;
+    b->d[i] = 0.25f * a_next + d1;
+  }
+  for (int i = 0; i < 3; ++i) b->force_sum[i] = 0.f;
+  for (int d = 0; d < u.dim; ++d)
+    b->origin2[parity ^ 1][d] = origin_rule(u.follow, u.origin0[d], b->d[d], u.grid_size[d], u.win_size[d]);
+}
+
+// Streamed (pulled) and masked populations of one cell; scalar loads.  With do_stream = 0 the cell itself.
+template <int DIM>
+__device__ __forceinline__ void pull_cell(const StepParams<DIM>& p, int c0, int c1, int c2, float (&f)[Lat<DIM>::Q],
+                                          bool use_mask) {
+  using L = Lat<DIM>;
+  const long long ncell = (long long)p.n0 * p.n1 * p.n2;
+#pragma unroll
+  for (int q = 0; q < L::Q; ++q) {
+    const int s0 = p.do_stream ? wrap(c0 - L::c(q, 0), p.n0) : c0;
+    const int s1 = p.do_stream ? wrap(c1 - L::c(q, 1), p.n1) : c1;
+    const int s2 = p.do_stream ? wrap(c2 - L::c(q, 2), p.n2) : c2;
+    f[q] = __ldg(p.fin + q * ncell + ((long long)s0 * p.n1 + s1) * p.n2 + s2);
+  }
+  if (use_mask && p.do_stream && p.mask && p.mask[((long long)c0 * p.n1 + c1) * p.n2 + c2]) {
+    float t[L::Q];
+#pragma unroll
+    for (int q = 0; q < L::Q; ++q) t[q] = f[q];
+#pragma unroll
+    for (int q = 0; q < L::Q; ++q) f[q] = t[L::opp(q)];
+  }
+}
+
+// Force window lookup, split so that the part that does not depend on the contiguous coordinate is done once
+// per thread: `base` is the flat window index of (c0, c1, 0) and `rows_inside` tells whether the leading
+// coordinates fall inside the window.
+template <int DIM>
+__device__ __forceinline__ void window_rows(const StepParams<DIM>& p, const int (&worg)[3], int c0, int c1,
+                                            bool& rows_inside, int& base) {
+  using L = Lat<DIM>;
+  rows_inside = p.gwin != nullptr;
+  base = 0;
+  const int coord[3] = {c0, c1, 0};
+#pragma unroll
+  for (int d = 0; d < L::D - 1; ++d) {
+    const int rel = coord[d + L::A0] - worg[d];
+    rows_inside = rows_inside && (unsigned)rel < (unsigned)p.wsz[d];
+    base = (base + rel) * p.wsz[d + 1];
+  }
+}
+
+template <int DIM>
+__device__ __forceinline__ void cell_force(const StepParams<DIM>& p, const int (&worg)[3], bool rows_inside, int base,
+                                           int c2, float (&g)[Lat<DIM>::D]) {
+  using L = Lat<DIM>;
+#pragma unroll
+  for (int d = 0; d < L::D; ++d) g[d] = p.g0[d];
+  const int rel = c2 - worg[L::D - 1];
+  if (rows_inside && (unsigned)rel < (unsigned)p.wsz[L::D - 1]) {
+    int wcells = 1;
+#pragma unroll
+    for (int d = 0; d < L::D; ++d) wcells *= p.wsz[d];
+#pragma unroll
+    for (int d = 0; d < L::D; ++d) g[d] += p.gwin[d * wcells + base + rel];
+  }
+}
+
+// moments -> (Guo velocity shift) -> equilibrium -> collision -> forcing, on one cell in registers.
+// Order of operations: examples/2d/poiseuille_channel.py:80-148 (EDM uses the uncorrected velocity,
+// Guo shifts u by g/(2 rho) before the equilibrium).
+template <int DIM, int COLL>
+__device__ __forceinline__ void collide_cell(float (&f)[Lat<DIM>::Q], const float (&g)[Lat<DIM>::D], int forcing,
+                                             const Relax& rx, const MrtMats<DIM, COLL == VSB_COLL_MRT>& mm) {
+  using L = Lat<DIM>;
+  float rho, u[L::D], feq[L::Q];
+  moments<DIM>(f, rho, u);
+  // a zero force contributes exactly nothing (u + 0, f + w*0): skip the work -- bit-identical
+  bool has_g = false;
+#pragma unroll
+  for (int d = 0; d < L::D; ++d) has_g = has_g || (g[d] != 0.f);
+  if (!has_g) forcing = VSB_FORCE_NONE;
+  if (forcing == VSB_FORCE_GUO) {
+#pragma unroll
+    for (int d = 0; d < L::D; ++d) u[d] += g[d] * 0.5f / rho;
+  }
+  equilibrium<DIM>(rho, u, feq);
+  if constexpr (COLL == VSB_COLL_BGK) collide_bgk<DIM>(f, feq, rx);
+  if constexpr (COLL == VSB_COLL_KBC) collide_kbc<DIM>(f, feq, rx);
+  if constexpr (COLL == VSB_COLL_REG) collide_reg<DIM>(f, feq, rx);
+  if constexpr (COLL == VSB_COLL_MRT) collide_mrt<DIM>(f, feq, mm.A);
+  if (forcing != VSB_FORCE_NONE) {
+    float G[L::Q];
+    guo_term<DIM>(g, u, G);
+    if (forcing == VSB_FORCE_EDM) {
+#pragma unroll
+      for (int q = 0; q < L::Q; ++q) f[q] += G[q];
+    } else {
+      if constexpr (COLL == VSB_COLL_MRT) {
+        matvec_add<DIM>(f, mm.B, G);
+      } else {
+#pragma unroll
+        for (int q = 0; q < L::Q; ++q) f[q] += G[q] * rx.guo_scale;
+      }
+    }
+  }
+}
+
+// Fill StepParams from the ABI struct (validation included).  Defined in vsb_step.cu.
+template <int DIM> int fill_params(const VsbStepArgs& a, StepParams<DIM>& p);
+
+}  // namespace vsb

@@ -40,11 +40,14 @@ def _parse_bc(name):
 
 
 class Stepper:
-    def __init__(self, spec, device="cuda", rows=None, vec=0, body=None, dyn_mode="host", follow=1, use_graph=False):
+    def __init__(self, spec, device="cuda", rows=None, vec=0, body=None, dyn_mode="host", follow=1, use_graph=False,
+                 fuse_ib=True, fuse_edges=True, overlap=True):
         """rows: (begin, end) range of the slowest axis that is physical domain (ghost layers outside; slab
         decomposition).  body: dict(m, k, c, added_mass, n_dof=2, d0, v0, a0) for a moving rigid body coupled by
         Newmark-beta; dyn_mode "host" (reference-faithful, one tiny D2H/H2D per step) or "device"
-        (vsb_body_newmark, graph-capturable).  follow: IB window rule for a moving body (1 trunc, 2 clip(floor))."""
+        (vsb_body_newmark, graph-capturable).  follow: IB window rule for a moving body (1 trunc, 2 clip(floor)).
+        fuse_ib / fuse_edges / overlap: use the single-kernel IB path, the single-kernel wall path and concurrent
+        streams when the configuration allows (all three only change scheduling, not arithmetic per cell)."""
         L.lib()
         if not torch.cuda.is_available():
             raise L.VsbError("vivsim_b200.Stepper needs a CUDA device (there is no CPU fallback)")
@@ -65,6 +68,9 @@ class Stepper:
         self._tmp = None
         self._graph = None
         self.n_launch_per_step = 0
+        self._parity = 0
+        self._want = dict(fuse_ib=bool(fuse_ib), fuse_edges=bool(fuse_edges), overlap=bool(overlap))
+        self._side = None
 
         a = L.VsbStepArgs()
         a.grid = L.grid_of(self.shape)
@@ -135,7 +141,18 @@ class Stepper:
         a.n_post = len(ops)
         a.post = self._post
         self._args = a
-        self.n_launch_per_step = self._count_launches()
+        lib = L.lib()
+        n_bc = sum(1 for o in ops if o.kind != L.BC["mask"])
+        a.do_stream, a.do_collide = 1, 1
+        a.f_in, a.f_out = self._bufs[0].data_ptr(), self._bufs[1].data_ptr()
+        self.edge_fused = bool(n_bc) and self._want["fuse_edges"] and bool(lib.vsb_edge_fused_supported(C.byref(a)))
+        self.ib_fused = (self.ib is not None and self._want["fuse_ib"]
+                         and bool(lib.vsb_ib_fused_supported(C.byref(self._mdf))))
+        # concurrent branches need every kernel of a step to be independent of launch order
+        self.overlap = (self._want["overlap"] and self.ib is not None and (n_bc == 0 or self.edge_fused))
+        if self.overlap or (self.edge_fused and self._want["overlap"]):
+            self._side = [torch.cuda.Stream(device=self.device) for _ in range(2)]
+        self.n_launch_per_step = self._count_launches(n_bc)
 
     # ------------------------------------------------------------------ setup helpers
     def _init_ib(self, a, body, dyn_mode, follow):
@@ -182,7 +199,6 @@ class Stepper:
         for d in range(dim):
             m.win_origin0[d] = int(np.floor(self.win_origin0[d]))
             m.win_size[d] = self.win_size[d]
-            m.grid_size[d] = self.shape[d]
             a.win_origin[d] = m.win_origin0[d]
             a.win_size[d] = self.win_size[d]
         m.markers0 = self._markers.data_ptr()
@@ -194,6 +210,7 @@ class Stepper:
         m.marker_force = self.marker_force.data_ptr()
         a.g_win = self._g_win.data_ptr()
         self.follow = 0
+        self._bparams = None
         if body is not None:
             self.body = dict(body)
             self.dyn_mode = dyn_mode
@@ -201,18 +218,39 @@ class Stepper:
                 raise ValueError("dyn_mode must be 'host' or 'device'")
             self.follow = int(follow)
             self.n_dof = int(body.get("n_dof", 2))
+            bp = L.VsbBodyParams()
+            bp.n_dof, bp.follow = (self.n_dof if dyn_mode == "device" else 0), self.follow
+            bp.m, bp.k, bp.c, bp.added_mass = (float(body[k]) for k in ("m", "k", "c", "added_mass"))
+            for d in range(3):
+                bp.origin0[d] = self.win_origin0[d] if d < dim else 0.0
+                bp.grid_size[d] = self.shape[d] if d < dim else 1
+                bp.win_size[d] = self.win_size[d] if d < dim else 1
+            self._bparams = bp
             self._body_dev = torch.zeros(L.BODY_BYTES // 4, device=dev, dtype=torch.float32)
             self._body_pin = torch.zeros(L.BODY_BYTES // 4, dtype=torch.float32).pin_memory()
             st = self._body_pin.numpy()
             st[0:self.n_dof] = np.asarray(body.get("d0", np.zeros(self.n_dof)), dtype=np.float32)
             st[3:3 + self.n_dof] = np.asarray(body.get("v0", np.zeros(self.n_dof)), dtype=np.float32)
             st[6:6 + self.n_dof] = np.asarray(body.get("a0", np.zeros(self.n_dof)), dtype=np.float32)
+            org = self._origin_for(st[0:3])
+            ints = st.view(np.int32)
+            ints[15:18] = org
+            ints[18:21] = org
             self._body_dev.copy_(self._body_pin, non_blocking=True)
             m.body = self._body_dev.data_ptr()
-            m.follow = self.follow
             a.body = self._body_dev.data_ptr()
         self._mdf = m
-        self._origin0_c = (C.c_float * 3)(*(list(self.win_origin0) + [0.0] * (3 - dim)))
+
+    def _origin_for(self, d):
+        """Integer window origin for displacement d (same fp32 rule as origin_rule in csrc/vsb_step.cuh)."""
+        out = np.zeros(3, dtype=np.int32)
+        for k in range(self.dim):
+            shifted = np.float32(self.win_origin0[k]) + (np.float32(d[k]) if self.follow else np.float32(0))
+            if self.follow == 2:
+                out[k] = min(max(int(np.floor(shifted)), 0), self.shape[k] - self.win_size[k])
+            else:
+                out[k] = int(shifted)   # truncation toward zero, like astype(int32)
+        return out
 
     def _check_window_clear_of(self, loc):
         if self.ib is None:
@@ -224,14 +262,19 @@ class Stepper:
         if (low and lo <= rb) or (not low and hi >= re):
             raise ValueError(f"the IB window touches the '{loc}' wall layer, which carries a boundary operation")
 
-    def _count_launches(self):
+    def _count_launches(self, n_bc):
         n = 1
-        if self._args.n_post:
-            n_bc = sum(1 for i in range(self._args.n_post) if self._post[i].kind != L.BC["mask"])
-            if n_bc:
-                n += 2 + self._args.n_post
+        if n_bc:
+            n += n_bc if self.edge_fused else 2 + self._args.n_post
         if self.ib is not None:
-            n += 1 + self.n_iter + (1 if self.body is not None and self.dyn_mode == "device" else 0)
+            if self.overlap:
+                n += 1                                    # second launch of the fused kernel (window x-range)
+            if self.ib_fused:
+                n += 1
+            else:
+                n += 1 + self.n_iter
+            if self.body is not None and self.dyn_mode == "device" and not self.ib_fused:
+                n += 1
         return n
 
     # ------------------------------------------------------------------ state access
@@ -264,33 +307,81 @@ class Stepper:
         n = self.n_dof
         return st[0:n].copy(), st[3:3 + n].copy(), st[6:6 + n].copy(), st[9:9 + n].copy()
 
+    def window_origin(self):
+        """Integer IB-window origin that the next step will use."""
+        if self._body_dev is None:
+            return tuple(int(np.floor(o)) for o in self.win_origin0)
+        ints = self._body_dev.cpu().numpy().view(np.int32)
+        return tuple(int(x) for x in ints[15 + 3 * self._parity:15 + 3 * self._parity + self.dim])
+
     def _require_state(self):
         if self._kind is None:
             raise L.VsbError("no state loaded: call set_f(f) first")
 
     # ------------------------------------------------------------------ stepping
     def _launch(self, src, dst, do_stream, do_collide):
+        """Enqueue one pass: (IB force) + fused kernel + wall layers.  Branches that do not depend on each other go
+        to side streams when `overlap` is on: the bulk of the grid does not wait for the immersed boundary."""
         a = self._args
         a.f_in, a.f_out = src.data_ptr(), dst.data_ptr()
         a.do_stream, a.do_collide = do_stream, do_collide
-        lib, st = L.lib(), L.stream()
-        if self.ib is not None and do_collide:
-            self._ib_zero.zero_()
-            L.check(lib.vsb_ib_window_moments(C.byref(a), self.follow, self._origin0_c, L.ptr(self._u_win),
-                                              C.c_void_p(self._body_dev.data_ptr()) if self._body_dev is not None else None,
-                                              st))
-            L.check(lib.vsb_ib_mdf(C.byref(self._mdf), st))
-            if self.body is not None:
-                self._newmark(st)
-        L.check(lib.vsb_step(C.byref(a), st))
+        a.parity = self._parity
+        lib = L.lib()
+        has_ops = a.n_post > 0 and do_stream
+        with_ib = self.ib is not None and do_collide
+        a.edges = 1 if (has_ops and self.edge_fused) else 0
+        a.band = 0
+        if not (self.overlap and with_ib):
+            if with_ib:
+                self._ib_part(L.stream())
+            L.check(lib.vsb_step(C.byref(a), L.stream()))
+            if a.edges:
+                L.check(lib.vsb_edge_fused(C.byref(a), L.stream()))
+        else:
+            main = torch.cuda.current_stream()
+            s_ib, s_edge = self._side
+            s_ib.wait_stream(main)
+            if a.edges:
+                s_edge.wait_stream(main)
+            a.band = 1                                        # everything but the window's x-range
+            L.check(lib.vsb_step(C.byref(a), L.stream()))
+            with torch.cuda.stream(s_ib):                     # IB chain, then the window's x-range
+                self._ib_part(L.stream())
+                a.band = 2
+                L.check(lib.vsb_step(C.byref(a), L.stream()))
+            if a.edges:
+                with torch.cuda.stream(s_edge):
+                    L.check(lib.vsb_edge_fused(C.byref(a), L.stream()))
+                main.wait_stream(s_edge)
+            main.wait_stream(s_ib)
+            a.band = 0
+        if with_ib:
+            self._parity ^= 1
 
-    def _newmark(self, st):
+    def _ib_part(self, st):
+        """Immersed-boundary force of this pass on stream `st` (the current stream), then the body update."""
+        lib, a, m = L.lib(), self._args, self._mdf
+        m.parity = self._parity
+        host_body = self.body is not None and self.dyn_mode == "host"
+        bp = C.byref(self._bparams) if self._bparams is not None else None
+        if self.ib_fused:
+            L.check(lib.vsb_ib_fused(C.byref(a), C.byref(m), bp, st))
+        else:
+            self._ib_zero.zero_()
+            band = a.band
+            a.band = 0
+            L.check(lib.vsb_ib_window_moments(C.byref(a), L.ptr(self._u_win), st))
+            a.band = band
+            L.check(lib.vsb_ib_mdf(C.byref(m), st))
+            if self.body is not None and not host_body:
+                L.check(lib.vsb_body_newmark(C.c_void_p(self._body_dev.data_ptr()), bp, self._parity, st))
+        if host_body:
+            self._host_newmark()
+
+    def _host_newmark(self):
+        """Rigid-body ODE on the host as in the reference recipe: h = sum(-F) + a * added_mass; Newmark-beta.
+        One 84-byte device->host read and one host->device write on the current stream."""
         b = self.body
-        if self.dyn_mode == "device":
-            L.check(L.lib().vsb_body_newmark(C.c_void_p(self._body_dev.data_ptr()), self.n_dof, C.c_double(b["m"]),
-                                             C.c_double(b["k"]), C.c_double(b["c"]), C.c_double(b["added_mass"]), st))
-            return
-        # host ODE as in the reference recipe: h = sum(-F) + a * added_mass ; Newmark-beta
         self._body_pin.copy_(self._body_dev, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         s = self._body_pin.numpy()
@@ -300,6 +391,8 @@ class Stepper:
         a2, v2, d2 = _dyn.newmark(acc, v, d, h, b["m"], b["k"], b["c"])
         s[0:n], s[3:3 + n], s[6:6 + n], s[9:9 + n] = d2, v2, a2, h
         s[12:15] = 0
+        nxt = 15 + 3 * (self._parity ^ 1)
+        s.view(np.int32)[nxt:nxt + 3] = self._origin_for(s[0:3])
         self._body_dev.copy_(self._body_pin, non_blocking=True)
 
     def _advance(self):
@@ -332,7 +425,7 @@ class Stepper:
         if graphable and n >= 2:
             if self._graph is None:
                 self._capture()
-            if self._graph_cur != self._cur:   # the graph was recorded starting from the other buffer
+            if self._graph_cur != self._cur or self._graph_parity != self._parity:   # recorded from the other buffer / parity
                 self._advance()
                 n -= 1
             while n >= 2:
@@ -358,6 +451,7 @@ class Stepper:
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         self._graph_cur = self._cur
+        self._graph_parity = self._parity
         with torch.cuda.graph(g):
             self._advance(); self._advance()
         torch.cuda.synchronize()
