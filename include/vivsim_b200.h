@@ -112,6 +112,7 @@ typedef struct {
   float h[3];             /* last total hydrodynamic force on the body: sum over markers of -F + a*added_mass */
   float force_sum[3];     /* accumulator: sum over markers of +F; cleared by the body update             */
   int origin2[2][3];      /* integer IB-window origin for step parity 0 / 1                               */
+  int ticket;             /* CTA arrival counter of the last MDF stage (0 between steps)                  */
 } VsbBodyState;
 
 /* Structural parameters and window rule of a translating rigid body (reference dyn.py:5-51 with gamma = 1/2,
@@ -126,16 +127,19 @@ typedef struct {
 } VsbBodyParams;
 
 /* multi_direct_forcing with the stencil computed on the fly (ib/mdf.py:10-64 + ib/stencil.py:27-51 /
- * ib3d/stencil.py:36-57), marker-parallel, on a window of the grid.
- *   u_win         (dim, wnx, wny[, wnz]) velocity on the window (read)
- *   g_win         same shape, ZEROED by the caller; receives spread(total marker force)
- *   scratch       (max(n_iter-1,0), dim, window) ZEROED by the caller
+ * ib3d/stencil.py:36-57), marker-parallel over many CTAs, on a window of the grid: n_iter launches.
+ * The velocity at the stencil points comes straight from the streamed populations of `args` (f_in, do_stream, mask),
+ * so no velocity field is materialised.  The last stage adds the total force to body->force_sum and, when
+ * params->n_dof > 0, the last CTA performs the body update of vsb_body_newmark.
+ *   g_win / scratch            this step's buffers: force field (dim, window) and (n_iter-1) x (dim, window) work
+ *                              fields; they must be ZERO on entry
+ *   g_win_next / scratch_next  the buffers the NEXT step will use: cleared by this call (double-buffer by step
+ *                              parity, so nothing is cleared while a kernel of this step may still read it)
  *   markers0      (M, dim) marker coordinates; the body state adds its displacement
  *   u_target      (M, dim) or NULL -> every marker targets the body velocity (body != NULL) or 0
  *   ds            (M) when ds_ptr != NULL else the scalar ds_value
  *   marker_u, marker_force (M, dim) work / output arrays (marker_force = +F; reaction = -F)
- *   body          device VsbBodyState or NULL (fixed body at markers0, window origin = win_origin0)
- * Launches n_iter kernels on `stream`. */
+ *   body          device VsbBodyState or NULL (fixed body at markers0, window origin = win_origin0) */
 typedef struct {
   int dim, delta_kind, n_iter, parity;
   int64_t n_markers;
@@ -144,15 +148,14 @@ typedef struct {
   const float* u_target;
   const float* ds_ptr;
   float ds_value;
-  float* u_win;
   float* g_win;
+  float* g_win_next;
   float* scratch;
+  float* scratch_next;
   float* marker_u;
   float* marker_force;
   VsbBodyState* body;
 } VsbMdfArgs;
-
-int vsb_ib_mdf(const VsbMdfArgs* args, vsb_stream_t stream);
 
 /* ---- fused time step ------------------------------------------------------------------- *
  * State convention: `f_in` / `f_out` hold the POST-COLLISION populations S_n = collide(F_n),
@@ -190,6 +193,9 @@ typedef struct {
 
 int vsb_step(const VsbStepArgs* args, vsb_stream_t stream);
 
+int vsb_ib_mdf(const VsbStepArgs* args, const VsbMdfArgs* mdf, const VsbBodyParams* params, vsb_stream_t stream);
+
+
 /* Wall layers in ONE kernel per face: pull the streamed populations of the wall cell (and of the adjacent fluid
  * cell when the operation reads it), apply the face operation, collide, store.  Valid when the face operations are
  * independent of each other: all on faces normal to one non-contiguous axis, at least 3 layers apart.
@@ -197,7 +203,7 @@ int vsb_step(const VsbStepArgs* args, vsb_stream_t stream);
 int vsb_edge_fused_supported(const VsbStepArgs* args);
 int vsb_edge_fused(const VsbStepArgs* args, vsb_stream_t stream);
 
-/* Velocity of the streamed state on the IB window: u_win <- u(stream(f_in)) (feeds vsb_ib_mdf).  Uses grid, f_in,
+/* Velocity of the streamed state on the IB window: u_win <- u(stream(f_in)) (diagnostic; vsb_ib_mdf does not need it).  Uses grid, f_in,
  * do_stream, win_origin / body + parity, win_size and the mask of `args`.  The window must not contain cells of a
  * face that carries a boundary operation. */
 int vsb_ib_window_moments(const VsbStepArgs* args, float* u_win, vsb_stream_t stream);

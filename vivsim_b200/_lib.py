@@ -43,10 +43,10 @@ class VsbPostOp(C.Structure):
 
 class VsbBodyState(C.Structure):
     _fields_ = [("d", C.c_float * 3), ("v", C.c_float * 3), ("a", C.c_float * 3), ("h", C.c_float * 3),
-                ("force_sum", C.c_float * 3), ("origin2", (C.c_int * 3) * 2)]
+                ("force_sum", C.c_float * 3), ("origin2", (C.c_int * 3) * 2), ("ticket", C.c_int)]
 
 
-BODY_BYTES = C.sizeof(VsbBodyState)   # 15 fp32 + 6 int32 = 84 bytes
+BODY_BYTES = C.sizeof(VsbBodyState)   # 15 fp32 + 7 int32 = 88 bytes
 
 
 class VsbBodyParams(C.Structure):
@@ -59,9 +59,9 @@ class VsbMdfArgs(C.Structure):
     _fields_ = [("dim", C.c_int), ("delta_kind", C.c_int), ("n_iter", C.c_int), ("parity", C.c_int),
                 ("n_markers", C.c_int64), ("win_origin0", C.c_int * 3), ("win_size", C.c_int * 3),
                 ("markers0", C.c_void_p), ("u_target", C.c_void_p),
-                ("ds_ptr", C.c_void_p), ("ds_value", C.c_float), ("u_win", C.c_void_p), ("g_win", C.c_void_p),
-                ("scratch", C.c_void_p), ("marker_u", C.c_void_p), ("marker_force", C.c_void_p),
-                ("body", C.c_void_p)]
+                ("ds_ptr", C.c_void_p), ("ds_value", C.c_float), ("g_win", C.c_void_p), ("g_win_next", C.c_void_p),
+                ("scratch", C.c_void_p), ("scratch_next", C.c_void_p), ("marker_u", C.c_void_p),
+                ("marker_force", C.c_void_p), ("body", C.c_void_p)]
 
 
 class VsbStepArgs(C.Structure):

@@ -63,7 +63,7 @@ __global__ void k_spread(int ncomp, long long ncell, float* __restrict__ grid, l
   for (int c = 0; c < ncomp; ++c) atomicAdd(&grid[c * ncell + i], vals[m * ncomp + c] * wt);
 }
 
-// ----------------------------------------------------------------------------- fused MDF stage
+// ----------------------------------------------------------------------------- MDF stage chain
 struct MdfParams {
   int delta_kind, n_iter, stage, parity;
   long long n_markers;
@@ -72,23 +72,29 @@ struct MdfParams {
   const float* u_target;
   const float* ds_ptr;
   float ds_value;
-  const float* u_win;
-  float* g_win;
-  float* scratch;
+  float* g_win;         // this step's force field (zero on entry of the last stage)
+  float* g_win_next;    // next step's force field: cleared by stage 0
+  float* scratch;       // this step's per-iteration fields, (n_iter - 1) x dim x window
+  float* scratch_next;  // next step's: buffer k is cleared by stage k
   float* marker_u;
   float* marker_force;
   VsbBodyState* body;
+  int update_body;
 };
 
-// Stage k of multi_direct_forcing (ib/mdf.py:31-64):
-//   k = 0     : u_m = interp(u)
+// Stage k of multi_direct_forcing (ib/mdf.py:31-64), one launch per iteration, markers spread over many CTAs:
+//   k = 0     : u at the stencil points = moments of the pulled (streamed, masked) populations, u_m = interp(u)
 //   k > 0     : u_m += interp(0.5 * spread(dF_{k-1}))        (buffer scratch[k-1], filled by stage k-1)
 //   dF_k = (U - u_m) 2 ds ; F += dF_k
-//   k < n-1   : spread dF_k -> scratch[k]     (zeroed by the caller)
-//   k = n-1   : spread F -> g_win             (the last iteration's u_m update is never used by the reference's
-//               outputs, so its spread + interpolate are skipped)
+//   k < n-1   : spread dF_k -> scratch[k]
+//   k = n-1   : spread F -> g_win ; total force -> body ; the last CTA to finish performs the body update
+//               (the last iteration's u_m update is never used by the reference's outputs, so its spread +
+//               interpolate are skipped)
+// Buffers are double-buffered by step parity: while this step accumulates into its own set, every stage clears the
+// matching buffer of the other set, so no memset is needed and nothing is cleared while it may still be read.
 template <int DIM>
-__global__ void k_mdf_stage(MdfParams p) {
+__global__ void k_mdf_stage(const StepParams<DIM> sp, const MdfParams p, const BodyUpdate bu) {
+  using L = Lat<DIM>;
   constexpr int NS = (DIM == 2) ? 16 : 64;   // 4^D stencil points
   constexpr int G = (DIM == 2) ? 16 : 32;    // lanes per marker
   constexpr int PPL = NS / G;                // stencil points per lane
@@ -97,13 +103,27 @@ __global__ void k_mdf_stage(MdfParams p) {
   __syncthreads();
 
   const long long gthread = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
   const long long m = gthread / G;
   const int gl = (int)(gthread % G);
   const bool active = m < p.n_markers;
   const long long wcells = (long long)p.wsize[0] * p.wsize[1] * (DIM == 3 ? p.wsize[2] : 1);
+  const bool last = p.stage == p.n_iter - 1;
+
+  // clear the other parity's buffers for the next step
+  if (p.stage == 0)
+    for (long long i = gthread; i < DIM * wcells; i += nthreads) p.g_win_next[i] = 0.f;
+  if (p.stage < p.n_iter - 1) {
+    float* z = p.scratch_next + (long long)p.stage * DIM * wcells;
+    for (long long i = gthread; i < DIM * wcells; i += nthreads) z[i] = 0.f;
+  }
+
+  int org[3] = {p.origin0[0], p.origin0[1], p.origin0[2]};
+  if (p.body) { org[0] = p.body->origin2[p.parity][0]; org[1] = p.body->origin2[p.parity][1]; org[2] = p.body->origin2[p.parity][2]; }
 
   float w[PPL];
   long long idx[PPL];
+  int node[PPL][DIM];
   bool ok[PPL];
   if (active) {
     float x[DIM];
@@ -111,45 +131,61 @@ __global__ void k_mdf_stage(MdfParams p) {
 #pragma unroll
     for (int d = 0; d < DIM; ++d) {
       float pos = p.markers0[m * DIM + d];
-      int org = p.origin0[d];
-      if (p.body) { pos += p.body->d[d]; org = p.body->origin2[p.parity][d]; }
-      x[d] = pos - (float)org;   // window-local coordinate, as in the reference's marker_x - ib_x0
+      if (p.body) pos += p.body->d[d];
+      x[d] = pos - (float)org[d];   // window-local coordinate, as in the reference's marker_x - ib_x0
       base[d] = (int)floorf(x[d]);
     }
 #pragma unroll
     for (int j = 0; j < PPL; ++j) {
       int s = gl * PPL + j;
-      int node[DIM];
       float wt = 1.f;
       bool inside = true;
 #pragma unroll
       for (int d = DIM - 1; d >= 0; --d) {
-        node[d] = base[d] + (s & 3) - 1;
+        node[j][d] = base[d] + (s & 3) - 1;
         s >>= 2;
-        wt *= delta(p.delta_kind, (float)node[d] - x[d]);
-        inside = inside && node[d] >= 0 && node[d] < p.wsize[d];
+        wt *= delta(p.delta_kind, (float)node[j][d] - x[d]);
+        inside = inside && node[j][d] >= 0 && node[j][d] < p.wsize[d];
       }
       w[j] = wt;
       ok[j] = inside;
-      idx[j] = (DIM == 2) ? (long long)node[0] * p.wsize[1] + node[1]
-                          : ((long long)node[0] * p.wsize[1] + node[1]) * p.wsize[2] + node[2];
+      idx[j] = (DIM == 2) ? (long long)node[j][0] * p.wsize[1] + node[j][1]
+                          : ((long long)node[j][0] * p.wsize[1] + node[j][1]) * p.wsize[2] + node[j][2];
     }
   } else {
 #pragma unroll
     for (int j = 0; j < PPL; ++j) { w[j] = 0.f; ok[j] = false; idx[j] = 0; }
   }
 
-  const float* src = (p.stage == 0) ? p.u_win : p.scratch + (long long)(p.stage - 1) * DIM * wcells;
   float um[DIM];
 #pragma unroll
-  for (int c = 0; c < DIM; ++c) {
-    float acc = 0.f;
+  for (int c = 0; c < DIM; ++c) um[c] = 0.f;
+  if (p.stage == 0) {
 #pragma unroll
     for (int j = 0; j < PPL; ++j)
-      if (ok[j]) acc += w[j] * src[c * wcells + idx[j]];
+      if (ok[j]) {
+        int cell[3] = {0, 0, 0};
 #pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    um[c] = acc;
+        for (int d = 0; d < DIM; ++d) cell[d + L::A0] = org[d] + node[j][d];
+        float f[L::Q], rho, u[DIM];
+        pull_cell<DIM>(sp, cell[0], cell[1], cell[2], f, true);
+        moments<DIM>(f, rho, u);
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) um[c] += w[j] * u[c];
+      }
+  } else {
+    const float* src = p.scratch + (long long)(p.stage - 1) * DIM * wcells;
+#pragma unroll
+    for (int j = 0; j < PPL; ++j)
+      if (ok[j]) {
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) um[c] += w[j] * src[c * wcells + idx[j]];
+      }
+  }
+#pragma unroll
+  for (int c = 0; c < DIM; ++c) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) um[c] += __shfl_xor_sync(0xffffffffu, um[c], o);
   }
 
   float spread_val[DIM];
@@ -165,7 +201,7 @@ __global__ void k_mdf_stage(MdfParams p) {
       const float F = (p.stage == 0 ? 0.f : p.marker_force[m * DIM + c]) + dF;
       u_new[c] = u_m;
       f_new[c] = F;
-      spread_val[c] = (p.stage == p.n_iter - 1) ? F : dF;
+      spread_val[c] = last ? F : dF;
     }
     __syncwarp(__activemask());
     if (gl == 0) {
@@ -175,27 +211,67 @@ __global__ void k_mdf_stage(MdfParams p) {
         p.marker_force[m * DIM + c] = f_new[c];
       }
     }
-    float* dst = (p.stage == p.n_iter - 1) ? p.g_win : p.scratch + (long long)p.stage * DIM * wcells;
+    float* dst = last ? p.g_win : p.scratch + (long long)p.stage * DIM * wcells;
 #pragma unroll
     for (int j = 0; j < PPL; ++j)
       if (ok[j]) {
 #pragma unroll
         for (int c = 0; c < DIM; ++c) atomicAdd(&dst[c * wcells + idx[j]], spread_val[c] * w[j]);
       }
-    if (p.stage == p.n_iter - 1 && p.body && gl == 0) {
+    if (last && p.body && gl == 0) {
 #pragma unroll
       for (int c = 0; c < DIM; ++c) atomicAdd(&s_force[c], spread_val[c]);
     }
   }
-  if (p.stage == p.n_iter - 1 && p.body) {
+  if (last && p.body) {
     __syncthreads();
     if (threadIdx.x < DIM) atomicAdd(&p.body->force_sum[threadIdx.x], s_force[threadIdx.x]);
+    if (p.update_body) {   // the last CTA to arrive sees every contribution and advances the body
+      __shared__ int s_last;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(&p.body->ticket, 1) == (int)gridDim.x - 1);
+      }
+      __syncthreads();
+      if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        p.body->ticket = 0;
+        body_update(p.body, bu, p.parity);
+      }
+    }
   }
 }
 
 // body update by one thread (see body_update in vsb_step.cuh)
 __global__ void k_body_newmark(VsbBodyState* b, BodyUpdate u, int parity) {
   if (threadIdx.x == 0 && blockIdx.x == 0) body_update(b, u, parity);
+}
+
+template <int DIM>
+static int mdf_impl(const VsbStepArgs& sa, const VsbMdfArgs& a, const VsbBodyParams* bp, cudaStream_t stream) {
+  StepParams<DIM> sp;
+  VsbStepArgs b = sa;
+  if (!b.f_out) b.f_out = a.g_win;   // unused by these kernels; only has to differ from f_in
+  b.band = 0;
+  if (int rc = fill_params<DIM>(b, sp)) return rc;
+  MdfParams p;
+  p.delta_kind = a.delta_kind; p.n_iter = a.n_iter; p.parity = a.parity & 1; p.n_markers = a.n_markers;
+  for (int d = 0; d < 3; ++d) { p.origin0[d] = a.win_origin0[d]; p.wsize[d] = a.win_size[d]; }
+  p.markers0 = a.markers0; p.u_target = a.u_target; p.ds_ptr = a.ds_ptr; p.ds_value = a.ds_value;
+  p.g_win = a.g_win; p.g_win_next = a.g_win_next; p.scratch = a.scratch; p.scratch_next = a.scratch_next;
+  p.marker_u = a.marker_u; p.marker_force = a.marker_force; p.body = a.body;
+  p.update_body = (a.body && bp && bp->n_dof > 0) ? 1 : 0;
+  BodyUpdate bu{};
+  if (p.update_body) bu = make_body_update(*bp, DIM);
+  const int lanes = (DIM == 2) ? 16 : 32;
+  const unsigned nb = blocks_for(a.n_markers * lanes, kBlock);
+  for (int k = 0; k < a.n_iter; ++k) {
+    p.stage = k;
+    k_mdf_stage<DIM><<<nb, kBlock, 0, stream>>>(sp, p, bu);
+  }
+  VSB_LAUNCH_CHECK("vsb_ib_mdf");
+  return VSB_OK;
 }
 
 }  // namespace vsb
@@ -250,31 +326,17 @@ int vsb_ib_spread(int n_comp, int64_t n_cells, float* grid, int64_t n_markers, i
   return VSB_OK;
 }
 
-int vsb_ib_mdf(const VsbMdfArgs* a, vsb_stream_t stream) {
-  VSB_REQUIRE(a != nullptr, "vsb_ib_mdf: null args");
-  VSB_REQUIRE(a->dim == 2 || a->dim == 3, "dim must be 2 or 3, got %d", a->dim);
+int vsb_ib_mdf(const VsbStepArgs* args, const VsbMdfArgs* a, const VsbBodyParams* params, vsb_stream_t stream) {
+  VSB_REQUIRE(args != nullptr && a != nullptr, "vsb_ib_mdf: null args");
+  VSB_REQUIRE((a->dim == 2 || a->dim == 3) && a->dim == args->grid.dim, "vsb_ib_mdf: dim must be 2 or 3 and match the grid");
   VSB_REQUIRE(a->delta_kind >= VSB_DELTA_PESKIN3 && a->delta_kind <= VSB_DELTA_HAT2, "unknown delta kernel %d", a->delta_kind);
   VSB_REQUIRE(a->n_iter >= 1, "n_iter must be >= 1, got %d", a->n_iter);
-  VSB_REQUIRE(a->n_markers >= 0 && a->markers0 && a->u_win && a->g_win && a->marker_u && a->marker_force,
+  VSB_REQUIRE(a->n_markers >= 0 && a->markers0 && a->g_win && a->g_win_next && a->marker_u && a->marker_force,
               "vsb_ib_mdf: null buffer");
-  VSB_REQUIRE(a->n_iter == 1 || a->scratch != nullptr, "vsb_ib_mdf: n_iter > 1 needs the scratch buffer");
+  VSB_REQUIRE(a->n_iter == 1 || (a->scratch && a->scratch_next), "vsb_ib_mdf: n_iter > 1 needs the scratch buffers");
   for (int d = 0; d < a->dim; ++d) VSB_REQUIRE(a->win_size[d] >= 4, "IB window must be at least 4 cells wide");
   if (a->n_markers == 0) return VSB_OK;
-  MdfParams p;
-  p.delta_kind = a->delta_kind; p.n_iter = a->n_iter; p.parity = a->parity & 1; p.n_markers = a->n_markers;
-  for (int d = 0; d < 3; ++d) { p.origin0[d] = a->win_origin0[d]; p.wsize[d] = a->win_size[d]; }
-  p.markers0 = a->markers0; p.u_target = a->u_target; p.ds_ptr = a->ds_ptr; p.ds_value = a->ds_value;
-  p.u_win = a->u_win; p.g_win = a->g_win; p.scratch = a->scratch; p.marker_u = a->marker_u;
-  p.marker_force = a->marker_force; p.body = a->body;
-  const int lanes = (a->dim == 2) ? 16 : 32;
-  const unsigned nb = blocks_for(a->n_markers * lanes, kBlock);
-  for (int k = 0; k < a->n_iter; ++k) {
-    p.stage = k;
-    if (a->dim == 2) k_mdf_stage<2><<<nb, kBlock, 0, (cudaStream_t)stream>>>(p);
-    else k_mdf_stage<3><<<nb, kBlock, 0, (cudaStream_t)stream>>>(p);
-  }
-  VSB_LAUNCH_CHECK("vsb_ib_mdf");
-  return VSB_OK;
+  return a->dim == 2 ? mdf_impl<2>(*args, *a, params, (cudaStream_t)stream) : mdf_impl<3>(*args, *a, params, (cudaStream_t)stream);
 }
 
 int vsb_body_newmark(VsbBodyState* body, const VsbBodyParams* params, int parity, vsb_stream_t stream) {

@@ -30,105 +30,116 @@ struct IbFusedParams {
   int update_body;
 };
 
-template <int DIM> struct Stencil {
-  static constexpr int NS = (DIM == 2) ? 16 : 64;
-  static constexpr int G = (DIM == 2) ? 16 : 32;
-  static constexpr int PPL = NS / G;
-  float w[PPL];
-  int idx[PPL];
-  int node[PPL][DIM];
-  bool ok[PPL];
+// Per-axis delta weights of one marker: w(point) = prod_d wq[d][offset_d]; offsets -1..2 around floor(x).
+template <int DIM> struct AxisWeights {
+  float wq[DIM][4];
+  int base[DIM];
 };
 
 template <int DIM>
-__device__ __forceinline__ void make_stencil(const IbFusedParams& m, const int (&org)[3], const int (&wsz)[3], int marker, int gl,
-                                             bool active, Stencil<DIM>& st) {
-  using S = Stencil<DIM>;
-  float x[DIM];
-  int base[DIM];
+__device__ __forceinline__ void axis_weights(int kind, const float* __restrict__ x, AxisWeights<DIM>& aw) {
 #pragma unroll
   for (int d = 0; d < DIM; ++d) {
-    float pos = active ? m.markers0[marker * DIM + d] : 2.0f;
-    if (m.body) pos += m.body->d[d];
-    x[d] = pos - (float)org[d];          // window-local coordinate, as the reference's marker_x - ib_x0
-    base[d] = (int)floorf(x[d]);
-  }
+    aw.base[d] = (int)floorf(x[d]);
 #pragma unroll
-  for (int j = 0; j < S::PPL; ++j) {
-    int s = gl * S::PPL + j;
-    float wt = 1.f;
-    bool inside = active;
-#pragma unroll
-    for (int d = DIM - 1; d >= 0; --d) {
-      st.node[j][d] = base[d] + (s & 3) - 1;
-      s >>= 2;
-      wt *= delta(m.delta_kind, (float)st.node[j][d] - x[d]);
-      inside = inside && st.node[j][d] >= 0 && st.node[j][d] < wsz[d];
-    }
-    st.w[j] = wt;
-    st.ok[j] = inside;
-    st.idx[j] = (DIM == 2) ? st.node[j][0] * wsz[1] + st.node[j][1]
-                           : (st.node[j][0] * wsz[1] + st.node[j][1]) * wsz[2] + st.node[j][2];
+    for (int o = 0; o < 4; ++o) aw.wq[d][o] = delta(kind, (float)(aw.base[d] + o - 1) - x[d]);
   }
 }
 
+// stencil point s (0 .. 4^DIM - 1, last axis fastest) of a marker: weight, window index, validity
 template <int DIM>
+__device__ __forceinline__ bool stencil_point(const AxisWeights<DIM>& aw, const int (&wsz)[3], int s, float& w, int& idx,
+                                              int (&node)[DIM]) {
+  w = 1.f;
+  bool inside = true;
+#pragma unroll
+  for (int d = DIM - 1; d >= 0; --d) {
+    const int o = s & 3;
+    s >>= 2;
+    node[d] = aw.base[d] + o - 1;
+    w *= (o == 0) ? aw.wq[d][0] : (o == 1) ? aw.wq[d][1] : (o == 2) ? aw.wq[d][2] : aw.wq[d][3];   // registers, no stack
+    inside = inside && node[d] >= 0 && node[d] < wsz[d];
+  }
+  idx = (DIM == 2) ? node[0] * wsz[1] + node[1] : (node[0] * wsz[1] + node[1]) * wsz[2] + node[2];
+  return inside;
+}
+
+// G lanes cooperate on one marker (G = 1 .. 32, chosen on the host so that one pass covers as many markers as
+// possible); each lane walks NS / G stencil points and the partial sums are combined with log2(G) shuffles.
+template <int DIM, int G>
 __global__ void __launch_bounds__(1024, 1) k_ib_fused(const StepParams<DIM> p, const IbFusedParams m, const BodyUpdate bu) {
   using L = Lat<DIM>;
-  using S = Stencil<DIM>;
-  extern __shared__ float sg[];   // [DIM][wcells] scratch field
+  constexpr int NS = (DIM == 2) ? 16 : 64;
+  constexpr int PPL = NS / G;
+  extern __shared__ float smem[];
   __shared__ float s_force[3];
   const int tid = threadIdx.x, nthr = blockDim.x;
-  const int groups = nthr / S::G, grp = tid / S::G, gl = tid % S::G;
+  const int groups = nthr / G, grp = tid / G, gl = tid % G;
   int org[3];
   window_origin<DIM>(p, org);
   int wcells = 1;
 #pragma unroll
   for (int d = 0; d < DIM; ++d) wcells *= p.wsz[d];
-  const int passes = (m.n_markers + groups - 1) / groups;
+  const int M = m.n_markers;
+  float* sg = smem;                      // [DIM][wcells] scratch field
+  float* s_pos = sg + DIM * wcells;      // [M][DIM] window-local marker coordinates
+  float* s_um = s_pos + M * DIM;         // [M][DIM] marker velocity
+  float* s_F = s_um + M * DIM;           // [M][DIM] accumulated marker force
+  const int passes = (M + groups - 1) / groups;
   if (tid < 3) s_force[tid] = 0.f;
+  float shift[DIM], vbody[DIM];
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) { shift[d] = m.body ? m.body->d[d] : 0.f; vbody[d] = m.body ? m.body->v[d] : 0.f; }
+  for (int i = tid; i < M * DIM; i += nthr) {
+    const int d = i % DIM;
+    s_pos[i] = (m.markers0[i] + shift[d]) - (float)org[d];   // as the reference's marker_x - ib_x0
+    s_F[i] = 0.f;
+  }
+  __syncthreads();
 
   for (int stage = 0; stage < m.n_iter; ++stage) {
     // ---- interpolate and update the marker state
     for (int pass = 0; pass < passes; ++pass) {
       const int marker = pass * groups + grp;
-      const bool active = marker < m.n_markers;
-      Stencil<DIM> st;
-      make_stencil<DIM>(m, org, p.wsz, marker, gl, active, st);
+      const bool active = marker < M;
+      AxisWeights<DIM> aw;
+      axis_weights<DIM>(m.delta_kind, s_pos + (active ? marker : 0) * DIM, aw);
       float acc[DIM];
 #pragma unroll
       for (int c = 0; c < DIM; ++c) acc[c] = 0.f;
-#pragma unroll
-      for (int j = 0; j < S::PPL; ++j) {
-        if (!st.ok[j]) continue;
+#pragma unroll 4
+      for (int j = 0; j < PPL; ++j) {
+        float w;
+        int idx, node[DIM];
+        const bool ok = stencil_point<DIM>(aw, p.wsz, gl * PPL + j, w, idx, node) && active;
+        if (!ok) continue;
         if (stage == 0) {
           int cell[3] = {0, 0, 0};
 #pragma unroll
-          for (int d = 0; d < DIM; ++d) cell[d + L::A0] = org[d] + st.node[j][d];
+          for (int d = 0; d < DIM; ++d) cell[d + L::A0] = org[d] + node[d];
           float f[L::Q], rho, u[DIM];
           pull_cell<DIM>(p, cell[0], cell[1], cell[2], f, true);
           moments<DIM>(f, rho, u);
 #pragma unroll
-          for (int c = 0; c < DIM; ++c) acc[c] += st.w[j] * u[c];
+          for (int c = 0; c < DIM; ++c) acc[c] += w * u[c];
         } else {
 #pragma unroll
-          for (int c = 0; c < DIM; ++c) acc[c] += st.w[j] * sg[c * wcells + st.idx[j]];
+          for (int c = 0; c < DIM; ++c) acc[c] += w * sg[c * wcells + idx];
         }
       }
 #pragma unroll
       for (int c = 0; c < DIM; ++c) {
 #pragma unroll
-        for (int o = S::G / 2; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+        for (int o = G / 2; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
       }
       if (active && gl == 0) {
-        const float ds2 = (m.ds_ptr ? m.ds_ptr[marker] : m.ds_value) * 2.0f;
+        const float ds2 = (m.ds_ptr ? __ldg(m.ds_ptr + marker) : m.ds_value) * 2.0f;
 #pragma unroll
         for (int c = 0; c < DIM; ++c) {
-          const float u_m = (stage == 0) ? acc[c] : m.marker_u[marker * DIM + c] + 0.5f * acc[c];
-          const float tgt = m.u_target ? m.u_target[marker * DIM + c] : (m.body ? m.body->v[c] : 0.f);
-          const float dF = (tgt - u_m) * ds2;
-          m.marker_u[marker * DIM + c] = u_m;
-          m.marker_force[marker * DIM + c] = (stage == 0 ? 0.f : m.marker_force[marker * DIM + c]) + dF;
+          const float u_m = (stage == 0) ? acc[c] : s_um[marker * DIM + c] + 0.5f * acc[c];
+          const float tgt = m.u_target ? __ldg(m.u_target + marker * DIM + c) : vbody[c];
+          s_um[marker * DIM + c] = u_m;
+          s_F[marker * DIM + c] += (tgt - u_m) * ds2;
         }
       }
     }
@@ -139,29 +150,32 @@ __global__ void __launch_bounds__(1024, 1) k_ib_fused(const StepParams<DIM> p, c
     const bool last = stage == m.n_iter - 1;
     for (int pass = 0; pass < passes; ++pass) {
       const int marker = pass * groups + grp;
-      const bool active = marker < m.n_markers;
-      Stencil<DIM> st;
-      make_stencil<DIM>(m, org, p.wsz, marker, gl, active, st);
+      const bool active = marker < M;
+      AxisWeights<DIM> aw;
+      axis_weights<DIM>(m.delta_kind, s_pos + (active ? marker : 0) * DIM, aw);
       float val[DIM];
 #pragma unroll
       for (int c = 0; c < DIM; ++c) {
         val[c] = 0.f;
         if (active) {
           if (last) {
-            val[c] = m.marker_force[marker * DIM + c];
-          } else {   // same arithmetic as above, so the value is identical to the dF that was accumulated
-            const float ds2 = (m.ds_ptr ? m.ds_ptr[marker] : m.ds_value) * 2.0f;
-            const float tgt = m.u_target ? m.u_target[marker * DIM + c] : (m.body ? m.body->v[c] : 0.f);
-            val[c] = (tgt - m.marker_u[marker * DIM + c]) * ds2;
+            val[c] = s_F[marker * DIM + c];
+          } else {   // same arithmetic as above, so this is exactly the dF that was accumulated
+            const float ds2 = (m.ds_ptr ? __ldg(m.ds_ptr + marker) : m.ds_value) * 2.0f;
+            const float tgt = m.u_target ? __ldg(m.u_target + marker * DIM + c) : vbody[c];
+            val[c] = (tgt - s_um[marker * DIM + c]) * ds2;
           }
         }
       }
+#pragma unroll 4
+      for (int j = 0; j < PPL; ++j) {
+        float w;
+        int idx, node[DIM];
+        if (stencil_point<DIM>(aw, p.wsz, gl * PPL + j, w, idx, node) && active) {
 #pragma unroll
-      for (int j = 0; j < S::PPL; ++j)
-        if (st.ok[j]) {
-#pragma unroll
-          for (int c = 0; c < DIM; ++c) atomicAdd(&sg[c * wcells + st.idx[j]], val[c] * st.w[j]);
+          for (int c = 0; c < DIM; ++c) atomicAdd(&sg[c * wcells + idx], val[c] * w);
         }
+      }
       if (last && active && gl == 0) {
 #pragma unroll
         for (int c = 0; c < DIM; ++c) atomicAdd(&s_force[c], val[c]);
@@ -169,8 +183,9 @@ __global__ void __launch_bounds__(1024, 1) k_ib_fused(const StepParams<DIM> p, c
     }
     __syncthreads();
   }
-  // ---- force field of the step: every window cell
+  // ---- outputs: force field on every window cell, marker state
   for (int i = tid; i < DIM * wcells; i += nthr) m.g_win[i] = sg[i];
+  for (int i = tid; i < M * DIM; i += nthr) { m.marker_force[i] = s_F[i]; m.marker_u[i] = s_um[i]; }
   if (tid == 0 && m.body) {
 #pragma unroll
     for (int c = 0; c < DIM; ++c) m.body->force_sum[c] += s_force[c];
@@ -183,7 +198,7 @@ constexpr size_t kMaxFusedSmem = 200 * 1024;
 static size_t fused_smem_bytes(const VsbMdfArgs& a) {
   size_t cells = 1;
   for (int d = 0; d < a.dim; ++d) cells *= (size_t)a.win_size[d];
-  return cells * a.dim * sizeof(float);
+  return (cells + 3 * (size_t)a.n_markers) * a.dim * sizeof(float);   // scratch field + marker position / velocity / force
 }
 
 template <int DIM>
@@ -208,15 +223,25 @@ static int ib_fused_impl(const VsbStepArgs& sa, const VsbMdfArgs& a, const VsbBo
   BodyUpdate bu{};
   if (m.update_body) bu = make_body_update(*bp, DIM);
   const size_t smem = fused_smem_bytes(a);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_ib_fused<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxFusedSmem);
+  // lanes per marker: as many as fit one pass of 1024 threads (more lanes = shorter serial chains)
+  int g = 1;
+  const int gmax = (DIM == 2) ? 16 : 32;
+  while (g * 2 <= gmax && (long long)m.n_markers * (g * 2) <= 1024) g *= 2;
+  auto launch = [&](auto kernel) -> int {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxFusedSmem);
     if (e != cudaSuccess) return cuda_fail(e, "vsb_ib_fused (shared memory attribute)");
-    attr_set = true;
+    kernel<<<1, 1024, smem, s>>>(p, m, bu);
+    VSB_LAUNCH_CHECK("vsb_ib_fused");
+    return VSB_OK;
+  };
+  switch (g) {
+    case 1: return launch(k_ib_fused<DIM, (DIM == 2 ? 1 : 2)>);   // 3-D keeps at least 2 lanes (32 points per lane)
+    case 2: return launch(k_ib_fused<DIM, 2>);
+    case 4: return launch(k_ib_fused<DIM, 4>);
+    case 8: return launch(k_ib_fused<DIM, 8>);
+    case 16: return launch(k_ib_fused<DIM, 16>);
+    default: return launch(k_ib_fused<DIM, 32>);
   }
-  k_ib_fused<DIM><<<1, 1024, smem, s>>>(p, m, bu);
-  VSB_LAUNCH_CHECK("vsb_ib_fused");
-  return VSB_OK;
 }
 
 }  // namespace vsb
@@ -227,6 +252,11 @@ extern "C" {
 
 int vsb_ib_fused_supported(const VsbMdfArgs* a) {
   if (!a || (a->dim != 2 && a->dim != 3) || a->n_markers <= 0 || a->n_markers > (1 << 24)) return 0;
+  // Shared-memory fp32 atomics retire at ~2 cycles per lane on the one SM this kernel occupies (measured: 512 markers
+  // x 16 points x 2 components x 5 iterations = 97 us), so the single-CTA form only pays for small bodies; larger ones
+  // use the multi-CTA chain (vsb_ib_mdf), whose global reductions are spread over the whole chip.
+  const long long atomics = a->n_markers * (a->dim == 2 ? 16 : 64) * a->dim * a->n_iter;
+  if (atomics > 8192) return 0;
   return fused_smem_bytes(*a) <= kMaxFusedSmem ? 1 : 0;
 }
 

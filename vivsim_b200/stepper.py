@@ -176,10 +176,10 @@ class Stepper:
         self.n_iter = int(ib.get("n_iter", 5))
         wshape = (dim,) + self.win_size
         self._markers = torch.as_tensor(markers, device=dev)
-        self._u_win = torch.zeros(wshape, device=dev)
-        # g_win and the per-iteration scratch buffers live in one allocation so a single memset clears them
-        self._ib_zero = torch.zeros((self.n_iter,) + wshape, device=dev)
-        self._g_win = self._ib_zero[0]
+        # force field [0] and per-iteration work fields [1:], double-buffered by step parity: each step clears the
+        # set the next step will accumulate into (see vsb_ib_mdf), so there is no memset on the step path
+        self._ib_buf = torch.zeros((2, self.n_iter) + wshape, device=dev)
+        self._g_win = self._ib_buf[0, 0]
         self._marker_u = torch.zeros((self.n_markers, dim), device=dev)
         self.marker_force = torch.zeros((self.n_markers, dim), device=dev)   # +F; reaction on the body is -F
         tgt = ib.get("u_target")
@@ -203,9 +203,6 @@ class Stepper:
             a.win_size[d] = self.win_size[d]
         m.markers0 = self._markers.data_ptr()
         m.u_target = self._u_target.data_ptr() if self._u_target is not None else None
-        m.u_win = self._u_win.data_ptr()
-        m.g_win = self._g_win.data_ptr()
-        m.scratch = self._ib_zero[1].data_ptr() if self.n_iter > 1 else None
         m.marker_u = self._marker_u.data_ptr()
         m.marker_force = self.marker_force.data_ptr()
         a.g_win = self._g_win.data_ptr()
@@ -269,12 +266,7 @@ class Stepper:
         if self.ib is not None:
             if self.overlap:
                 n += 1                                    # second launch of the fused kernel (window x-range)
-            if self.ib_fused:
-                n += 1
-            else:
-                n += 1 + self.n_iter
-            if self.body is not None and self.dyn_mode == "device" and not self.ib_fused:
-                n += 1
+            n += 1 if self.ib_fused else self.n_iter
         return n
 
     # ------------------------------------------------------------------ state access
@@ -326,6 +318,9 @@ class Stepper:
         a.f_in, a.f_out = src.data_ptr(), dst.data_ptr()
         a.do_stream, a.do_collide = do_stream, do_collide
         a.parity = self._parity
+        if self.ib is not None and do_collide:     # force field of this step (double-buffered by parity)
+            self._g_win = self._ib_buf[self._parity, 0]
+            a.g_win = self._g_win.data_ptr()
         lib = L.lib()
         has_ops = a.n_post > 0 and do_stream
         with_ib = self.ib is not None and do_collide
@@ -343,12 +338,12 @@ class Stepper:
             s_ib.wait_stream(main)
             if a.edges:
                 s_edge.wait_stream(main)
-            a.band = 1                                        # everything but the window's x-range
-            L.check(lib.vsb_step(C.byref(a), L.stream()))
-            with torch.cuda.stream(s_ib):                     # IB chain, then the window's x-range
-                self._ib_part(L.stream())
+            with torch.cuda.stream(s_ib):                     # IB chain first (its few CTAs should not queue
+                self._ib_part(L.stream())                     # behind the bulk), then the window's x-range
                 a.band = 2
                 L.check(lib.vsb_step(C.byref(a), L.stream()))
+            a.band = 1                                        # everything but the window's x-range
+            L.check(lib.vsb_step(C.byref(a), L.stream()))
             if a.edges:
                 with torch.cuda.stream(s_edge):
                     L.check(lib.vsb_edge_fused(C.byref(a), L.stream()))
@@ -361,20 +356,18 @@ class Stepper:
     def _ib_part(self, st):
         """Immersed-boundary force of this pass on stream `st` (the current stream), then the body update."""
         lib, a, m = L.lib(), self._args, self._mdf
-        m.parity = self._parity
+        par = self._parity
+        m.parity = par
+        buf = self._ib_buf
+        m.g_win, m.g_win_next = buf[par, 0].data_ptr(), buf[par ^ 1, 0].data_ptr()
+        if self.n_iter > 1:
+            m.scratch, m.scratch_next = buf[par, 1].data_ptr(), buf[par ^ 1, 1].data_ptr()
         host_body = self.body is not None and self.dyn_mode == "host"
         bp = C.byref(self._bparams) if self._bparams is not None else None
         if self.ib_fused:
             L.check(lib.vsb_ib_fused(C.byref(a), C.byref(m), bp, st))
         else:
-            self._ib_zero.zero_()
-            band = a.band
-            a.band = 0
-            L.check(lib.vsb_ib_window_moments(C.byref(a), L.ptr(self._u_win), st))
-            a.band = band
-            L.check(lib.vsb_ib_mdf(C.byref(m), st))
-            if self.body is not None and not host_body:
-                L.check(lib.vsb_body_newmark(C.c_void_p(self._body_dev.data_ptr()), bp, self._parity, st))
+            L.check(lib.vsb_ib_mdf(C.byref(a), C.byref(m), bp, st))
         if host_body:
             self._host_newmark()
 
