@@ -33,6 +33,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "MLUPS (IB-LBM step, D2Q9 1024x1024 VIV cylinder, 512 markers, MDF + Guo)"
 L2_BYTES = 126e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_step<2,BGK,vec4> launch at 1024^2 (ncu --set full, profiles/)
+TRAFFIC_NCU = 39.4e6
 
 
 def peaks():
@@ -230,19 +232,50 @@ def run_ours(args):
     n_rep = int(-(-4 * L2_BYTES // bytes_per_domain)) + 1          # ensemble working set > 4x L2
     f0 = configs.uniform_state(spec, noise=1e-3)
     steppers = []
-    for i in range(n_rep):
-        st = Stepper(spec, body=dict(body), dyn_mode="device")
-        st.set_f(f0)
-        st.step(1)     # prologue: internal state is now S_0
-        steppers.append(st)
     steps_each = 2
-    graph = build_graph(steppers, steps_each)
     K, W = args.steps, args.warmup
-    run_loop(graph, steppers, steps_each, W)
+    if world == 1:
+        for i in range(n_rep):
+            st = Stepper(spec, body=dict(body), dyn_mode="device")
+            st.set_f(f0)
+            st.step(1)     # prologue: internal state is now S_0
+            steppers.append(st)
+        graph = build_graph(steppers, steps_each)
+        loop = lambda n: run_loop(graph, steppers, steps_each, n)
+        multi = None
+    else:
+        # weak scaling: every ensemble member is one (world x 1024) x 1024 channel cut into 1024-wide slabs, one
+        # elastically mounted cylinder per slab; after every step the populations crossing the cuts are exchanged
+        from vivsim_b200.multidevice import SlabStepper
+        nxl = spec["shape"][0]
+        gspec = dict(spec, shape=(nxl * world, spec["shape"][1]))
+        gspec.pop("ib")
+
+        def local_ib(slab):
+            sp, _ = configs.viv_cylinder_2d(center=(slab.x0 + nxl / 2, spec["shape"][1] / 2))
+            return sp["ib"]
+
+        f_loc = torch.cat([f0[:, -1:], f0, f0[:, :1]], dim=1).contiguous()     # local slab + periodic ghost layers
+        for i in range(n_rep):
+            st = SlabStepper(gspec, local_ib=local_ib, body=dict(body), dyn_mode="device")
+            st.set_f_local(f_loc)
+            st.step(1)
+            steppers.append(st)
+
+        def loop(n):
+            for k in range(n):
+                steppers[k % n_rep].step(1)
+
+        graph = None
+        multi = {"decomposition": f"{world} slabs of {nxl} x {spec['shape'][1]} along x per ensemble member",
+                 "exchange": "NCCL send/recv of the 3 populations crossing each cut, one contiguous 4 KB row each, "
+                             "after every step (torch.distributed batch_isend_irecv)",
+                 "halo_bytes_per_step_per_rank": steppers[0].slab.halo_bytes_per_step()}
+    loop(W)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         time.sleep(0.3)
-    dt, w0, w1 = timed(lambda: run_loop(graph, steppers, steps_each, K), sync)
+    dt, w0, w1 = timed(lambda: loop(K), sync)
     if world > 1:
         t = torch.tensor([dt], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -254,26 +287,70 @@ def run_ours(args):
     if sampler and (clocks is None or clocks["samples"] < 3):
         # the timed region is shorter than the 100 ms sampling period: sample an identical follow-up loop
         t_a = time.time()
-        while time.time() - t_a < 1.5:
-            run_loop(graph, steppers, steps_each, 2 * len(steppers) * 50)
+        while time.time() - t_a < 1.5 and world == 1:
+            loop(2 * len(steppers) * 50)
             torch.cuda.synchronize()
         clocks = sampler.summary(t_a, time.time())
         clock_note = "timed region shorter than the sampling period; sampled during an identical untimed follow-up loop"
     if sampler:
         sampler.stop()
 
+    # ---- e2e through the public API from HOST buffers
+    f_host = f0.cpu().pin_memory()
+    state_bytes = f_host.numel() * 4
+    ke = max(10, min(K, 3000))
+    if world == 1:
+        # host-side rigid-body ODE as north_star prescribes: every step one device->host read of the body force and
+        # one host->device write of the kinematics (88 B each way, synchronous)
+        st = Stepper(spec, body=dict(body), dyn_mode="host")
+        st.set_f(f_host); st.step(5); st.get_f()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        st.set_f(f_host)
+        st.step(ke)
+        f_back = st.get_f().to("cpu", non_blocking=False)
+        torch.cuda.synchronize()
+        te = time.perf_counter() - t0
+        per_step_io = _lib.BODY_BYTES
+        e2e_note = ("pinned f -> device once, per step: device->host read of the body force + host Newmark + "
+                    "host->device kinematics (88 B each way, synchronous), f -> host once; single L2-resident domain")
+        del st
+    else:
+        # N GPUs: pinned slab -> device, ke steps with halo exchange (body ODE on the device), slab -> host
+        f_loc_host = torch.cat([f_host[:, -1:], f_host, f_host[:, :1]], dim=1).contiguous().pin_memory()
+        st = steppers[0]
+        sync()
+        t0 = time.perf_counter()
+        st.set_f_local(f_loc_host)
+        st.step(ke)
+        f_back = st.get_f_local().to("cpu", non_blocking=False)
+        sync()
+        te = time.perf_counter() - t0
+        t = torch.tensor([te], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        te = float(t)
+        per_step_io = 0
+        e2e_note = ("per rank: pinned slab -> device once, steps with NCCL halo exchange and the body ODE on the device, "
+                    "slab -> host once; max over ranks")
+    assert bool(torch.isfinite(f_back).all())
+    e2e = {"value": cells * ke * world / te / 1e6, "unit": "MLUPS", "steps": ke,
+           "h2d_bytes_per_step": state_bytes / ke + per_step_io, "d2h_bytes_per_step": state_bytes / ke + per_step_io,
+           "note": e2e_note}
+
     line = None
     if rank == 0:
-        # ---- single domain, L2-resident
-        g1 = build_graph(steppers[:1], steps_each)
-        n1 = max(200, min(K, 20000))
-        run_loop(g1, steppers[:1], steps_each, 50)
-        dt1, _, _ = timed(lambda: run_loop(g1, steppers[:1], steps_each, n1), torch.cuda.synchronize)
-        l2_mlups = cells * n1 / dt1 / 1e6
+        l2_mlups = None
+        if world == 1:
+            # ---- single domain, L2-resident
+            g1 = build_graph(steppers[:1], steps_each)
+            n1 = max(200, min(K, 20000))
+            run_loop(g1, steppers[:1], steps_each, 50)
+            dt1, _, _ = timed(lambda: run_loop(g1, steppers[:1], steps_each, n1), torch.cuda.synchronize)
+            l2_mlups = cells * n1 / dt1 / 1e6
 
-        # ---- roofline of the dominant kernel: vsb_step alone (no IB, no wall fix-up), rotating buffers
-        # same kernel instantiation and runtime flags as in the step (Guo forcing enabled, force zero outside the
-        # IB window, which covers 1 % of the cells)
+        # ---- roofline of the dominant kernel: vsb_step alone (no IB, no wall kernels), rotating buffers; same kernel
+        # instantiation and runtime flags as in the step (Guo forcing enabled, force zero outside the IB window,
+        # which covers 1 % of the cells)
         plain = dict(spec); plain.pop("ib"); plain["post"] = []
         ks = [Stepper(plain).set_f(f0) for _ in range(n_rep)]
         for s in ks:
@@ -286,34 +363,16 @@ def run_ours(args):
         achieved = 72.0 * cells / per_launch / 1e9
         roofline = {"bound": "hbm", "kernel": "vsb::k_step<2, BGK, vec4> (fused pull-stream + moments + BGK + Guo)",
                     "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
-                    "traffic": None, "peak_source": peak_src, "us_per_launch": per_launch * 1e6,
+                    "traffic": TRAFFIC_NCU, "peak_source": peak_src, "us_per_launch": per_launch * 1e6,
                     "algorithmic_bytes_per_launch": 72 * cells,
                     "note": "72 B/cell (9 x 4 B read + 9 x 4 B write) x 1048576 cells per launch; CUDA events over "
-                            f"{nk} launches rotating over {n_rep} domains (working set {n_rep * bytes_per_domain / 1e6:.0f} MB > L2)"}
+                            f"{nk} launches rotating over {n_rep} domains (working set {n_rep * bytes_per_domain / 1e6:.0f} MB > L2); "
+                            "traffic = dram read + write bytes of one launch from the committed ncu --set full capture "
+                            "(profiles/): the 37.7 MB of writes mostly stay in the 126 MB L2 until later launches evict them"}
         del ks, gk
 
-        # ---- e2e through the public API from host buffers, host-side rigid-body ODE
-        f_host = f0.cpu().pin_memory()
-        st = Stepper(spec, body=dict(body), dyn_mode="host")
-        st.set_f(f_host); st.step(5); st.get_f()
-        torch.cuda.synchronize()
-        ke = max(10, min(K, 3000))
-        t0 = time.perf_counter()
-        st.set_f(f_host)
-        st.step(ke)
-        f_back = st.get_f().to("cpu", non_blocking=False)
-        torch.cuda.synchronize()
-        te = time.perf_counter() - t0
-        assert bool(torch.isfinite(f_back).all())
-        state_bytes = f_host.numel() * 4
-        e2e = {"value": cells * ke / te / 1e6, "unit": "MLUPS", "steps": ke,
-               "h2d_bytes_per_step": state_bytes / ke + _lib.BODY_BYTES, "d2h_bytes_per_step": state_bytes / ke + _lib.BODY_BYTES,
-               "note": "pinned f -> device once, per step: device->host read of the body force + host Newmark + "
-                       "host->device kinematics (72 B each way, synchronous), f -> host once; single L2-resident domain"}
-        del st
-
         also = []
-        if not args.no_extra:
+        if not args.no_extra and world == 1:
             for name, n in (("c3", 40), ("c4", 12)):
                 try:
                     also.append(extra_workload(name, n, hbm_gbs))
@@ -321,24 +380,25 @@ def run_ours(args):
                     also.append({"workload": name, "error": f"{type(exc).__name__}: {exc}"})
 
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             cpu, _ = time_cpu(budget_s=12.0)
 
-        finite = all(bool(torch.isfinite(s.state).all()) for s in steppers)
+        inner = [s.stepper if world > 1 else s for s in steppers]
+        finite = all(bool(torch.isfinite(s.state).all()) for s in inner)
         line = {"metric": METRIC, "value": value, "unit": "MLUPS", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "C2: D2Q9 BGK IB-LBM VIV cylinder 1024x1024, 512 markers, MDF(5) + Guo forcing, "
-                                       "2-DOF Newmark body on device",
+                                       "2-DOF Newmark body on device" + (f"; per GPU, {world} slabs per channel" if world > 1 else ""),
                            "cells_per_step": cells, "ensemble_domains": n_rep,
                            "l2": f"{n_rep} independent domains rotated so the working set ({n_rep * bytes_per_domain / 1e6:.0f} MB) "
                                  "exceeds 4x L2: inputs come from HBM every step (no L2 flush needed)",
                            "l2_resident_mlups": l2_mlups,
                            "hbm_frac_of_measured": value / world * 1e6 * 72 / (hbm_gbs * 1e9),
-                           "multi_gpu": "one ensemble per rank, no exchange (replicas only)" if world > 1 else None,
+                           "multi_gpu": multi,
                            "state_finite": finite},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-                "gpu_launches": steppers[0].n_launch_per_step * K,
+                "gpu_launches": inner[0].n_launch_per_step * K,
                 "clocks": dict(clocks or {}, **({"note": clock_note} if clock_note else {})),
                 "also": also}
     if world > 1:
