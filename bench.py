@@ -262,15 +262,24 @@ def run_ours(args):
             st.step(1)
             steppers.append(st)
 
-        def loop(n):
-            for k in range(n):
-                steppers[k % n_rep].step(1)
+        peer = all(s.halo == "peer" for s in steppers)
+        if peer:    # halo kernels are part of the step graph: same replay loop as on one GPU
+            graph = build_graph(steppers, steps_each)
+            loop = lambda n: run_loop(graph, steppers, steps_each, n)
+            exchange = ("vsb_halo_push: one kernel per step stores the 3 crossing populations' edge rows (4 KB each) "
+                        "into the neighbours' ghost rows through peer-mapped symmetric memory (NVLink) and hand-shakes "
+                        "with flag words; captured in the step's CUDA graph, no NCCL on the data path")
+        else:
+            graph = None
 
-        graph = None
+            def loop(n):
+                for k in range(n):
+                    steppers[k % n_rep].step(1)
+
+            exchange = ("NCCL send/recv of the 3 populations crossing each cut after every step (eager; symmetric "
+                        f"memory unavailable: {steppers[0].halo_error})")
         multi = {"decomposition": f"{world} slabs of {nxl} x {spec['shape'][1]} along x per ensemble member",
-                 "exchange": "NCCL send/recv of the 3 populations crossing each cut, one contiguous 4 KB row each, "
-                             "after every step (torch.distributed batch_isend_irecv)",
-                 "halo_bytes_per_step_per_rank": steppers[0].slab.halo_bytes_per_step()}
+                 "exchange": exchange, "halo_bytes_per_step_per_rank": steppers[0].slab.halo_bytes_per_step()}
     loop(W)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -385,6 +394,8 @@ def run_ours(args):
 
         inner = [s.stepper if world > 1 else s for s in steppers]
         finite = all(bool(torch.isfinite(s.state).all()) for s in inner)
+        if world > 1 and any(s.peer is not None and s.peer.timed_out() for s in steppers):
+            raise RuntimeError("a halo wait timed out: the ranks did not run the same number of steps")
         line = {"metric": METRIC, "value": value, "unit": "MLUPS", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",

@@ -219,6 +219,29 @@ int vsb_body_newmark(VsbBodyState* body, const VsbBodyParams* params, int parity
 int vsb_ib_fused_supported(const VsbMdfArgs* mdf);
 int vsb_ib_fused(const VsbStepArgs* args, const VsbMdfArgs* mdf, const VsbBodyParams* params, vsb_stream_t stream);
 
+/* ---- multi-GPU: halo exchange over peer memory ----------------------------------------- *
+ * Slab decomposition along x, one ghost layer per side (local extent grid.nx = nx_local + 2).  Replaces the
+ * reference's vivsim/multidevice.py:13-38 (four lax.ppermute of the populations crossing a cut).  One kernel copies
+ * the edge layers of the crossing populations (3 of 9 in D2Q9, 5 of 19 in D3Q19) of `state` directly into the ring
+ * neighbours' ghost layers through peer-mapped pointers (NVLink), publishes the step number in the neighbours' flag
+ * words and waits for theirs, so that everything enqueued after it sees complete ghost layers.  Graph-capturable.
+ *   left_state / right_state   address of the SAME buffer in the left / right neighbour, mapped into this process
+ *   my_flags (2 words)         [0] written by the left neighbour, [1] by the right neighbour
+ *   left_flags / right_flags   the neighbours' flag words, peer-mapped
+ *   counter (3 words, local)   step number, CTA ticket, timeout indicator (set to 1 if a neighbour never arrived) */
+typedef struct {
+  VsbGrid grid;
+  const float* state;
+  float* left_state;
+  float* right_state;
+  uint32_t* my_flags;
+  uint32_t* left_flags;
+  uint32_t* right_flags;
+  uint32_t* counter;
+} VsbHaloArgs;
+
+int vsb_halo_push(const VsbHaloArgs* args, vsb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

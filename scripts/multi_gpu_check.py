@@ -26,9 +26,27 @@ def main():
     ok = True
 
     def compare(name, spec, f0, n, local_ib=None, global_ib_spec=None):
+        for halo in ("nccl", "peer"):
+            _compare(f"{name} / {halo}", spec, f0, n, halo, local_ib, global_ib_spec)
+
+    def _compare(name, spec, f0, n, halo, local_ib, global_ib_spec):
         nonlocal ok
-        s = SlabStepper(spec, local_ib=local_ib).set_f_global(f0)
-        s.step(n)
+        s = SlabStepper(spec, local_ib=local_ib, halo=halo).set_f_global(f0)
+        s.step(n // 2)
+        if halo == "peer":           # second half through a captured CUDA graph (2 steps per replay)
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                s.advance_raw(2)
+            torch.cuda.current_stream().wait_stream(side); torch.cuda.synchronize(); dist.barrier()
+            with torch.cuda.graph(g):
+                s.advance_raw(2)
+            for _ in range((n - n // 2 - 2) // 2):
+                g.replay()
+            torch.cuda.synchronize()
+            assert not s.peer.timed_out(), "halo wait timed out"
+        else:
+            s.step(n - n // 2)
         got = s.gather_f()
         force = s.total_force()
         if rank == 0:
@@ -62,7 +80,7 @@ def main():
     spec = dict(dim=3, shape=shape, collision="bgk", omega=1.6, forcing="guo", g=(1e-5, 0.0, 2e-5), post=[])
     f0 = configs.uniform_state(dict(spec, u0=0.04), noise=1e-3)
     dist.broadcast(f0, 0)
-    compare("3d bgk", spec, f0, 10)
+    compare("3d bgk", spec, f0, 12)
 
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

@@ -91,6 +91,54 @@ def wait_all(reqs):
         r.wait()
 
 
+class PeerHalo:
+    """Ghost-layer exchange through peer-mapped symmetric memory (vsb_halo_push): the state buffers of all ranks are
+    allocated with torch.distributed._symmetric_memory, so a kernel on this GPU stores straight into the neighbours'
+    ghost layers over NVLink and signals with a flag word; no NCCL call, graph-capturable."""
+
+    def __init__(self, slab, q, group=None):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib as L
+        group = group if group is not None else dist.group.WORLD
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.slab = slab
+        self.buf = symm.empty((2, q) + slab.local_shape, dtype=torch.float32, device=dev)
+        self.buf.zero_()
+        self.flags = symm.empty((16,), dtype=torch.int32, device=dev)
+        self.flags.zero_()
+        self._h_buf = symm.rendezvous(self.buf, group)
+        self._h_flags = symm.rendezvous(self.flags, group)
+        torch.cuda.synchronize()
+        dist.barrier(group)                       # every rank's flags are zero before anyone can signal
+        self.counter = torch.zeros(4, dtype=torch.int32, device=dev)
+        nbytes = self.buf[0].numel() * 4
+        bp, fp = self._h_buf.buffer_ptrs, self._h_flags.buffer_ptrs
+        me, left, right = slab.rank, slab.left, slab.right
+        self.args = []
+        for i in range(2):
+            a = L.VsbHaloArgs()
+            a.grid = L.grid_of(slab.local_shape)
+            a.state = bp[me] + i * nbytes
+            a.left_state = bp[left] + i * nbytes
+            a.right_state = bp[right] + i * nbytes
+            a.my_flags, a.left_flags, a.right_flags = fp[me], fp[left], fp[right]
+            a.counter = self.counter.data_ptr()
+            self.args.append(a)
+        self._C, self._L = C, L
+
+    def buffers(self):
+        return [self.buf[0], self.buf[1]]
+
+    def push(self, index):
+        """Exchange the ghost layers of buffer `index` on the current stream."""
+        L, C = self._L, self._C
+        L.check(L.lib().vsb_halo_push(C.byref(self.args[index]), L.stream()))
+
+    def timed_out(self):
+        return bool(self.counter[2].item())
+
+
 def localize_spec(spec, slab, local_ib=None):
     """Per-rank step description: local extent with ghost layers, x-face operations only on the owning rank,
     immersed body (``spec['ib']`` or ``local_ib(slab)``, global coordinates) shifted to local coordinates."""
@@ -140,10 +188,14 @@ def localize_spec(spec, slab, local_ib=None):
 
 
 class SlabStepper:
-    """One rank's part of a slab-decomposed simulation: a ``Stepper`` on the local extent plus the halo
-    exchange after every step.  Collective: every rank must call ``step`` with the same count."""
+    """One rank's part of a slab-decomposed simulation: a ``Stepper`` on the local extent plus the halo exchange after
+    every step.  Collective: every rank must call ``step`` / ``advance_raw`` with the same count.
 
-    def __init__(self, spec, rank=None, world=None, group=None, local_ib=None, body=None, overlap=True, **kw):
+    halo = "peer": ghost layers are written directly into the neighbours' buffers by vsb_halo_push (symmetric memory,
+    NVLink; graph-capturable).  halo = "nccl": torch.distributed send/recv of the edge layers.  "auto": peer when the
+    symmetric-memory rendezvous succeeds, else NCCL."""
+
+    def __init__(self, spec, rank=None, world=None, group=None, local_ib=None, body=None, halo="auto", **kw):
         from .stepper import Stepper
         self.group = group
         if world is None:
@@ -152,10 +204,20 @@ class SlabStepper:
         self.slab = Slab(spec["shape"], rank, world)
         self.local_spec = localize_spec(spec, self.slab, local_ib)
         has_body = self.local_spec["ib"] is not None
-        self.stepper = Stepper(self.local_spec, rows=self.slab.rows, body=body if has_body else None, **kw)
+        self.peer = None
+        self.halo_error = None
+        if world > 1 and halo in ("auto", "peer"):
+            try:
+                self.peer = PeerHalo(self.slab, 9 if self.slab.dim == 2 else 19, group)
+            except Exception as exc:   # noqa: BLE001 -- symmetric memory unavailable: fall back to NCCL unless forced
+                if halo == "peer":
+                    raise
+                self.halo_error = f"{type(exc).__name__}: {exc}"
+        self.halo = "peer" if self.peer is not None else ("nccl" if world > 1 else "local")
+        buffers = self.peer.buffers() if self.peer is not None else None
+        self.stepper = Stepper(self.local_spec, rows=self.slab.rows, body=body if has_body else None, buffers=buffers, **kw)
         self.owns_body = has_body
-        self.overlap = bool(overlap)
-        self._comm = torch.cuda.Stream() if self.overlap and self.slab.world > 1 else None
+        self.n_launch_per_step = self.stepper.n_launch_per_step + (1 if self.peer is not None else 0)
 
     # -- state in / out (reference convention F)
     def set_f_global(self, f_global):
@@ -191,15 +253,17 @@ class SlabStepper:
     # -- stepping
     def _exchange(self):
         st = self.stepper
-        if self._comm is None:
+        if self.peer is not None:
+            self.peer.push(st._cur)
+        else:
             wait_all(exchange_halo(st.state, self.slab, self.group))
-            return
-        # issue the exchange on a side stream so that it only orders against the kernels that produced the
-        # edge layers; the main stream waits for it before the next step reads the ghost layers
-        self._comm.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(self._comm):
-            wait_all(exchange_halo(st.state, self.slab, self.group))
-        torch.cuda.current_stream().wait_stream(self._comm)
+
+    def advance_raw(self, n=1):
+        """n x (fused step + halo exchange) on the current stream; graph-capturable with halo == "peer"."""
+        for _ in range(int(n)):
+            self.stepper.advance_raw(1)
+            self._exchange()
+        return self
 
     def step(self, n=1):
         st = self.stepper

@@ -41,7 +41,7 @@ def _parse_bc(name):
 
 class Stepper:
     def __init__(self, spec, device="cuda", rows=None, vec=0, body=None, dyn_mode="host", follow=1, use_graph=False,
-                 fuse_ib=True, fuse_edges=True, overlap=True):
+                 fuse_ib=True, fuse_edges=True, overlap=True, buffers=None):
         """rows: (begin, end) range of the slowest axis that is physical domain (ghost layers outside; slab
         decomposition).  body: dict(m, k, c, added_mass, n_dof=2, d0, v0, a0) for a moving rigid body coupled by
         Newmark-beta; dyn_mode "host" (reference-faithful, one tiny D2H/H2D per step) or "device"
@@ -62,7 +62,13 @@ class Stepper:
         self.vec = int(vec)
         self.use_graph = bool(use_graph)
         self._keep = []
-        self._bufs = [torch.zeros((self.q,) + self.shape, device=self.device, dtype=torch.float32) for _ in range(2)]
+        if buffers is None:
+            self._bufs = [torch.zeros((self.q,) + self.shape, device=self.device, dtype=torch.float32) for _ in range(2)]
+        else:   # caller-owned ping-pong buffers (e.g. peer-mapped symmetric memory for the multi-GPU halo)
+            self._bufs = list(buffers)
+            for b in self._bufs:
+                if tuple(b.shape) != (self.q,) + self.shape or b.dtype != torch.float32 or not b.is_cuda or not b.is_contiguous():
+                    raise ValueError("buffers must be two contiguous fp32 CUDA tensors of shape (Q, *shape)")
         self._cur = 0
         self._kind = None          # 'F' (reference state) or 'S' (post-collision state)
         self._tmp = None
