@@ -34,10 +34,13 @@ def test_recipe_matches_reference(golden, name, vec):
     spec, f0, n, key = dict(cases.all_fluid_cases(g))[name]
     st = run_stepper(spec, f0, n, vec=vec)
     assert_close(N(st.get_f()), g[key], what=name)
+    # marker forces (U - u_m) 2 ds are differences of nearly equal numbers and the spread uses fp32 atomics whose
+    # order varies from run to run: after 10 steps they agree to a few 1e-6..1e-5 of the largest force (3e-5 bound);
+    # the single-step force parity at 1e-5 is test_single_step_marker_force
     if name == "cylinder_c2":
-        assert_close(-N(st.marker_force), g["c2_h_last"], what="marker force")
+        assert_close(-N(st.marker_force), g["c2_h_last"], rtol=3e-5, what="marker force")
     if name == "sphere":
-        assert_close(-N(st.marker_force), g["sphere_h_last"], what="marker force")
+        assert_close(-N(st.marker_force), g["sphere_h_last"], rtol=3e-5, what="marker force")
 
 
 def test_get_f_is_idempotent_and_steps_compose(golden):
@@ -224,3 +227,17 @@ def test_moving_window_follows_body():
     for f, d in outs[1:]:
         assert_close(f, outs[0][0], what="moving body paths agree")
         assert_close(d, outs[0][1], rtol=1e-4, what="displacement")
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_single_step_marker_force(dim):
+    """north_star: IB forces within 1e-5 relative per step -- one step from the same state, CUDA vs oracle."""
+    if dim == 2:
+        spec = recipes.cylinder2d_spec(nx=96, ny=64, n_marker=64, radius=7.5, u0=0.08, nu=0.02, n_iter=5)
+    else:
+        spec = recipes.sphere3d_spec(nx=40, ny=24, nz=24, diameter=8.0, u0=0.05, re=100.0, n_iter=3, subdivisions=2)
+    f0 = recipes.uniform_init(spec, noise=2e-3, seed=4)
+    f_ref, h_ref = recipes.step(spec, f0)
+    st = run_stepper(spec, f0, 1)
+    assert_close(-N(st.marker_force), h_ref, what="single-step marker force")
+    assert_close(N(st.get_f()), f_ref, what="single-step f")

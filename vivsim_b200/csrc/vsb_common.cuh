@@ -77,6 +77,19 @@ __host__ __device__ constexpr int mirror_dir(int q, int axis) {
   return -1;
 }
 
+// Opposite-direction pairs (q, opp(q)) with q the smaller index: the rest population 0 plus NP pairs cover the
+// lattice.  Used to share work between a direction and its opposite: c_opp = -c, so (c.u)^2, c_a c_b and the
+// projected non-equilibrium part are equal for the two, and feq_q = A + B, feq_opp = A - B.
+template <int DIM> struct Pairs;
+template <> struct Pairs<2> {
+  static constexpr int NP = 4;
+  __host__ __device__ static constexpr int q(int k) { constexpr int t[4] = {1, 2, 5, 6}; return t[k]; }
+};
+template <> struct Pairs<3> {
+  static constexpr int NP = 9;
+  __host__ __device__ static constexpr int q(int k) { constexpr int t[9] = {1, 3, 5, 7, 8, 11, 12, 15, 16}; return t[k]; }
+};
+
 // ----------------------------------------------------------------------------- per-cell math
 // rho = sum f, u = sum c f / rho            (reference lbm/basic.py:107-110, lbm3d/basic.py:102-105)
 template <int DIM>
@@ -113,16 +126,25 @@ __device__ __forceinline__ float dot_c(int q, const float (&v)[Lat<DIM>::D]) {
 }
 
 // feq_q = rho w_q (1 + 3 c.u + 4.5 (c.u)^2 - 1.5 u.u)   (lbm/basic.py:132-135, lbm3d/basic.py:121-130)
+// evaluated per opposite pair: A = rho w (1 - 1.5 u.u + 4.5 (c.u)^2), B = 3 rho w (c.u); feq_q = A + B, feq_opp = A - B.
 template <int DIM>
 __device__ __forceinline__ void equilibrium(float rho, const float (&u)[Lat<DIM>::D], float (&feq)[Lat<DIM>::Q]) {
   using L = Lat<DIM>;
+  using P = Pairs<DIM>;
   float usq = 0.f;
 #pragma unroll
   for (int d = 0; d < L::D; ++d) usq += u[d] * u[d];
+  const float base = 1.0f - 1.5f * usq;
+  feq[0] = rho * L::w(0) * base;
 #pragma unroll
-  for (int q = 0; q < L::Q; ++q) {
+  for (int k = 0; k < P::NP; ++k) {
+    const int q = P::q(k);
     const float cu = dot_c<DIM>(q, u);
-    feq[q] = rho * L::w(q) * (1.0f + 3.0f * cu + 4.5f * cu * cu - 1.5f * usq);
+    const float rw = rho * L::w(q);
+    const float A = rw * (base + 4.5f * cu * cu);
+    const float B = 3.0f * rw * cu;
+    feq[q] = A + B;
+    feq[L::opp(q)] = A - B;
   }
 }
 
@@ -142,9 +164,15 @@ __device__ __forceinline__ void guo_term(const float (&g)[Lat<DIM>::D], const fl
 }
 
 // P fneq, P_qr = w_q/(2 cs^4) (c_q c_q - cs^2 I):(c_r c_r)   (lbm/collision/reg.py:23-47, lbm3d/collision/reg.py:10-41)
+// The result is the same for a direction and its opposite, so only pair[k] = (P fneq)_{q(k)} and rest = (P fneq)_0
+// are produced.
 template <int DIM>
-__device__ __forceinline__ void second_order_projection(const float (&fneq)[Lat<DIM>::Q], float (&out)[Lat<DIM>::Q]) {
+__device__ __forceinline__ void projection_pairs(const float (&fneq)[Lat<DIM>::Q], float& rest, float (&pair)[Pairs<DIM>::NP]) {
   using L = Lat<DIM>;
+  using P = Pairs<DIM>;
+  float e[P::NP];   // fneq_q + fneq_opp
+#pragma unroll
+  for (int k = 0; k < P::NP; ++k) e[k] = fneq[P::q(k)] + fneq[L::opp(P::q(k))];
   float pi[L::D][L::D];
 #pragma unroll
   for (int a = 0; a < L::D; ++a)
@@ -152,10 +180,10 @@ __device__ __forceinline__ void second_order_projection(const float (&fneq)[Lat<
     for (int b = a; b < L::D; ++b) {
       float s = 0.f;
 #pragma unroll
-      for (int q = 0; q < L::Q; ++q) {
-        const int cc = L::c(q, a + L::A0) * L::c(q, b + L::A0);
-        if (cc > 0) s += fneq[q];
-        if (cc < 0) s -= fneq[q];
+      for (int k = 0; k < P::NP; ++k) {
+        const int cc = L::c(P::q(k), a + L::A0) * L::c(P::q(k), b + L::A0);
+        if (cc > 0) s += e[k];
+        if (cc < 0) s -= e[k];
       }
       pi[a][b] = s;
       pi[b][a] = s;
@@ -163,19 +191,33 @@ __device__ __forceinline__ void second_order_projection(const float (&fneq)[Lat<
   float tr = 0.f;
 #pragma unroll
   for (int a = 0; a < L::D; ++a) tr += pi[a][a];
+  const float tr3 = tr * (1.0f / 3.0f);
+  rest = L::w(0) * 4.5f * (-tr3);
 #pragma unroll
-  for (int q = 0; q < L::Q; ++q) {
-    float s = 0.f;
+  for (int k = 0; k < P::NP; ++k) {
+    float s = -tr3;
 #pragma unroll
-    for (int a = 0; a < L::D; ++a)
+    for (int a = 0; a < L::D; ++a) {
+      if (L::c(P::q(k), a + L::A0) != 0) s += pi[a][a];
 #pragma unroll
-      for (int b = 0; b < L::D; ++b) {
-        const int cc = L::c(q, a + L::A0) * L::c(q, b + L::A0);
-        if (cc > 0) s += pi[a][b];
-        if (cc < 0) s -= pi[a][b];
+      for (int b = a + 1; b < L::D; ++b) {
+        const int cc = L::c(P::q(k), a + L::A0) * L::c(P::q(k), b + L::A0);
+        if (cc > 0) s += 2.0f * pi[a][b];
+        if (cc < 0) s -= 2.0f * pi[a][b];
       }
-    out[q] = L::w(q) * 4.5f * (s - tr * (1.0f / 3.0f));
+    }
+    pair[k] = L::w(P::q(k)) * 4.5f * s;
   }
+}
+
+template <int DIM>
+__device__ __forceinline__ void second_order_projection(const float (&fneq)[Lat<DIM>::Q], float (&out)[Lat<DIM>::Q]) {
+  using P = Pairs<DIM>;
+  float rest, pair[P::NP];
+  projection_pairs<DIM>(fneq, rest, pair);
+  out[0] = rest;
+#pragma unroll
+  for (int k = 0; k < P::NP; ++k) { out[P::q(k)] = pair[k]; out[Lat<DIM>::opp(P::q(k))] = pair[k]; }
 }
 
 // Relaxation constants prepared on the host exactly as Python evaluates them
@@ -206,43 +248,66 @@ __device__ __forceinline__ void collide_bgk(float (&f)[Lat<DIM>::Q], const float
 // feq + (1 - omega) P (f - feq)                           (lbm/collision/reg.py:49, lbm3d/collision/reg.py:60-62)
 template <int DIM>
 __device__ __forceinline__ void collide_reg(float (&f)[Lat<DIM>::Q], const float (&feq)[Lat<DIM>::Q], const Relax& r) {
-  constexpr int Q = Lat<DIM>::Q;
-  float fneq[Q], pr[Q];
+  using L = Lat<DIM>;
+  using P = Pairs<DIM>;
+  constexpr int Q = L::Q;
+  float rest, pair[P::NP];
 #pragma unroll
-  for (int q = 0; q < Q; ++q) fneq[q] = f[q] - feq[q];
-  second_order_projection<DIM>(fneq, pr);
+  for (int q = 0; q < Q; ++q) f[q] -= feq[q];   // fneq in place
+  projection_pairs<DIM>(f, rest, pair);
+  f[0] = feq[0] + r.one_minus_omega * rest;
 #pragma unroll
-  for (int q = 0; q < Q; ++q) f[q] = feq[q] + r.one_minus_omega * pr[q];
+  for (int k = 0; k < P::NP; ++k) {
+    const int q = P::q(k), o = L::opp(q);
+    const float v = r.one_minus_omega * pair[k];
+    f[q] = feq[q] + v;
+    f[o] = feq[o] + v;
+  }
 }
 
 // Entropic KBC.  2-D: shear part from N = Pxx - Pyy and Pxy only (lbm/collision/kbc.py:37-44);
 // 3-D: shear part = full second-order projection (lbm3d/collision/kbc.py:29-31).  Mixing: kbc.py:47-59 / :32-42.
+// In both lattices the shear part is equal for a direction and its opposite, so it is held per pair.
 template <int DIM>
 __device__ __forceinline__ void collide_kbc(float (&f)[Lat<DIM>::Q], const float (&feq)[Lat<DIM>::Q], const Relax& r) {
-  constexpr int Q = Lat<DIM>::Q;
-  float fneq[Q], sh[Q];
+  using L = Lat<DIM>;
+  using P = Pairs<DIM>;
+  constexpr int Q = L::Q;
+  float fneq[Q], sh0, sh[P::NP];
 #pragma unroll
   for (int q = 0; q < Q; ++q) fneq[q] = f[q] - feq[q];
   if constexpr (DIM == 2) {
     const float n4 = (fneq[1] - fneq[2] + fneq[3] - fneq[4]) * 0.25f;
     const float p4 = (fneq[5] - fneq[6] + fneq[7] - fneq[8]) * 0.25f;
-    sh[0] = 0.f;
-    sh[1] = n4; sh[2] = -n4; sh[3] = n4; sh[4] = -n4;
-    sh[5] = p4; sh[6] = -p4; sh[7] = p4; sh[8] = -p4;
+    sh0 = 0.f;
+    sh[0] = n4; sh[1] = -n4; sh[2] = p4; sh[3] = -p4;   // pairs (1,3) (2,4) (5,7) (6,8)
   } else {
-    second_order_projection<DIM>(fneq, sh);
+    projection_pairs<DIM>(fneq, sh0, sh);
   }
-  float s_sh = 0.f, s_hh = 0.f;
+  float s_sh, s_hh;
+  {
+    const float hi = fneq[0] - sh0;
+    const float inv = __fdividef(1.0f, feq[0] + 1e-20f);   // MUFU.RCP, <= 2 ulp
+    s_sh = hi * sh0 * inv;
+    s_hh = hi * hi * inv;
+  }
 #pragma unroll
-  for (int q = 0; q < Q; ++q) {
-    const float hi = fneq[q] - sh[q];
-    const float inv = __fdividef(1.0f, feq[q] + 1e-20f);   // MUFU.RCP, <= 2 ulp
-    s_sh += hi * sh[q] * inv;
-    s_hh += hi * hi * inv;
+  for (int k = 0; k < P::NP; ++k) {
+    const int q = P::q(k), o = L::opp(q);
+    const float hq = fneq[q] - sh[k], ho = fneq[o] - sh[k];
+    const float tq = hq * __fdividef(1.0f, feq[q] + 1e-20f), to = ho * __fdividef(1.0f, feq[o] + 1e-20f);
+    s_sh += sh[k] * (tq + to);
+    s_hh += hq * tq + ho * to;
   }
   const float half_gamma = r.inv_omega - r.one_minus_inv_omega * s_sh / (s_hh + 1e-20f);
+  // f -= omega (sh + hg (fneq - sh)); keep the difference (fneq - sh) explicit: hg can be large where it is tiny
+  f[0] -= r.omega * (sh0 + half_gamma * (fneq[0] - sh0));
 #pragma unroll
-  for (int q = 0; q < Q; ++q) f[q] -= r.omega * (sh[q] + half_gamma * (fneq[q] - sh[q]));
+  for (int k = 0; k < P::NP; ++k) {
+    const int q = P::q(k), o = L::opp(q);
+    f[q] -= r.omega * (sh[k] + half_gamma * (fneq[q] - sh[k]));
+    f[o] -= r.omega * (sh[k] + half_gamma * (fneq[o] - sh[k]));
+  }
 }
 
 // f + A (feq - f), A given                               (lbm/collision/mrt.py:88, lbm3d/collision/mrt.py:96-98)

@@ -40,7 +40,7 @@ __device__ __forceinline__ void store_vec(float* __restrict__ p, const float (&v
 }
 
 template <int DIM, int COLL, int VEC>
-__global__ void __launch_bounds__(256) k_step(const StepParams<DIM> p, const MrtMats<DIM, COLL == VSB_COLL_MRT> mm) {
+__global__ void __launch_bounds__(256, (DIM == 3) ? 2 : 3) k_step(const StepParams<DIM> p, const MrtMats<DIM, COLL == VSB_COLL_MRT> mm) {
   using L = Lat<DIM>;
   constexpr int Q = L::Q;
   const int nv = p.n2 / VEC;
@@ -477,7 +477,9 @@ static int step_impl(const VsbStepArgs& a, cudaStream_t s) {
     }
   }
   int vec = a.vec;
-  if (vec == 0) vec = (DIM == 2) ? 4 : 2;
+  // measured on B200 (scripts/vec_sweep.py): 4 cells per thread (128-bit accesses) is fastest for every lattice and
+  // collision model once the kernel is held to 128 registers
+  if (vec == 0) vec = 4;
   while (vec > 1 && (p.n2 % vec != 0 || ((uintptr_t)a.f_in % (4 * vec)) || ((uintptr_t)a.f_out % (4 * vec)))) vec >>= 1;
   VSB_REQUIRE(vec == 1 || vec == 2 || vec == 4, "vsb_step: vec must be 0, 1, 2 or 4");
   const int nrow = (p.band == 2) ? std::min(p.wsz[0], p.r_end - p.r_begin) : p.r_end - p.r_begin;
