@@ -34,7 +34,7 @@ sys.path.insert(0, ROOT)
 METRIC = "MLUPS (IB-LBM step, D2Q9 1024x1024 VIV cylinder, 512 markers, MDF + Guo)"
 L2_BYTES = 126e6
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_step<2,BGK,vec4> launch at 1024^2 (ncu --set full, profiles/)
-TRAFFIC_NCU = 39.4e6
+TRAFFIC_NCU = 39.4e6   # 37.88 MB read + 1.5 MB written to DRAM during the launch (the rest of the writes leave L2 later)
 
 
 def peaks():
@@ -422,7 +422,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20000)
+    ap.add_argument("--steps", type=int, default=50000)
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extra", action="store_true", help="skip the C3 / C4 single-GPU measurements")

@@ -212,6 +212,12 @@ int vsb_ib_window_moments(const VsbStepArgs* args, float* u_win, vsb_stream_t st
  * origin2[parity ^ 1] <- window origin for the next step.  `parity` is the parity of the step being completed. */
 int vsb_body_newmark(VsbBodyState* body, const VsbBodyParams* params, int parity, vsb_stream_t stream);
 
+/* The same body update with the ODE on the HOST (north_star keeps dyn.py's rigid-body ODE on the host): copies the
+ * body state to `pinned` (page-locked host memory), SYNCHRONISES `stream`, advances (a, v, d) on the CPU, and copies
+ * the state back asynchronously.  The only entry point that synchronises. */
+int vsb_body_newmark_host(VsbBodyState* body, VsbBodyState* pinned, const VsbBodyParams* params, int parity,
+                          vsb_stream_t stream);
+
 /* The whole immersed-boundary part of one step in ONE kernel (single CTA, scratch in shared memory):
  * velocity at the stencil points from the streamed state, all multi-direct-forcing iterations, the force field
  * written to mdf->g_win (every window cell, no memset needed), the body update of vsb_body_newmark.

@@ -11,9 +11,9 @@ echo "== smoke" ; python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail
 echo "== bench" ; python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err ; tail -c 3000 $OUT/bench_$TAG.json ; tail -5 $OUT/bench_$TAG.err
 echo "== bench reference arm" ; python bench.py --impl reference --steps 200 > $OUT/bench_ref_$TAG.json 2>> $OUT/bench_$TAG.err ; cat $OUT/bench_ref_$TAG.json
 echo "== ncu launch list"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_$TAG.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 -s 300 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --steps 36 --warmup 18 --no-extra --no-cpu-baseline > $OUT/ncu_bench_$TAG.log 2>&1
 echo "== ncu full capture of the fused kernel"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_step -s 40 -c 3 -f -o $OUT/prof_step2d_$TAG \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_step -s 60 -c 4 -f -o $OUT/prof_step2d_$TAG \
     python bench.py --steps 36 --warmup 18 --no-extra --no-cpu-baseline >> $OUT/ncu_bench_$TAG.log 2>&1
 ls -la $OUT | tail -20

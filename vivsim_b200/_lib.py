@@ -25,7 +25,7 @@ EXPORTS = [
     "vsb_guo_forcing_term", "vsb_forcing", "vsb_post_op", "vsb_boundary_characteristic", "vsb_ib_delta",
     "vsb_ib_stencil", "vsb_ib_interpolate", "vsb_ib_spread", "vsb_ib_mdf", "vsb_step", "vsb_ib_window_moments",
     "vsb_body_newmark", "vsb_edge_fused", "vsb_edge_fused_supported", "vsb_ib_fused", "vsb_ib_fused_supported",
-    "vsb_halo_push",
+    "vsb_halo_push", "vsb_body_newmark_host",
 ]
 
 

@@ -339,6 +339,37 @@ int vsb_ib_mdf(const VsbStepArgs* args, const VsbMdfArgs* a, const VsbBodyParams
   return a->dim == 2 ? mdf_impl<2>(*args, *a, params, (cudaStream_t)stream) : mdf_impl<3>(*args, *a, params, (cudaStream_t)stream);
 }
 
+int vsb_body_newmark_host(VsbBodyState* body, VsbBodyState* pinned, const VsbBodyParams* bp, int parity,
+                          vsb_stream_t stream) {
+  VSB_REQUIRE(body && pinned && bp, "vsb_body_newmark_host: null argument");
+  VSB_REQUIRE(bp->n_dof >= 1 && bp->n_dof <= 3, "n_dof must be 1..3, got %d", bp->n_dof);
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaMemcpyAsync(pinned, body, sizeof(VsbBodyState), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return cuda_fail(e, "vsb_body_newmark_host (device -> host)");
+  // dyn.py:27-51 with gamma = 1/2, beta = 1/4, dt = 1, in fp32 like the reference's jnp arithmetic;
+  // h = sum(-F) + a * added_mass (examples/2d/vortex_induced_vibration.py:135-136)
+  const float denom = (float)(bp->m + 0.5 * bp->c + 0.25 * bp->k);
+  const float k = (float)bp->k, c = (float)bp->c, am = (float)bp->added_mass;
+  for (int i = 0; i < bp->n_dof; ++i) {
+    const float h = -pinned->force_sum[i] + pinned->a[i] * am;
+    const float v1 = pinned->v[i] + 0.5f * pinned->a[i];
+    const float d1 = pinned->d[i] + pinned->v[i] + 0.25f * pinned->a[i];
+    const float a_next = (h - c * v1 - k * d1) / denom;
+    pinned->h[i] = h;
+    pinned->a[i] = a_next;
+    pinned->v[i] = 0.5f * a_next + v1;
+    pinned->d[i] = 0.25f * a_next + d1;
+  }
+  for (int i = 0; i < 3; ++i) pinned->force_sum[i] = 0.f;
+  const int dim = bp->grid_size[2] <= 1 ? 2 : 3;
+  for (int d = 0; d < dim; ++d)
+    pinned->origin2[(parity & 1) ^ 1][d] = origin_rule(bp->follow, bp->origin0[d], pinned->d[d], bp->grid_size[d], bp->win_size[d]);
+  e = cudaMemcpyAsync(body, pinned, sizeof(VsbBodyState), cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return cuda_fail(e, "vsb_body_newmark_host (host -> device)");
+  return VSB_OK;
+}
+
 int vsb_body_newmark(VsbBodyState* body, const VsbBodyParams* params, int parity, vsb_stream_t stream) {
   VSB_REQUIRE(body != nullptr && params != nullptr, "vsb_body_newmark: null argument");
   VSB_REQUIRE(params->n_dof >= 1 && params->n_dof <= 3, "n_dof must be 1..3, got %d", params->n_dof);

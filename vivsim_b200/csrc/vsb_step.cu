@@ -39,8 +39,13 @@ __device__ __forceinline__ void store_vec(float* __restrict__ p, const float (&v
   *reinterpret_cast<T*>(p) = t;
 }
 
+// register budget: 128 (2 CTAs / SM) in 3-D; in 2-D 64 (4 CTAs) for BGK / regularised, 85 (3 CTAs) for KBC / MRT
+template <int DIM, int COLL> constexpr int step_min_ctas() {
+  return DIM == 3 ? 2 : ((COLL == VSB_COLL_KBC || COLL == VSB_COLL_MRT) ? 3 : 4);
+}
+
 template <int DIM, int COLL, int VEC>
-__global__ void __launch_bounds__(256, (DIM == 3) ? 2 : 3) k_step(const StepParams<DIM> p, const MrtMats<DIM, COLL == VSB_COLL_MRT> mm) {
+__global__ void __launch_bounds__(256, step_min_ctas<DIM, COLL>()) k_step(const StepParams<DIM> p, const MrtMats<DIM, COLL == VSB_COLL_MRT> mm) {
   using L = Lat<DIM>;
   constexpr int Q = L::Q;
   const int nv = p.n2 / VEC;

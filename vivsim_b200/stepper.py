@@ -27,7 +27,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from . import _api, _lib as L, dyn as _dyn
+from . import _api, _lib as L
 
 _WRAPS = ("velocity", "pressure", "force_corrected")
 
@@ -229,6 +229,9 @@ class Stepper:
                 bp.grid_size[d] = self.shape[d] if d < dim else 1
                 bp.win_size[d] = self.win_size[d] if d < dim else 1
             self._bparams = bp
+            hp = L.VsbBodyParams.from_buffer_copy(bp)      # host-ODE variant: same numbers, n_dof always set
+            hp.n_dof = self.n_dof
+            self._hparams = hp
             self._body_dev = torch.zeros(L.BODY_BYTES // 4, device=dev, dtype=torch.float32)
             self._body_pin = torch.zeros(L.BODY_BYTES // 4, dtype=torch.float32).pin_memory()
             st = self._body_pin.numpy()
@@ -332,27 +335,33 @@ class Stepper:
         with_ib = self.ib is not None and do_collide
         a.edges = 1 if (has_ops and self.edge_fused) else 0
         a.band = 0
+        main = torch.cuda.current_stream()
+        st_main = C.c_void_p(main.cuda_stream)
+        ref = C.byref(a)
         if not (self.overlap and with_ib):
             if with_ib:
-                self._ib_part(L.stream())
-            L.check(lib.vsb_step(C.byref(a), L.stream()))
+                self._ib_part(st_main)
+            L.check(lib.vsb_step(ref, st_main))
             if a.edges:
-                L.check(lib.vsb_edge_fused(C.byref(a), L.stream()))
+                L.check(lib.vsb_edge_fused(ref, st_main))
         else:
-            main = torch.cuda.current_stream()
             s_ib, s_edge = self._side
+            st_ib = C.c_void_p(s_ib.cuda_stream)
             s_ib.wait_stream(main)
+            host_body = self.body is not None and self.dyn_mode == "host"
+            if host_body:
+                # the host ODE synchronises the IB stream: get the bulk going first so it runs meanwhile
+                a.band = 1
+                L.check(lib.vsb_step(ref, st_main))
+            self._ib_part(st_ib)                               # IB chain (its few CTAs should not queue behind
+            a.band = 2                                         # the bulk), then the window's x-range
+            L.check(lib.vsb_step(ref, st_ib))
+            if not host_body:
+                a.band = 1                                     # everything but the window's x-range
+                L.check(lib.vsb_step(ref, st_main))
             if a.edges:
                 s_edge.wait_stream(main)
-            with torch.cuda.stream(s_ib):                     # IB chain first (its few CTAs should not queue
-                self._ib_part(L.stream())                     # behind the bulk), then the window's x-range
-                a.band = 2
-                L.check(lib.vsb_step(C.byref(a), L.stream()))
-            a.band = 1                                        # everything but the window's x-range
-            L.check(lib.vsb_step(C.byref(a), L.stream()))
-            if a.edges:
-                with torch.cuda.stream(s_edge):
-                    L.check(lib.vsb_edge_fused(C.byref(a), L.stream()))
+                L.check(lib.vsb_edge_fused(ref, C.c_void_p(s_edge.cuda_stream)))
                 main.wait_stream(s_edge)
             main.wait_stream(s_ib)
             a.band = 0
@@ -360,7 +369,7 @@ class Stepper:
             self._parity ^= 1
 
     def _ib_part(self, st):
-        """Immersed-boundary force of this pass on stream `st` (the current stream), then the body update."""
+        """Immersed-boundary force of this pass on stream `st`, then the body update."""
         lib, a, m = L.lib(), self._args, self._mdf
         par = self._parity
         m.parity = par
@@ -368,31 +377,15 @@ class Stepper:
         m.g_win, m.g_win_next = buf[par, 0].data_ptr(), buf[par ^ 1, 0].data_ptr()
         if self.n_iter > 1:
             m.scratch, m.scratch_next = buf[par, 1].data_ptr(), buf[par ^ 1, 1].data_ptr()
-        host_body = self.body is not None and self.dyn_mode == "host"
         bp = C.byref(self._bparams) if self._bparams is not None else None
         if self.ib_fused:
             L.check(lib.vsb_ib_fused(C.byref(a), C.byref(m), bp, st))
         else:
             L.check(lib.vsb_ib_mdf(C.byref(a), C.byref(m), bp, st))
-        if host_body:
-            self._host_newmark()
-
-    def _host_newmark(self):
-        """Rigid-body ODE on the host as in the reference recipe: h = sum(-F) + a * added_mass; Newmark-beta.
-        One 84-byte device->host read and one host->device write on the current stream."""
-        b = self.body
-        self._body_pin.copy_(self._body_dev, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        s = self._body_pin.numpy()
-        n = self.n_dof
-        d, v, acc = s[0:n].copy(), s[3:3 + n].copy(), s[6:6 + n].copy()
-        h = (-s[12:12 + n] + acc * np.float32(b["added_mass"])).astype(np.float32)
-        a2, v2, d2 = _dyn.newmark(acc, v, d, h, b["m"], b["k"], b["c"])
-        s[0:n], s[3:3 + n], s[6:6 + n], s[9:9 + n] = d2, v2, a2, h
-        s[12:15] = 0
-        nxt = 15 + 3 * (self._parity ^ 1)
-        s.view(np.int32)[nxt:nxt + 3] = self._origin_for(s[0:3])
-        self._body_dev.copy_(self._body_pin, non_blocking=True)
+        if self.body is not None and self.dyn_mode == "host":
+            # rigid-body ODE on the host (north_star): 88 B device -> host, Newmark-beta on the CPU, 88 B back
+            L.check(lib.vsb_body_newmark_host(C.c_void_p(self._body_dev.data_ptr()), C.c_void_p(self._body_pin.data_ptr()),
+                                              C.byref(self._hparams), par, st))
 
     def _advance(self):
         src, dst = self._bufs[self._cur], self._bufs[1 - self._cur]
