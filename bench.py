@@ -266,9 +266,10 @@ def run_ours(args):
         if peer:    # halo kernels are part of the step graph: same replay loop as on one GPU
             graph = build_graph(steppers, steps_each)
             loop = lambda n: run_loop(graph, steppers, steps_each, n)
-            exchange = ("vsb_halo_push: one kernel per step stores the 3 crossing populations' edge rows (4 KB each) "
-                        "into the neighbours' ghost rows through peer-mapped symmetric memory (NVLink) and hand-shakes "
-                        "with flag words; captured in the step's CUDA graph, no NCCL on the data path")
+            exchange = ("peer-mapped symmetric memory over NVLink, inside the step's CUDA graph, no NCCL on the data path: "
+                        "interior rows start at once; a second stream waits for the neighbours' flag words "
+                        "(vsb_halo_wait), updates the two edge rows and stores the 3 crossing populations' edge rows "
+                        "(4 KB each) into the neighbours' ghost rows (vsb_halo_send)")
         else:
             graph = None
 

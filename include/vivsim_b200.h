@@ -189,6 +189,9 @@ typedef struct {
                                  2: only that x-range (lets the bulk run concurrently with the IB kernels) */
   int edges;                  /* 0: ordered wall fix-up inside vsb_step; 1: none -- the caller runs
                                  vsb_edge_fused and the fused pass leaves those wall layers untouched */
+  int sub_begin, sub_end;     /* rows of [row_begin, row_end) this launch updates (sub_end = 0: all of them);
+                                 lets edge rows, which read ghost layers, run later than the interior */
+  int edge_rows_only;         /* 1: update just the first and the last physical row (ignores sub_begin / sub_end) */
 } VsbStepArgs;
 
 int vsb_step(const VsbStepArgs* args, vsb_stream_t stream);
@@ -247,6 +250,14 @@ typedef struct {
 } VsbHaloArgs;
 
 int vsb_halo_push(const VsbHaloArgs* args, vsb_stream_t stream);
+
+/* The two halves of vsb_halo_push for overlapping the hand-shake with compute:
+ *   vsb_halo_send   copy the edge layers into the neighbours' ghost layers and publish the step number (no wait);
+ *   vsb_halo_wait   wait until both neighbours have published the current step number.
+ * Per step: interior rows (no ghost dependency) run at once; vsb_halo_wait -> edge rows -> vsb_halo_send run on a
+ * second stream.  vsb_halo_push == send followed by wait. */
+int vsb_halo_send(const VsbHaloArgs* args, vsb_stream_t stream);
+int vsb_halo_wait(const VsbHaloArgs* args, vsb_stream_t stream);
 
 #ifdef __cplusplus
 }

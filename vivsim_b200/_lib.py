@@ -25,7 +25,7 @@ EXPORTS = [
     "vsb_guo_forcing_term", "vsb_forcing", "vsb_post_op", "vsb_boundary_characteristic", "vsb_ib_delta",
     "vsb_ib_stencil", "vsb_ib_interpolate", "vsb_ib_spread", "vsb_ib_mdf", "vsb_step", "vsb_ib_window_moments",
     "vsb_body_newmark", "vsb_edge_fused", "vsb_edge_fused_supported", "vsb_ib_fused", "vsb_ib_fused_supported",
-    "vsb_halo_push", "vsb_body_newmark_host",
+    "vsb_halo_push", "vsb_body_newmark_host", "vsb_halo_send", "vsb_halo_wait",
 ]
 
 
@@ -72,7 +72,7 @@ class VsbStepArgs(C.Structure):
                 ("f_out", C.c_void_p), ("g_uniform", C.c_float * 3), ("g_win", C.c_void_p),
                 ("win_origin", C.c_int * 3), ("win_size", C.c_int * 3), ("body", C.c_void_p), ("parity", C.c_int),
                 ("n_post", C.c_int), ("post", C.POINTER(VsbPostOp)), ("vec", C.c_int), ("band", C.c_int),
-                ("edges", C.c_int)]
+                ("edges", C.c_int), ("sub_begin", C.c_int), ("sub_end", C.c_int), ("edge_rows_only", C.c_int)]
 
 
 class VsbHaloArgs(C.Structure):

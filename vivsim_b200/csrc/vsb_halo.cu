@@ -30,7 +30,9 @@ struct HaloParams {
   unsigned* counter;               // [0] step number, [1] CTA ticket, [2] set to 1 if a wait timed out
 };
 
-__global__ void k_halo_push(const HaloParams p) {
+// mode bit 0: copy + publish; bit 1: wait
+__global__ void k_halo_push(const HaloParams p, const int mode) {
+  if (mode & 1) {
   // copy: blockIdx.y selects (direction, population); x covers the layer in float4 units when aligned
   const int job = blockIdx.y;
   const bool to_right = job < p.n_dirs;
@@ -47,23 +49,28 @@ __global__ void k_halo_push(const HaloParams p) {
   } else {
     for (long long i = t; i < p.row_elems; i += stride) dst[i] = src[i];
   }
-  // publish + wait, by the last CTA to finish copying
+  }
+  // publish (+ wait), by the last CTA to finish copying
   __threadfence_system();
   __shared__ int s_last;
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned total = gridDim.x * gridDim.y;
-    s_last = (atomicAdd(&p.counter[1], 1u) == total - 1);
+    s_last = (mode & 1) ? (atomicAdd(&p.counter[1], 1u) == total - 1) : 1;
   }
   __syncthreads();
   if (s_last && threadIdx.x == 0) {
-    __threadfence_system();
-    p.counter[1] = 0;
-    const unsigned step = p.counter[0] + 1;
-    p.counter[0] = step;
-    p.left_flags[1] = step;    // "your right neighbour has delivered step `step`"
-    p.right_flags[0] = step;   // "your left neighbour has delivered step `step`"
-    __threadfence_system();
+    unsigned step = p.counter[0];
+    if (mode & 1) {
+      __threadfence_system();
+      p.counter[1] = 0;
+      step += 1;
+      p.counter[0] = step;
+      p.left_flags[1] = step;    // "your right neighbour has delivered step `step`"
+      p.right_flags[0] = step;   // "your left neighbour has delivered step `step`"
+      __threadfence_system();
+    }
+    if (!(mode & 2)) return;
     unsigned long long t0, t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     while ((int)(p.my_flags[0] - step) < 0 || (int)(p.my_flags[1] - step) < 0) {
@@ -79,14 +86,12 @@ __global__ void k_halo_push(const HaloParams p) {
 
 using namespace vsb;
 
-extern "C" {
-
-int vsb_halo_push(const VsbHaloArgs* a, vsb_stream_t stream) {
-  VSB_REQUIRE(a != nullptr, "vsb_halo_push: null args");
+static int halo_launch(const VsbHaloArgs* a, int mode, vsb_stream_t stream) {
+  VSB_REQUIRE(a != nullptr, "vsb_halo: null args");
   VSB_REQUIRE(a->grid.dim == 2 || a->grid.dim == 3, "dim must be 2 or 3, got %d", a->grid.dim);
   VSB_REQUIRE(a->state && a->left_state && a->right_state && a->my_flags && a->left_flags && a->right_flags && a->counter,
-              "vsb_halo_push: null pointer");
-  VSB_REQUIRE(a->grid.nx >= 6, "vsb_halo_push: the local extent needs at least 4 physical layers plus 2 ghost layers");
+              "vsb_halo: null pointer");
+  VSB_REQUIRE(a->grid.nx >= 6, "vsb_halo: the local extent needs at least 4 physical layers plus 2 ghost layers");
   HaloParams p;
   p.row_elems = (long long)a->grid.ny * (a->grid.dim == 3 ? a->grid.nz : 1);
   p.plane_elems = (long long)a->grid.nx * p.row_elems;
@@ -103,11 +108,21 @@ int vsb_halo_push(const VsbHaloArgs* a, vsb_stream_t stream) {
   p.state = a->state; p.left_state = a->left_state; p.right_state = a->right_state;
   p.my_flags = a->my_flags; p.left_flags = a->left_flags; p.right_flags = a->right_flags; p.counter = a->counter;
   const int block = 256;
-  long long per = (p.row_elems / 4 + block - 1) / block;
-  const unsigned gx = (unsigned)(per < 1 ? 1 : (per > 64 ? 64 : per));
-  k_halo_push<<<dim3(gx, 2 * p.n_dirs), block, 0, (cudaStream_t)stream>>>(p);
-  VSB_LAUNCH_CHECK("vsb_halo_push");
+  if (mode == 2) {   // wait only: one thread
+    k_halo_push<<<dim3(1, 1), 32, 0, (cudaStream_t)stream>>>(p, mode);
+  } else {
+    long long per = (p.row_elems / 4 + block - 1) / block;
+    const unsigned gx = (unsigned)(per < 1 ? 1 : (per > 64 ? 64 : per));
+    k_halo_push<<<dim3(gx, 2 * p.n_dirs), block, 0, (cudaStream_t)stream>>>(p, mode);
+  }
+  VSB_LAUNCH_CHECK("vsb_halo");
   return VSB_OK;
 }
+
+extern "C" {
+
+int vsb_halo_push(const VsbHaloArgs* a, vsb_stream_t stream) { return halo_launch(a, 3, stream); }
+int vsb_halo_send(const VsbHaloArgs* a, vsb_stream_t stream) { return halo_launch(a, 1, stream); }
+int vsb_halo_wait(const VsbHaloArgs* a, vsb_stream_t stream) { return halo_launch(a, 2, stream); }
 
 }  // extern "C"

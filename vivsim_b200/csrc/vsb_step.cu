@@ -53,9 +53,9 @@ __global__ void __launch_bounds__(256, step_min_ctas<DIM, COLL>()) k_step(const 
   window_origin<DIM>(p, worg);
   // rows of the slowest axis handled by this launch: all of [r_begin, r_end), or only / all but the x-range of
   // the force window (band), so that the bulk can run while the IB kernels still produce the window's force
-  const int band_lo = max(p.r_begin, worg[0]), band_hi = min(p.r_end, worg[0] + p.wsz[0]);
-  const int row0 = (p.band == 2) ? band_lo : p.r_begin;
-  const int nrow = (p.band == 2) ? max(band_hi - band_lo, 0) : p.r_end - p.r_begin;
+  const int band_lo = max(p.s_begin, worg[0]), band_hi = min(p.s_end, worg[0] + p.wsz[0]);
+  const int row0 = (p.band == 2) ? band_lo : p.s_begin;
+  const int nrow = p.edge_rows ? 2 : ((p.band == 2) ? max(band_hi - band_lo, 0) : p.s_end - p.s_begin);
   const long long rows = (DIM == 2) ? (long long)nrow : (long long)nrow * p.n1;
   const long long total = rows * nv;
   long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -63,8 +63,10 @@ __global__ void __launch_bounds__(256, step_min_ctas<DIM, COLL>()) k_step(const 
   if (!active) gid = 0;          // the lane stays in the shuffles; it loads and stores nothing
   const int j = (int)(gid % nv);
   const long long row = gid / nv;
-  const int i0 = (DIM == 2) ? 0 : row0 + (int)(row / p.n1);
-  const int i1 = (DIM == 2) ? row0 + (int)row : (int)(row % p.n1);
+  const int rx = (DIM == 2) ? (int)row : (int)(row / p.n1);          // row counter along the slowest axis
+  const int ix0 = p.edge_rows ? (rx == 0 ? p.r_begin : p.r_end - 1) : row0 + rx;
+  const int i0 = (DIM == 2) ? 0 : ix0;
+  const int i1 = (DIM == 2) ? ix0 : (int)(row % p.n1);
   const int i2 = j * VEC;
   const int lane = threadIdx.x & 31;
   const long long ncell = (long long)p.n0 * p.n1 * p.n2;
@@ -335,6 +337,12 @@ int fill_params(const VsbStepArgs& a, StepParams<DIM>& p) {
   p.r_end = a.row_end > 0 ? a.row_end : nrows;
   VSB_REQUIRE(0 <= p.r_begin && p.r_begin < p.r_end && p.r_end <= nrows, "vsb_step: bad row range [%d, %d) of %d",
               a.row_begin, a.row_end, nrows);
+  p.s_begin = a.sub_end > 0 ? a.sub_begin : p.r_begin;
+  p.s_end = a.sub_end > 0 ? a.sub_end : p.r_end;
+  p.edge_rows = a.edge_rows_only ? 1 : 0;
+  VSB_REQUIRE(!p.edge_rows || (a.band == 0 && p.r_end - p.r_begin >= 2), "vsb_step: edge_rows_only needs band = 0 and >= 2 rows");
+  VSB_REQUIRE(p.r_begin <= p.s_begin && p.s_begin < p.s_end && p.s_end <= p.r_end,
+              "vsb_step: sub-range [%d, %d) outside the rows [%d, %d)", a.sub_begin, a.sub_end, p.r_begin, p.r_end);
   VSB_REQUIRE(a.f_in && a.f_out && a.f_in != a.f_out, "vsb_step: f_in / f_out must be distinct non-null buffers");
   p.fin = a.f_in; p.fout = a.f_out;
   p.do_stream = a.do_stream; p.do_collide = a.do_collide; p.forcing = a.forcing;
@@ -487,7 +495,7 @@ static int step_impl(const VsbStepArgs& a, cudaStream_t s) {
   if (vec == 0) vec = 4;
   while (vec > 1 && (p.n2 % vec != 0 || ((uintptr_t)a.f_in % (4 * vec)) || ((uintptr_t)a.f_out % (4 * vec)))) vec >>= 1;
   VSB_REQUIRE(vec == 1 || vec == 2 || vec == 4, "vsb_step: vec must be 0, 1, 2 or 4");
-  const int nrow = (p.band == 2) ? std::min(p.wsz[0], p.r_end - p.r_begin) : p.r_end - p.r_begin;
+  const int nrow = p.edge_rows ? 2 : ((p.band == 2) ? std::min(p.wsz[0], p.s_end - p.s_begin) : p.s_end - p.s_begin);
   const long long rows = (DIM == 2) ? (long long)nrow : (long long)nrow * p.n1;
   const long long total = rows * (p.n2 / vec);
   constexpr int kBlock = 256;
@@ -498,7 +506,8 @@ static int step_impl(const VsbStepArgs& a, cudaStream_t s) {
   VSB_LAUNCH_CHECK("vsb_step (fused kernel)");
 
   if (!have_ops || a.edges == 1) return VSB_OK;
-  VSB_REQUIRE(a.band == 0, "vsb_step: the ordered wall fix-up (edges = 0) cannot be combined with band modes");
+  VSB_REQUIRE(a.band == 0 && !p.edge_rows && p.s_begin == p.r_begin && p.s_end == p.r_end,
+              "vsb_step: the ordered wall fix-up (edges = 0) cannot be combined with band modes or row sub-ranges");
   // layers touched by face operations: wall layer and adjacent fluid layer of each face
   LineSet ls;
   ls.n = 0;

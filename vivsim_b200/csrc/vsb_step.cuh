@@ -20,7 +20,9 @@ __device__ __forceinline__ void static_for(F&& body) {
 
 template <int DIM> struct StepParams {
   int n0, n1, n2;
-  int r_begin, r_end;   // rows of array axis A0 (the slowest real axis) to update
+  int r_begin, r_end;   // physical rows of array axis A0 (the slowest real axis); ghost layers lie outside
+  int s_begin, s_end;   // rows this launch updates, within [r_begin, r_end)
+  int edge_rows;        // 1: only rows r_begin and r_end - 1
   const float* fin;
   float* fout;
   int do_stream, do_collide, forcing;

@@ -130,10 +130,20 @@ class PeerHalo:
     def buffers(self):
         return [self.buf[0], self.buf[1]]
 
-    def push(self, index):
-        """Exchange the ghost layers of buffer `index` on the current stream."""
+    def push(self, index, st=None):
+        """Send the edge layers of buffer `index` and wait for the neighbours' (stream `st` or the current one)."""
         L, C = self._L, self._C
-        L.check(L.lib().vsb_halo_push(C.byref(self.args[index]), L.stream()))
+        L.check(L.lib().vsb_halo_push(C.byref(self.args[index]), st if st is not None else L.stream()))
+
+    def send(self, index, st=None):
+        """Copy the edge layers of buffer `index` into the neighbours' ghost layers and publish the step number."""
+        L, C = self._L, self._C
+        L.check(L.lib().vsb_halo_send(C.byref(self.args[index]), st if st is not None else L.stream()))
+
+    def wait(self, st=None):
+        """Wait until both neighbours have published the current step number."""
+        L, C = self._L, self._C
+        L.check(L.lib().vsb_halo_wait(C.byref(self.args[0]), st if st is not None else L.stream()))
 
     def timed_out(self):
         return bool(self.counter[2].item())
@@ -217,7 +227,9 @@ class SlabStepper:
         buffers = self.peer.buffers() if self.peer is not None else None
         self.stepper = Stepper(self.local_spec, rows=self.slab.rows, body=body if has_body else None, buffers=buffers, **kw)
         self.owns_body = has_body
-        self.n_launch_per_step = self.stepper.n_launch_per_step + (1 if self.peer is not None else 0)
+        if self.peer is not None:
+            self.stepper.attach_halo(self.peer)     # the halo kernels become part of every pass of the stepper
+        self.n_launch_per_step = self.stepper.n_launch_per_step
 
     # -- state in / out (reference convention F)
     def set_f_global(self, f_global):
@@ -230,6 +242,8 @@ class SlabStepper:
 
     def get_f_local(self):
         """Physical rows of F_n on this rank, shape (Q, nx_local, ...)."""
+        if self.peer is not None and self.stepper._kind == "S":
+            self.peer.wait()                      # the neighbours' last sends into this rank's ghost layers
         return self.stepper.get_f()[:, 1:-1].contiguous()
 
     def gather_f(self):
@@ -252,11 +266,8 @@ class SlabStepper:
 
     # -- stepping
     def _exchange(self):
-        st = self.stepper
-        if self.peer is not None:
-            self.peer.push(st._cur)
-        else:
-            wait_all(exchange_halo(st.state, self.slab, self.group))
+        if self.peer is None:                     # peer mode: the stepper's passes already contain the halo kernels
+            wait_all(exchange_halo(self.stepper.state, self.slab, self.group))
 
     def advance_raw(self, n=1):
         """n x (fused step + halo exchange) on the current stream; graph-capturable with halo == "peer"."""

@@ -75,6 +75,7 @@ class Stepper:
         self._graph = None
         self.n_launch_per_step = 0
         self._parity = 0
+        self.halo = None
         self._want = dict(fuse_ib=bool(fuse_ib), fuse_edges=bool(fuse_edges), overlap=bool(overlap))
         self._side = None
 
@@ -278,6 +279,19 @@ class Stepper:
             n += 1 if self.ib_fused else self.n_iter
         return n
 
+    def attach_halo(self, halo):
+        """Multi-GPU slabs: `halo` (multidevice.PeerHalo) exchanges ghost layers inside every collide pass.  When all
+        face operations sit on x faces (or there are none) the exchange is pipelined: interior rows start at once,
+        while a second stream waits for the neighbours, updates the two edge rows and sends them on."""
+        self.halo = halo
+        locs = [self._post[i].loc for i in range(self._args.n_post) if self._post[i].kind != L.BC["mask"]]
+        x_only = all(loc in (L.LOC["left"], L.LOC["right"]) for loc in locs)
+        self.halo_pipelined = (self.rows[1] - self.rows[0] >= 4) and (not locs or (self.edge_fused and x_only))
+        if self._side is None:
+            self._side = [torch.cuda.Stream(device=self.device) for _ in range(2)]
+        self._halo_stream = torch.cuda.Stream(device=self.device)
+        self.n_launch_per_step += 3 if self.halo_pipelined else 1
+
     # ------------------------------------------------------------------ state access
     def set_f(self, f):
         """Load the reference-convention state F (post-streaming, post-boundary populations)."""
@@ -338,11 +352,20 @@ class Stepper:
         main = torch.cuda.current_stream()
         st_main = C.c_void_p(main.cuda_stream)
         ref = C.byref(a)
+        halo = self.halo if do_collide else None
+        dst_index = 1 - self._cur
+        pipelined = halo is not None and self.halo_pipelined
+        rb, re = self.rows
+        if pipelined:
+            s_halo = self._halo_stream
+            st_halo = C.c_void_p(s_halo.cuda_stream)
+            s_halo.wait_stream(main)
+            a.sub_begin, a.sub_end = rb + 1, re - 1            # interior rows: no ghost-layer dependency
         if not (self.overlap and with_ib):
             if with_ib:
                 self._ib_part(st_main)
             L.check(lib.vsb_step(ref, st_main))
-            if a.edges:
+            if a.edges and not pipelined:
                 L.check(lib.vsb_edge_fused(ref, st_main))
         else:
             s_ib, s_edge = self._side
@@ -359,12 +382,25 @@ class Stepper:
             if not host_body:
                 a.band = 1                                     # everything but the window's x-range
                 L.check(lib.vsb_step(ref, st_main))
-            if a.edges:
+            if a.edges and not pipelined:
                 s_edge.wait_stream(main)
                 L.check(lib.vsb_edge_fused(ref, C.c_void_p(s_edge.cuda_stream)))
                 main.wait_stream(s_edge)
             main.wait_stream(s_ib)
             a.band = 0
+        if pipelined:
+            # second stream: neighbours' ghost layers -> the two edge rows (and the x walls) -> send them on
+            halo.wait(st_halo)
+            a.band = 0
+            a.sub_begin, a.sub_end, a.edge_rows_only = 0, 0, 1
+            L.check(lib.vsb_step(ref, st_halo))
+            a.edge_rows_only = 0
+            if a.edges:
+                L.check(lib.vsb_edge_fused(ref, st_halo))
+            halo.send(dst_index, st_halo)
+            main.wait_stream(s_halo)
+        elif halo is not None:
+            halo.push(dst_index, st_main)
         if with_ib:
             self._parity ^= 1
 
