@@ -131,8 +131,11 @@ typedef struct {
  * The velocity at the stencil points comes straight from the streamed populations of `args` (f_in, do_stream, mask),
  * so no velocity field is materialised.  The last stage adds the total force to body->force_sum and, when
  * params->n_dof > 0, the last CTA performs the body update of vsb_body_newmark.
- *   g_win / scratch            this step's buffers: force field (dim, window) and (n_iter-1) x (dim, window) work
- *                              fields; they must be ZERO on entry
+ * Window fields are stored cell-major with the components packed per cell: float2 in 2-D, float4 (last unused) in
+ * 3-D, i.e. shape (wnx, wny[, wnz], 2 | 4) -- one vector gather / vector reduction per stencil point.
+ *   u_win                      optional precomputed window velocity (vsb_ib_window_moments); NULL -> stage 0 takes the
+ *                              velocity at each stencil point from the streamed populations (better for sparse markers)
+ *   g_win / scratch            this step's buffers: force field and (n_iter-1) work fields; ZERO on entry
  *   g_win_next / scratch_next  the buffers the NEXT step will use: cleared by this call (double-buffer by step
  *                              parity, so nothing is cleared while a kernel of this step may still read it)
  *   markers0      (M, dim) marker coordinates; the body state adds its displacement
@@ -148,6 +151,7 @@ typedef struct {
   const float* u_target;
   const float* ds_ptr;
   float ds_value;
+  const float* u_win;
   float* g_win;
   float* g_win_next;
   float* scratch;
@@ -177,7 +181,7 @@ typedef struct {
   const float* f_in;
   float* f_out;
   float g_uniform[3];         /* uniform body force added everywhere                           */
-  const float* g_win;         /* optional force field on a window (dim, wnx, wny[, wnz])       */
+  const float* g_win;         /* optional force field on a window, cell-major (wnx, wny[, wnz], 2 | 4) */
   int win_origin[3], win_size[3];
   const VsbBodyState* body;   /* optional: window origin is read from body->origin2[parity]    */
   int parity;
@@ -206,7 +210,7 @@ int vsb_ib_mdf(const VsbStepArgs* args, const VsbMdfArgs* mdf, const VsbBodyPara
 int vsb_edge_fused_supported(const VsbStepArgs* args);
 int vsb_edge_fused(const VsbStepArgs* args, vsb_stream_t stream);
 
-/* Velocity of the streamed state on the IB window: u_win <- u(stream(f_in)) (diagnostic; vsb_ib_mdf does not need it).  Uses grid, f_in,
+/* Velocity of the streamed state on the IB window, cell-major (wnx, wny[, wnz], 2 | 4): u_win <- u(stream(f_in)).  Uses grid, f_in,
  * do_stream, win_origin / body + parity, win_size and the mask of `args`.  The window must not contain cells of a
  * face that carries a boundary operation. */
 int vsb_ib_window_moments(const VsbStepArgs* args, float* u_win, vsb_stream_t stream);

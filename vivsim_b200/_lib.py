@@ -60,7 +60,8 @@ class VsbMdfArgs(C.Structure):
     _fields_ = [("dim", C.c_int), ("delta_kind", C.c_int), ("n_iter", C.c_int), ("parity", C.c_int),
                 ("n_markers", C.c_int64), ("win_origin0", C.c_int * 3), ("win_size", C.c_int * 3),
                 ("markers0", C.c_void_p), ("u_target", C.c_void_p),
-                ("ds_ptr", C.c_void_p), ("ds_value", C.c_float), ("g_win", C.c_void_p), ("g_win_next", C.c_void_p),
+                ("ds_ptr", C.c_void_p), ("ds_value", C.c_float), ("u_win", C.c_void_p), ("g_win", C.c_void_p),
+                ("g_win_next", C.c_void_p),
                 ("scratch", C.c_void_p), ("scratch_next", C.c_void_p), ("marker_u", C.c_void_p),
                 ("marker_force", C.c_void_p), ("body", C.c_void_p)]
 

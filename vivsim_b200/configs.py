@@ -67,11 +67,66 @@ def sphere_3d(nx=256, ny=256, nz=256, diameter=48.0, u0=0.05, re=2000.0, n_iter=
     return spec, None
 
 
-def viv_cylinder_2d_large(n=16384, u0=0.05, re=1e4, n_iter=5):
-    """C4: D2Q9 KBC VIV cylinder Re = 1e4 on n x n, D = n/20, 4D markers, EDM."""
+def viv_cylinder_2d_large(n=16384, u0=0.05, re=1e4, n_iter=5, center_x=None):
+    """C4: D2Q9 KBC VIV cylinder Re = 1e4 on n x n, D = n/20, 4D markers, EDM.  center_x defaults to 3n/16, the
+    middle of the second of eight slabs, so the same geometry runs on 1, 2, 4 and 8 GPUs."""
     d = n / 20
+    cx = 3 * n / 16 if center_x is None else center_x
     spec, body = viv_cylinder_2d(nx=n, ny=n, n_marker=int(4 * d), radius=d / 2, u0=u0, nu=u0 * d / re, n_iter=n_iter,
-                                 collision="kbc", forcing="edm", moving=True, center=(n / 4, n / 2))
+                                 collision="kbc", forcing="edm", moving=True, center=(cx, n / 2))
+    return spec, body
+
+
+def cylinder_surface_markers(center, radius, height, spacing=0.5):
+    """Markers and area weights of a finite z-aligned cylinder: lateral surface on a (theta, z) grid and two caps of
+    concentric rings, all at <= `spacing` lattice units (the resolution rule of examples/3d/oscillating_cylinder.py:
+    146-149).  The weight of a marker is the surface area it represents."""
+    cx, cy, cz = center
+    n_t = int(math.ceil(2 * math.pi * radius / spacing))
+    n_z = int(math.ceil(height / spacing))
+    theta = np.linspace(0.0, 2 * math.pi, n_t, endpoint=False)
+    z = np.linspace(cz - height / 2, cz + height / 2, n_z + 1)
+    tt, zz = np.meshgrid(theta, z, indexing="ij")
+    lat = np.stack([cx + radius * np.cos(tt), cy + radius * np.sin(tt), zz], axis=-1).reshape(-1, 3)
+    wz = np.full(n_z + 1, height / n_z)
+    wz[0] = wz[-1] = 0.5 * height / n_z
+    w_lat = ((2 * math.pi * radius / n_t) * np.broadcast_to(wz, (n_t, n_z + 1))).reshape(-1)
+    pts, wts = [lat], [w_lat]
+    n_r = max(1, int(math.ceil(radius / spacing)))
+    edges = np.linspace(0.0, radius, n_r + 1)
+    for z_cap in (z[0], z[-1]):
+        for k in range(n_r):                     # ring k represents the annulus edges[k] .. edges[k + 1]
+            r_mid = 0.5 * (edges[k] + edges[k + 1])
+            n_k = max(6, int(math.ceil(2 * math.pi * r_mid / spacing)))
+            t = np.linspace(0.0, 2 * math.pi, n_k, endpoint=False)
+            pts.append(np.stack([cx + r_mid * np.cos(t), cy + r_mid * np.sin(t), np.full(n_k, z_cap)], axis=-1))
+            wts.append(np.full(n_k, math.pi * (edges[k + 1] ** 2 - edges[k] ** 2) / n_k))
+    return np.concatenate(pts).astype(np.float32), np.concatenate(wts).astype(np.float32)
+
+
+def oscillating_cylinder_3d(nx=1024, ny=512, nz=512, diameter=None, u0=0.05, re=1000.0, n_iter=3, collision="mrt",
+                            forcing="guo", mass_ratio=2.0, reduced_velocity=5.0, center_x=None, pad=4, moving=True):
+    """C5: D3Q19 MRT flow past an elastically mounted finite cylinder along z (examples/3d/oscillating_cylinder.py:
+    229-282 recipe): MDF(3), Guo-MRT forcing, NEBB inlet / equilibrium outlet, y and z periodic, 2-DOF Newmark body,
+    IB window following the body with clip(floor()).  center_x defaults to 5 nx / 16 (middle of the third of eight
+    slabs)."""
+    d = nx / 10 if diameter is None else diameter
+    h = nz - 24
+    cx = 5 * nx / 16 if center_x is None else center_x
+    center = (cx, ny / 2, nz / 2)
+    markers, ds = cylinder_surface_markers(center, d / 2, h)
+    origin, size = _window(markers, pad)
+    nu = u0 * d / re
+    spec = dict(dim=3, shape=(nx, ny, nz), collision=collision, omega=get_omega(nu), forcing=forcing, u0=u0,
+                ib=dict(markers=markers, ds=ds, kernel="peskin4", n_iter=n_iter, u_target=None, window=(origin, size)),
+                post=[("nebb", "left", {"ux_wall": u0}), ("equilibrium", "right", {"ux_wall": u0})])
+    body = None
+    if moving:
+        vol = math.pi * (d / 2) ** 2 * h
+        fn = u0 / (reduced_velocity * d)
+        m = vol * mass_ratio
+        k = (2 * math.pi * fn) ** 2 * m * (1 + 1 / mass_ratio)
+        body = dict(m=m, k=k, c=0.0, added_mass=vol, n_dof=2, d0=(0.0, 0.0), v0=(0.0, 1e-2 * u0), a0=(0.0, 0.0))
     return spec, body
 
 

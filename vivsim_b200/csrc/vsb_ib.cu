@@ -2,6 +2,8 @@
 // spread, and marker-parallel multi-direct forcing with the stencil evaluated on the fly.
 // A group of lanes owns one marker; its stencil points are spread over the lanes and reduced
 // with warp shuffles; spreading uses fp32 atomics (REDG) into window-sized buffers.
+#include <type_traits>
+
 #include "vsb_step.cuh"
 
 namespace vsb {
@@ -72,6 +74,7 @@ struct MdfParams {
   const float* u_target;
   const float* ds_ptr;
   float ds_value;
+  const float* u_win;   // optional: precomputed window velocity (stage 0 interpolates it instead of pulling populations)
   float* g_win;         // this step's force field (zero on entry of the last stage)
   float* g_win_next;    // next step's force field: cleared by stage 0
   float* scratch;       // this step's per-iteration fields, (n_iter - 1) x dim x window
@@ -110,12 +113,14 @@ __global__ void k_mdf_stage(const StepParams<DIM> sp, const MdfParams p, const B
   const long long wcells = (long long)p.wsize[0] * p.wsize[1] * (DIM == 3 ? p.wsize[2] : 1);
   const bool last = p.stage == p.n_iter - 1;
 
+  constexpr int NC = WinVec<DIM>::NC;
+  using VecF = typename std::conditional<DIM == 2, float2, float4>::type;
   // clear the other parity's buffers for the next step
   if (p.stage == 0)
-    for (long long i = gthread; i < DIM * wcells; i += nthreads) p.g_win_next[i] = 0.f;
+    for (long long i = gthread; i < NC * wcells; i += nthreads) p.g_win_next[i] = 0.f;
   if (p.stage < p.n_iter - 1) {
-    float* z = p.scratch_next + (long long)p.stage * DIM * wcells;
-    for (long long i = gthread; i < DIM * wcells; i += nthreads) z[i] = 0.f;
+    float* z = p.scratch_next + (long long)p.stage * NC * wcells;
+    for (long long i = gthread; i < NC * wcells; i += nthreads) z[i] = 0.f;
   }
 
   int org[3] = {p.origin0[0], p.origin0[1], p.origin0[2]};
@@ -160,7 +165,7 @@ __global__ void k_mdf_stage(const StepParams<DIM> sp, const MdfParams p, const B
   float um[DIM];
 #pragma unroll
   for (int c = 0; c < DIM; ++c) um[c] = 0.f;
-  if (p.stage == 0) {
+  if (p.stage == 0 && p.u_win == nullptr) {
 #pragma unroll
     for (int j = 0; j < PPL; ++j)
       if (ok[j]) {
@@ -174,12 +179,14 @@ __global__ void k_mdf_stage(const StepParams<DIM> sp, const MdfParams p, const B
         for (int c = 0; c < DIM; ++c) um[c] += w[j] * u[c];
       }
   } else {
-    const float* src = p.scratch + (long long)(p.stage - 1) * DIM * wcells;
+    const VecF* src = reinterpret_cast<const VecF*>(p.stage == 0 ? p.u_win : p.scratch + (long long)(p.stage - 1) * NC * wcells);
 #pragma unroll
     for (int j = 0; j < PPL; ++j)
       if (ok[j]) {
-#pragma unroll
-        for (int c = 0; c < DIM; ++c) um[c] += w[j] * src[c * wcells + idx[j]];
+        const VecF v = src[idx[j]];
+        um[0] += w[j] * v.x;
+        um[1] += w[j] * v.y;
+        if constexpr (DIM == 3) um[2] += w[j] * v.z;
       }
   }
 #pragma unroll
@@ -211,12 +218,12 @@ __global__ void k_mdf_stage(const StepParams<DIM> sp, const MdfParams p, const B
         p.marker_force[m * DIM + c] = f_new[c];
       }
     }
-    float* dst = last ? p.g_win : p.scratch + (long long)p.stage * DIM * wcells;
+    VecF* dst = reinterpret_cast<VecF*>(last ? p.g_win : p.scratch + (long long)p.stage * NC * wcells);
 #pragma unroll
     for (int j = 0; j < PPL; ++j)
-      if (ok[j]) {
-#pragma unroll
-        for (int c = 0; c < DIM; ++c) atomicAdd(&dst[c * wcells + idx[j]], spread_val[c] * w[j]);
+      if (ok[j]) {   // one vector reduction (red.global.add.v2/v4.f32) per stencil point
+        if constexpr (DIM == 2) atomicAdd(dst + idx[j], make_float2(spread_val[0] * w[j], spread_val[1] * w[j]));
+        else atomicAdd(dst + idx[j], make_float4(spread_val[0] * w[j], spread_val[1] * w[j], spread_val[2] * w[j], 0.f));
       }
     if (last && p.body && gl == 0) {
 #pragma unroll
@@ -259,7 +266,7 @@ static int mdf_impl(const VsbStepArgs& sa, const VsbMdfArgs& a, const VsbBodyPar
   p.delta_kind = a.delta_kind; p.n_iter = a.n_iter; p.parity = a.parity & 1; p.n_markers = a.n_markers;
   for (int d = 0; d < 3; ++d) { p.origin0[d] = a.win_origin0[d]; p.wsize[d] = a.win_size[d]; }
   p.markers0 = a.markers0; p.u_target = a.u_target; p.ds_ptr = a.ds_ptr; p.ds_value = a.ds_value;
-  p.g_win = a.g_win; p.g_win_next = a.g_win_next; p.scratch = a.scratch; p.scratch_next = a.scratch_next;
+  p.u_win = a.u_win; p.g_win = a.g_win; p.g_win_next = a.g_win_next; p.scratch = a.scratch; p.scratch_next = a.scratch_next;
   p.marker_u = a.marker_u; p.marker_force = a.marker_force; p.body = a.body;
   p.update_body = (a.body && bp && bp->n_dof > 0) ? 1 : 0;
   BodyUpdate bu{};

@@ -184,7 +184,12 @@ __global__ void __launch_bounds__(1024, 1) k_ib_fused(const StepParams<DIM> p, c
     __syncthreads();
   }
   // ---- outputs: force field on every window cell, marker state
-  for (int i = tid; i < DIM * wcells; i += nthr) m.g_win[i] = sg[i];
+  for (int i = tid; i < DIM * wcells; i += nthr) {   // cell-major, components packed (see WinVec)
+    const int c = i / wcells, cell = i - c * wcells;
+    m.g_win[cell * WinVec<DIM>::NC + c] = sg[i];
+  }
+  if (DIM == 3)
+    for (int i = tid; i < wcells; i += nthr) m.g_win[i * 4 + 3] = 0.f;
   for (int i = tid; i < M * DIM; i += nthr) { m.marker_force[i] = s_F[i]; m.marker_u[i] = s_um[i]; }
   if (tid == 0 && m.body) {
 #pragma unroll

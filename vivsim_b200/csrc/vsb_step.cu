@@ -9,6 +9,7 @@
 // edge issue one extra scalar load (which also performs the periodic wrap).  Shifts along the
 // other axes only change the row that is read, so every access stays aligned and coalesced.
 #include <algorithm>
+#include <cmath>
 
 #include "vsb_bc.cuh"
 #include "vsb_step.cuh"
@@ -263,7 +264,7 @@ __global__ void k_window_moments(const StepParams<DIM> p, float* __restrict__ u_
   pull_cell<DIM>(p, c[0], c[1], c[2], f, true);
   moments<DIM>(f, rho, u);
 #pragma unroll
-  for (int d = 0; d < L::D; ++d) u_win[d * wcells + t] = u[d];
+  for (int d = 0; d < L::D; ++d) u_win[t * WinVec<DIM>::NC + d] = u[d];
 }
 
 // Wall layer of one face in one kernel: pull, face operation, (mask), collide, store.  Only for face operations
@@ -498,11 +499,36 @@ static int step_impl(const VsbStepArgs& a, cudaStream_t s) {
   const int nrow = p.edge_rows ? 2 : ((p.band == 2) ? std::min(p.wsz[0], p.s_end - p.s_begin) : p.s_end - p.s_begin);
   const long long rows = (DIM == 2) ? (long long)nrow : (long long)nrow * p.n1;
   const long long total = rows * (p.n2 / vec);
-  constexpr int kBlock = 256;
-  const unsigned nb = blocks_for(total, kBlock);
-  if (vec == 4) k_step<DIM, COLL, 4><<<nb, kBlock, 0, s>>>(p, mm);
-  else if (vec == 2) k_step<DIM, COLL, 2><<<nb, kBlock, 0, s>>>(p, mm);
-  else k_step<DIM, COLL, 1><<<nb, kBlock, 0, s>>>(p, mm);
+  // Block size: for grids of only a few waves (e.g. 1024^2 = 1.73 waves of 256-thread blocks) the partly filled last
+  // wave costs up to a whole wave; choose the multiple of 32 in [128, 256] that fills the last wave best.
+  auto launch = [&](auto kernel) {
+    static int regs = 0, n_sm = 0;
+    if (regs == 0) {
+      cudaFuncAttributes fa;
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (cudaFuncGetAttributes(&fa, kernel) == cudaSuccess) regs = fa.numRegs;
+      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+      if (regs <= 0) regs = 128;
+      if (n_sm <= 0) n_sm = 148;
+    }
+    int best_bs = 256;
+    double best = -1.0;
+    for (int bs = 256; bs >= 128; bs -= 32) {
+      const long long nb = (total + bs - 1) / bs;
+      const int warps = bs / 32;
+      const int per_sm = std::max(1, std::min(std::min(65536 / (((regs + 7) / 8 * 8) * 32) / warps, 2048 / bs), 32));
+      const double waves = (double)nb / ((double)per_sm * n_sm);
+      const double fill = waves / std::ceil(waves);                       // how full the average wave is
+      const double occ = std::min(1.0, per_sm * bs / 768.0);              // mild preference for >= 768 threads / SM
+      const double score = fill * (0.9 + 0.1 * occ) + (bs == 256 ? 1e-3 : 0.0);
+      if (score > best) { best = score; best_bs = bs; }
+    }
+    kernel<<<blocks_for(total, best_bs), best_bs, 0, s>>>(p, mm);
+  };
+  if (vec == 4) launch(k_step<DIM, COLL, 4>);
+  else if (vec == 2) launch(k_step<DIM, COLL, 2>);
+  else launch(k_step<DIM, COLL, 1>);
   VSB_LAUNCH_CHECK("vsb_step (fused kernel)");
 
   if (!have_ops || a.edges == 1) return VSB_OK;

@@ -152,13 +152,20 @@ __device__ __forceinline__ void cell_force(const StepParams<DIM>& p, const int (
   for (int d = 0; d < L::D; ++d) g[d] = p.g0[d];
   const int rel = c2 - worg[L::D - 1];
   if (rows_inside && (unsigned)rel < (unsigned)p.wsz[L::D - 1]) {
-    int wcells = 1;
-#pragma unroll
-    for (int d = 0; d < L::D; ++d) wcells *= p.wsz[d];
-#pragma unroll
-    for (int d = 0; d < L::D; ++d) g[d] += p.gwin[d * wcells + base + rel];
+    // window fields are stored cell-major with the components packed (float2 in 2-D, float4 in 3-D) so that the IB
+    // kernels can use one vector gather / one vector atomic per stencil point
+    if constexpr (L::D == 2) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(p.gwin) + base + rel);
+      g[0] += v.x; g[1] += v.y;
+    } else {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p.gwin) + base + rel);
+      g[0] += v.x; g[1] += v.y; g[2] += v.z;
+    }
   }
 }
+
+// components per cell of a window field: 2 (float2) in 2-D, 4 (float4, last unused) in 3-D
+template <int DIM> struct WinVec { static constexpr int NC = (DIM == 2) ? 2 : 4; };
 
 // moments -> (Guo velocity shift) -> equilibrium -> collision -> forcing, on one cell in registers.
 // Order of operations: examples/2d/poiseuille_channel.py:80-148 (EDM uses the uncorrected velocity,

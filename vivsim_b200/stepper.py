@@ -181,12 +181,18 @@ class Stepper:
                                  "out-of-range stencil indices undefined)")
         self.n_markers = markers.shape[0]
         self.n_iter = int(ib.get("n_iter", 5))
-        wshape = (dim,) + self.win_size
         self._markers = torch.as_tensor(markers, device=dev)
         # force field [0] and per-iteration work fields [1:], double-buffered by step parity: each step clears the
         # set the next step will accumulate into (see vsb_ib_mdf), so there is no memset on the step path
-        self._ib_buf = torch.zeros((2, self.n_iter) + wshape, device=dev)
+        # layout: cell-major with the components packed per cell (float2 in 2-D, float4 in 3-D)
+        nc = 2 if dim == 2 else 4
+        self._ib_buf = torch.zeros((2, self.n_iter) + self.win_size + (nc,), device=dev)
         self._g_win = self._ib_buf[0, 0]
+        # dense marker sets (many stencil points per window cell, e.g. a finely meshed 3-D surface) interpolate a
+        # precomputed window velocity; sparse ones take it from the streamed populations at their stencil points
+        wcells = int(np.prod(self.win_size))
+        self._use_uwin = self.n_markers * 4 ** dim > 2 * wcells
+        self._u_win = torch.zeros(self.win_size + (nc,), device=dev) if self._use_uwin else None
         self._marker_u = torch.zeros((self.n_markers, dim), device=dev)
         self.marker_force = torch.zeros((self.n_markers, dim), device=dev)   # +F; reaction on the body is -F
         tgt = ib.get("u_target")
@@ -276,7 +282,7 @@ class Stepper:
         if self.ib is not None:
             if self.overlap:
                 n += 1                                    # second launch of the fused kernel (window x-range)
-            n += 1 if self.ib_fused else self.n_iter
+            n += 1 if self.ib_fused else self.n_iter + (1 if self._use_uwin else 0)
         return n
 
     def attach_halo(self, halo):
@@ -417,6 +423,10 @@ class Stepper:
         if self.ib_fused:
             L.check(lib.vsb_ib_fused(C.byref(a), C.byref(m), bp, st))
         else:
+            m.u_win = None
+            if self._use_uwin:
+                L.check(lib.vsb_ib_window_moments(C.byref(a), L.ptr(self._u_win), st))
+                m.u_win = self._u_win.data_ptr()
             L.check(lib.vsb_ib_mdf(C.byref(a), C.byref(m), bp, st))
         if self.body is not None and self.dyn_mode == "host":
             # rigid-body ODE on the host (north_star): 88 B device -> host, Newmark-beta on the CPU, 88 B back
