@@ -232,6 +232,19 @@ int vsb_body_newmark_host(VsbBodyState* body, VsbBodyState* pinned, const VsbBod
 int vsb_ib_fused_supported(const VsbMdfArgs* mdf);
 int vsb_ib_fused(const VsbStepArgs* args, const VsbMdfArgs* mdf, const VsbBodyParams* params, vsb_stream_t stream);
 
+/* One whole time step with the rigid-body ODE on the host, orchestrated in a single call (the per-step CPU cost of
+ * issuing it from an interpreted host language would otherwise dominate): bulk of the grid on `main`; on `ib` the MDF
+ * chain, vsb_body_newmark_host (synchronises `ib` only) and the window's x-range; wall kernels on `edge`; joins back
+ * into `main`.  Streams and events are created by the caller (cudaStream_t / cudaEvent_t passed as void*).
+ * args->edges must be 1 when there are face operations (independent ones, see vsb_edge_fused_supported). */
+typedef struct {
+  void* main; void* ib; void* edge;            /* cudaStream_t */
+  void* ev_fork; void* ev_ib; void* ev_edge;   /* cudaEvent_t  */
+} VsbHostPlan;
+
+int vsb_step_host_ode(VsbStepArgs* args, const VsbMdfArgs* mdf, const VsbBodyParams* params, VsbBodyState* pinned,
+                      const VsbHostPlan* plan);
+
 /* ---- multi-GPU: halo exchange over peer memory ----------------------------------------- *
  * Slab decomposition along x, one ghost layer per side (local extent grid.nx = nx_local + 2).  Replaces the
  * reference's vivsim/multidevice.py:13-38 (four lax.ppermute of the populations crossing a cut).  One kernel copies

@@ -28,7 +28,7 @@ def declared_symbols():
 
 def test_header_symbols_exported(lib):
     names = declared_symbols()
-    assert len(names) >= 26
+    assert len(names) >= 27
     for n in names:
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
     from vivsim_b200 import _lib

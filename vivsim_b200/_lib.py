@@ -25,7 +25,7 @@ EXPORTS = [
     "vsb_guo_forcing_term", "vsb_forcing", "vsb_post_op", "vsb_boundary_characteristic", "vsb_ib_delta",
     "vsb_ib_stencil", "vsb_ib_interpolate", "vsb_ib_spread", "vsb_ib_mdf", "vsb_step", "vsb_ib_window_moments",
     "vsb_body_newmark", "vsb_edge_fused", "vsb_edge_fused_supported", "vsb_ib_fused", "vsb_ib_fused_supported",
-    "vsb_halo_push", "vsb_body_newmark_host", "vsb_halo_send", "vsb_halo_wait",
+    "vsb_halo_push", "vsb_body_newmark_host", "vsb_halo_send", "vsb_halo_wait", "vsb_step_host_ode",
 ]
 
 
@@ -74,6 +74,11 @@ class VsbStepArgs(C.Structure):
                 ("win_origin", C.c_int * 3), ("win_size", C.c_int * 3), ("body", C.c_void_p), ("parity", C.c_int),
                 ("n_post", C.c_int), ("post", C.POINTER(VsbPostOp)), ("vec", C.c_int), ("band", C.c_int),
                 ("edges", C.c_int), ("sub_begin", C.c_int), ("sub_end", C.c_int), ("edge_rows_only", C.c_int)]
+
+
+class VsbHostPlan(C.Structure):
+    _fields_ = [("main", C.c_void_p), ("ib", C.c_void_p), ("edge", C.c_void_p), ("ev_fork", C.c_void_p),
+                ("ev_ib", C.c_void_p), ("ev_edge", C.c_void_p)]
 
 
 class VsbHaloArgs(C.Structure):

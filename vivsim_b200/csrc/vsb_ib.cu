@@ -377,6 +377,37 @@ int vsb_body_newmark_host(VsbBodyState* body, VsbBodyState* pinned, const VsbBod
   return VSB_OK;
 }
 
+int vsb_step_host_ode(VsbStepArgs* a, const VsbMdfArgs* mdf, const VsbBodyParams* bp, VsbBodyState* pinned,
+                      const VsbHostPlan* plan) {
+  VSB_REQUIRE(a && mdf && bp && pinned && plan, "vsb_step_host_ode: null argument");
+  VSB_REQUIRE(mdf->body != nullptr, "vsb_step_host_ode: needs a body state");
+  cudaStream_t main = (cudaStream_t)plan->main, ib = (cudaStream_t)plan->ib, edge = (cudaStream_t)plan->edge;
+  cudaEvent_t fork = (cudaEvent_t)plan->ev_fork, ib_done = (cudaEvent_t)plan->ev_ib, edge_done = (cudaEvent_t)plan->ev_edge;
+  VSB_REQUIRE(ib && fork && ib_done, "vsb_step_host_ode: plan needs the ib stream and the fork / ib events (main may be the default stream)");
+  cudaError_t e = cudaEventRecord(fork, main);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(ib, fork, 0);
+  if (e != cudaSuccess) return cuda_fail(e, "vsb_step_host_ode (fork)");
+  const int has_edges = a->edges && a->n_post > 0 && a->do_stream;
+  int rc;
+  a->band = 1;                                     // the bulk runs while the host advances the body
+  if ((rc = vsb_step(a, main))) return rc;
+  if (has_edges) {
+    VSB_REQUIRE(edge && edge_done, "vsb_step_host_ode: plan needs the edge stream / event");
+    if ((e = cudaStreamWaitEvent(edge, fork, 0)) != cudaSuccess) return cuda_fail(e, "vsb_step_host_ode (edge fork)");
+    if ((rc = vsb_edge_fused(a, edge))) return rc;
+    if ((e = cudaEventRecord(edge_done, edge)) != cudaSuccess) return cuda_fail(e, "vsb_step_host_ode (edge join)");
+  }
+  if ((rc = vsb_ib_mdf(a, mdf, nullptr, ib))) return rc;                         // force on the markers and the window
+  if ((rc = vsb_body_newmark_host(mdf->body, pinned, bp, mdf->parity, ib))) return rc;   // device -> host, ODE, host -> device
+  a->band = 2;
+  if ((rc = vsb_step(a, ib))) return rc;
+  a->band = 0;
+  if ((e = cudaEventRecord(ib_done, ib)) != cudaSuccess) return cuda_fail(e, "vsb_step_host_ode (ib join)");
+  if ((e = cudaStreamWaitEvent(main, ib_done, 0)) != cudaSuccess) return cuda_fail(e, "vsb_step_host_ode (join)");
+  if (has_edges && (e = cudaStreamWaitEvent(main, edge_done, 0)) != cudaSuccess) return cuda_fail(e, "vsb_step_host_ode (join)");
+  return VSB_OK;
+}
+
 int vsb_body_newmark(VsbBodyState* body, const VsbBodyParams* params, int parity, vsb_stream_t stream) {
   VSB_REQUIRE(body != nullptr && params != nullptr, "vsb_body_newmark: null argument");
   VSB_REQUIRE(params->n_dof >= 1 && params->n_dof <= 3, "n_dof must be 1..3, got %d", params->n_dof);

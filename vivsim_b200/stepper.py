@@ -367,7 +367,10 @@ class Stepper:
             st_halo = C.c_void_p(s_halo.cuda_stream)
             s_halo.wait_stream(main)
             a.sub_begin, a.sub_end = rb + 1, re - 1            # interior rows: no ghost-layer dependency
-        if not (self.overlap and with_ib):
+        if (self.overlap and with_ib and not pipelined and self.body is not None and self.dyn_mode == "host"
+                and not self.ib_fused and (not has_ops or self.edge_fused)):
+            self._host_ode_step(main)                          # the whole pass in one C call
+        elif not (self.overlap and with_ib):
             if with_ib:
                 self._ib_part(st_main)
             L.check(lib.vsb_step(ref, st_main))
@@ -409,6 +412,27 @@ class Stepper:
             halo.push(dst_index, st_main)
         if with_ib:
             self._parity ^= 1
+
+    def _host_ode_step(self, main):
+        """One pass with the rigid-body ODE on the host through vsb_step_host_ode (fork / join in C)."""
+        a, m = self._args, self._mdf
+        if getattr(self, "_plan", None) is None:
+            self._plan_events = [torch.cuda.Event() for _ in range(3)]
+            for ev in self._plan_events:
+                ev.record(main)                                # materialise the cudaEvent_t handles
+            self._plan = L.VsbHostPlan()
+            self._plan.ib, self._plan.edge = self._side[0].cuda_stream, self._side[1].cuda_stream
+            self._plan.ev_fork, self._plan.ev_ib, self._plan.ev_edge = (ev.cuda_event for ev in self._plan_events)
+        self._plan.main = main.cuda_stream
+        par = self._parity
+        m.parity = par
+        buf = self._ib_buf
+        m.g_win, m.g_win_next = buf[par, 0].data_ptr(), buf[par ^ 1, 0].data_ptr()
+        if self.n_iter > 1:
+            m.scratch, m.scratch_next = buf[par, 1].data_ptr(), buf[par ^ 1, 1].data_ptr()
+        m.u_win = None
+        L.check(L.lib().vsb_step_host_ode(C.byref(a), C.byref(m), C.byref(self._hparams),
+                                          C.c_void_p(self._body_pin.data_ptr()), C.byref(self._plan)))
 
     def _ib_part(self, st):
         """Immersed-boundary force of this pass on stream `st`, then the body update."""
