@@ -192,7 +192,9 @@ typedef struct {
   int band;                   /* 0: all rows; 1: all rows except the x-range of the force window;
                                  2: only that x-range (lets the bulk run concurrently with the IB kernels) */
   int edges;                  /* 0: ordered wall fix-up inside vsb_step; 1: none -- the caller runs
-                                 vsb_edge_fused and the fused pass leaves those wall layers untouched */
+                                 vsb_edge_fused and the fused pass leaves those wall layers untouched;
+                                 2: the wall layers are processed by extra blocks of the same launch
+                                 (1 and 2 need independent face operations, see vsb_edge_fused_supported) */
   int sub_begin, sub_end;     /* rows of [row_begin, row_end) this launch updates (sub_end = 0: all of them);
                                  lets edge rows, which read ghost layers, run later than the interior */
   int edge_rows_only;         /* 1: update just the first and the last physical row (ignores sub_begin / sub_end) */

@@ -167,12 +167,23 @@ __device__ __forceinline__ void guo_term(const float (&g)[Lat<DIM>::D], const fl
 // The result is the same for a direction and its opposite, so only pair[k] = (P fneq)_{q(k)} and rest = (P fneq)_0
 // are produced.
 template <int DIM>
+__device__ __forceinline__ void projection_from_sums(float (&e)[Pairs<DIM>::NP], float& rest, float (&pair)[Pairs<DIM>::NP]);
+
+template <int DIM>
 __device__ __forceinline__ void projection_pairs(const float (&fneq)[Lat<DIM>::Q], float& rest, float (&pair)[Pairs<DIM>::NP]) {
   using L = Lat<DIM>;
   using P = Pairs<DIM>;
   float e[P::NP];   // fneq_q + fneq_opp
 #pragma unroll
   for (int k = 0; k < P::NP; ++k) e[k] = fneq[P::q(k)] + fneq[L::opp(P::q(k))];
+  projection_from_sums<DIM>(e, rest, pair);
+}
+
+// e[k] = fneq_q + fneq_opp for pair k  ->  rest = (P fneq)_0, pair[k] = (P fneq)_{q(k)}
+template <int DIM>
+__device__ __forceinline__ void projection_from_sums(float (&e)[Pairs<DIM>::NP], float& rest, float (&pair)[Pairs<DIM>::NP]) {
+  using L = Lat<DIM>;
+  using P = Pairs<DIM>;
   float pi[L::D][L::D];
 #pragma unroll
   for (int a = 0; a < L::D; ++a)
@@ -272,21 +283,26 @@ template <int DIM>
 __device__ __forceinline__ void collide_kbc(float (&f)[Lat<DIM>::Q], const float (&feq)[Lat<DIM>::Q], const Relax& r) {
   using L = Lat<DIM>;
   using P = Pairs<DIM>;
-  constexpr int Q = L::Q;
-  float fneq[Q], sh0, sh[P::NP];
-#pragma unroll
-  for (int q = 0; q < Q; ++q) fneq[q] = f[q] - feq[q];
+  // fneq = f - feq is recomputed where it is used instead of being held in Q more registers: with 4 cells per thread
+  // the D3Q19 kernel sits at the 128-register budget
+  float sh0, sh[P::NP];
   if constexpr (DIM == 2) {
-    const float n4 = (fneq[1] - fneq[2] + fneq[3] - fneq[4]) * 0.25f;
-    const float p4 = (fneq[5] - fneq[6] + fneq[7] - fneq[8]) * 0.25f;
+    const float n4 = ((f[1] - feq[1]) - (f[2] - feq[2]) + (f[3] - feq[3]) - (f[4] - feq[4])) * 0.25f;
+    const float p4 = ((f[5] - feq[5]) - (f[6] - feq[6]) + (f[7] - feq[7]) - (f[8] - feq[8])) * 0.25f;
     sh0 = 0.f;
     sh[0] = n4; sh[1] = -n4; sh[2] = p4; sh[3] = -p4;   // pairs (1,3) (2,4) (5,7) (6,8)
   } else {
-    projection_pairs<DIM>(fneq, sh0, sh);
+    float e[P::NP];
+#pragma unroll
+    for (int k = 0; k < P::NP; ++k) {
+      const int q = P::q(k), o = L::opp(q);
+      e[k] = (f[q] - feq[q]) + (f[o] - feq[o]);
+    }
+    projection_from_sums<DIM>(e, sh0, sh);
   }
   float s_sh, s_hh;
   {
-    const float hi = fneq[0] - sh0;
+    const float hi = (f[0] - feq[0]) - sh0;
     const float inv = __fdividef(1.0f, feq[0] + 1e-20f);   // MUFU.RCP, <= 2 ulp
     s_sh = hi * sh0 * inv;
     s_hh = hi * hi * inv;
@@ -294,19 +310,19 @@ __device__ __forceinline__ void collide_kbc(float (&f)[Lat<DIM>::Q], const float
 #pragma unroll
   for (int k = 0; k < P::NP; ++k) {
     const int q = P::q(k), o = L::opp(q);
-    const float hq = fneq[q] - sh[k], ho = fneq[o] - sh[k];
+    const float hq = (f[q] - feq[q]) - sh[k], ho = (f[o] - feq[o]) - sh[k];
     const float tq = hq * __fdividef(1.0f, feq[q] + 1e-20f), to = ho * __fdividef(1.0f, feq[o] + 1e-20f);
     s_sh += sh[k] * (tq + to);
     s_hh += hq * tq + ho * to;
   }
   const float half_gamma = r.inv_omega - r.one_minus_inv_omega * s_sh / (s_hh + 1e-20f);
   // f -= omega (sh + hg (fneq - sh)); keep the difference (fneq - sh) explicit: hg can be large where it is tiny
-  f[0] -= r.omega * (sh0 + half_gamma * (fneq[0] - sh0));
+  f[0] -= r.omega * (sh0 + half_gamma * ((f[0] - feq[0]) - sh0));
 #pragma unroll
   for (int k = 0; k < P::NP; ++k) {
     const int q = P::q(k), o = L::opp(q);
-    f[q] -= r.omega * (sh[k] + half_gamma * (fneq[q] - sh[k]));
-    f[o] -= r.omega * (sh[k] + half_gamma * (fneq[o] - sh[k]));
+    f[q] -= r.omega * (sh[k] + half_gamma * ((f[q] - feq[q]) - sh[k]));
+    f[o] -= r.omega * (sh[k] + half_gamma * ((f[o] - feq[o]) - sh[k]));
   }
 }
 

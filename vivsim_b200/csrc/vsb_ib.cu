@@ -387,7 +387,7 @@ int vsb_step_host_ode(VsbStepArgs* a, const VsbMdfArgs* mdf, const VsbBodyParams
   cudaError_t e = cudaEventRecord(fork, main);
   if (e == cudaSuccess) e = cudaStreamWaitEvent(ib, fork, 0);
   if (e != cudaSuccess) return cuda_fail(e, "vsb_step_host_ode (fork)");
-  const int has_edges = a->edges && a->n_post > 0 && a->do_stream;
+  const int has_edges = a->edges == 1 && a->n_post > 0 && a->do_stream;   // edges == 2: the walls ride in the bulk launch
   int rc;
   a->band = 1;                                     // the bulk runs while the host advances the body
   if ((rc = vsb_step(a, main))) return rc;

@@ -11,7 +11,6 @@
 #include <algorithm>
 #include <cmath>
 
-#include "vsb_bc.cuh"
 #include "vsb_step.cuh"
 
 namespace vsb {
@@ -40,6 +39,9 @@ __device__ __forceinline__ void store_vec(float* __restrict__ p, const float (&v
   *reinterpret_cast<T*>(p) = t;
 }
 
+template <int DIM, int COLL>
+__device__ __forceinline__ void edge_block(const StepParams<DIM>& p, const MrtMats<DIM, COLL == VSB_COLL_MRT>& mm);
+
 // register budget: 128 (2 CTAs / SM) in 3-D; in 2-D 64 (4 CTAs) for BGK / regularised, 85 (3 CTAs) for KBC / MRT
 template <int DIM, int COLL> constexpr int step_min_ctas() {
   return DIM == 3 ? 2 : ((COLL == VSB_COLL_KBC || COLL == VSB_COLL_MRT) ? 3 : 4);
@@ -49,6 +51,10 @@ template <int DIM, int COLL, int VEC>
 __global__ void __launch_bounds__(256, step_min_ctas<DIM, COLL>()) k_step(const StepParams<DIM> p, const MrtMats<DIM, COLL == VSB_COLL_MRT> mm) {
   using L = Lat<DIM>;
   constexpr int Q = L::Q;
+  if (blockIdx.x >= p.nb_bulk) {   // blocks appended after the bulk: wall layers of the face operations (edges = 2)
+    edge_block<DIM, COLL>(p, mm);
+    return;
+  }
   const int nv = p.n2 / VEC;
   int worg[3];
   window_origin<DIM>(p, worg);
@@ -267,17 +273,16 @@ __global__ void k_window_moments(const StepParams<DIM> p, float* __restrict__ u_
   for (int d = 0; d < L::D; ++d) u_win[t * WinVec<DIM>::NC + d] = u[d];
 }
 
-// Wall layer of one face in one kernel: pull, face operation, (mask), collide, store.  Only for face operations
-// that are independent of each other (see vsb_edge_fused_supported), so no ordering between launches is needed.
+// One wall cell: pull, face operation, (mask), collide, store.  Face operations handled this way are independent of
+// each other (see vsb_edge_fused_supported), so no ordering between them is needed.
 template <int DIM, int COLL, int LOC>
-__global__ void k_edge_fused(const StepParams<DIM> p, const MrtMats<DIM, COLL == VSB_COLL_MRT> mm, int wall_layer, int kind,
-                             int wrap_kind, WallVals w, int mask_before) {
+__device__ __forceinline__ void edge_cell(const StepParams<DIM>& p, const MrtMats<DIM, COLL == VSB_COLL_MRT>& mm, int wall_layer,
+                                          int kind, int wrap_kind, const WallVals& w, int mask_before, long long k) {
   using L = Lat<DIM>;
   using G = FaceGeom<DIM, LOC>;
   constexpr int Q = L::Q, D = L::D;
   const int n[3] = {p.n0, p.n1, p.n2};
   const long long nface = (long long)n[G::TA] * n[G::TB];
-  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= nface) return;
   int c[3];
   c[G::TA] = (int)(k / n[G::TB]);
@@ -328,6 +333,33 @@ __global__ void k_edge_fused(const StepParams<DIM> p, const MrtMats<DIM, COLL ==
   for (int q = 0; q < Q; ++q) p.fout[q * ncell + cell] = fw[q];
 }
 
+// Wall layer of one face as a kernel of its own (vsb_edge_fused).
+template <int DIM, int COLL, int LOC>
+__global__ void k_edge_fused(const StepParams<DIM> p, const MrtMats<DIM, COLL == VSB_COLL_MRT> mm, int wall_layer, int kind,
+                             int wrap_kind, WallVals w, int mask_before) {
+  edge_cell<DIM, COLL, LOC>(p, mm, wall_layer, kind, wrap_kind, w, mask_before, (long long)blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+template <int DIM, int COLL>
+__device__ __forceinline__ void edge_block(const StepParams<DIM>& p, const MrtMats<DIM, COLL == VSB_COLL_MRT>& mm) {
+  unsigned b = blockIdx.x - p.nb_bulk;
+  int e = 0;
+  if (p.n_wall > 1 && b >= p.wall_blocks0) { e = 1; b -= p.wall_blocks0; }
+  const WallOpDev& op = p.wall[e];
+  const long long k = (long long)b * blockDim.x + threadIdx.x;
+  if constexpr (DIM == 2) {
+    if (op.loc == 0) edge_cell<2, COLL, 0>(p, mm, op.layer, op.kind, op.wrap, op.w, op.mask_before, k);
+    else edge_cell<2, COLL, 1>(p, mm, op.layer, op.kind, op.wrap, op.w, op.mask_before, k);
+  } else {
+    switch (op.loc) {
+      case 0: edge_cell<3, COLL, 0>(p, mm, op.layer, op.kind, op.wrap, op.w, op.mask_before, k); break;
+      case 1: edge_cell<3, COLL, 1>(p, mm, op.layer, op.kind, op.wrap, op.w, op.mask_before, k); break;
+      case 2: edge_cell<3, COLL, 2>(p, mm, op.layer, op.kind, op.wrap, op.w, op.mask_before, k); break;
+      default: edge_cell<3, COLL, 3>(p, mm, op.layer, op.kind, op.wrap, op.w, op.mask_before, k); break;
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------- host side
 template <int DIM>
 int fill_params(const VsbStepArgs& a, StepParams<DIM>& p) {
@@ -356,6 +388,9 @@ int fill_params(const VsbStepArgs& a, StepParams<DIM>& p) {
   VSB_REQUIRE(a.band == 0 || a.win_size[0] > 0, "vsb_step: band mode needs a force window");
   p.band = a.band;
   p.n_skip = 0;
+  p.n_wall = 0;
+  p.nb_bulk = 0xffffffffu;
+  p.wall_blocks0 = 0;
   int n_mask = 0;
   for (int i = 0; i < a.n_post; ++i)
     if (a.post[i].kind == VSB_POST_MASK) { p.mask = a.post[i].mask; ++n_mask; }
@@ -479,15 +514,24 @@ static int step_impl(const VsbStepArgs& a, cudaStream_t s) {
   MrtMats<DIM, COLL == VSB_COLL_MRT> mm;
   fill_mats<DIM, COLL>(a, mm);
   const bool have_ops = a.n_post > 0 && a.do_stream;
-  if (a.edges == 1 && have_ops) {
+  if ((a.edges == 1 || a.edges == 2) && have_ops) {
     int mask_before = 0;
-    VSB_REQUIRE(edges_independent<DIM>(a, p, mask_before), "vsb_step: edges = 1 needs independent face operations");
+    VSB_REQUIRE(edges_independent<DIM>(a, p, mask_before), "vsb_step: edges = 1 / 2 need independent face operations");
     for (int i = 0; i < a.n_post; ++i) {
-      if (a.post[i].kind == VSB_POST_MASK) continue;
+      const VsbPostOp& op = a.post[i];
+      if (op.kind == VSB_POST_MASK) continue;
       int ax, wall, extent;
-      wall_of<DIM>(p, a.post[i].loc, ax, wall, extent);
+      wall_of<DIM>(p, op.loc, ax, wall, extent);
       VSB_REQUIRE(p.n_skip < 2, "vsb_step: too many wall layers");
       p.skip_axis[p.n_skip] = ax; p.skip_layer[p.n_skip] = wall; ++p.n_skip;
+      // edges = 2: the wall layer is processed by blocks appended to the launch that covers its rows
+      const bool covered = a.band != 2 && (ax != Lat<DIM>::A0 || p.edge_rows || (wall >= p.s_begin && wall < p.s_end));
+      if (a.edges == 2 && covered) {
+        WallOpDev& wo = p.wall[p.n_wall++];
+        wo.kind = op.kind; wo.wrap = op.wrap; wo.loc = op.loc; wo.layer = wall; wo.mask_before = mask_before;
+        wo.w.rho = op.rho;
+        for (int d = 0; d < 3; ++d) { wo.w.u[d] = op.u[d]; wo.w.g[d] = op.g[d]; }
+      }
     }
   }
   int vec = a.vec;
@@ -524,14 +568,23 @@ static int step_impl(const VsbStepArgs& a, cudaStream_t s) {
       const double score = fill * (0.9 + 0.1 * occ) + (bs == 256 ? 1e-3 : 0.0);
       if (score > best) { best = score; best_bs = bs; }
     }
-    kernel<<<blocks_for(total, best_bs), best_bs, 0, s>>>(p, mm);
+    p.nb_bulk = blocks_for(total, best_bs);
+    unsigned extra = 0;
+    for (int e = 0; e < p.n_wall; ++e) {
+      const int n[3] = {p.n0, p.n1, p.n2};
+      const int ax = p.wall[e].loc / 2 + Lat<DIM>::A0;
+      const unsigned nbw = blocks_for((long long)n[0] * n[1] * n[2] / n[ax], best_bs);
+      if (e == 0) p.wall_blocks0 = nbw;
+      extra += nbw;
+    }
+    kernel<<<p.nb_bulk + extra, best_bs, 0, s>>>(p, mm);
   };
   if (vec == 4) launch(k_step<DIM, COLL, 4>);
   else if (vec == 2) launch(k_step<DIM, COLL, 2>);
   else launch(k_step<DIM, COLL, 1>);
   VSB_LAUNCH_CHECK("vsb_step (fused kernel)");
 
-  if (!have_ops || a.edges == 1) return VSB_OK;
+  if (!have_ops || a.edges == 1 || a.edges == 2) return VSB_OK;
   VSB_REQUIRE(a.band == 0 && !p.edge_rows && p.s_begin == p.r_begin && p.s_end == p.r_end,
               "vsb_step: the ordered wall fix-up (edges = 0) cannot be combined with band modes or row sub-ranges");
   // layers touched by face operations: wall layer and adjacent fluid layer of each face

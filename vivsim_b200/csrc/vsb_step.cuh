@@ -3,7 +3,7 @@
 
 #include <utility>
 
-#include "vsb_common.cuh"
+#include "vsb_bc.cuh"
 #include "vsb_internal.h"
 
 namespace vsb {
@@ -17,6 +17,12 @@ template <int N, class F>
 __device__ __forceinline__ void static_for(F&& body) {
   static_for_impl(body, std::make_integer_sequence<int, N>{});
 }
+
+// One face operation handled inside the fused kernel's launch (extra blocks after the bulk blocks).
+struct WallOpDev {
+  int kind, wrap, loc, layer, mask_before;
+  WallVals w;
+};
 
 template <int DIM> struct StepParams {
   int n0, n1, n2;
@@ -36,6 +42,9 @@ template <int DIM> struct StepParams {
   int band;             // 0 all rows, 1 skip the window's x-range, 2 only the window's x-range
   int n_skip;           // wall layers (normal to a non-contiguous axis) left to the fused wall kernel
   int skip_axis[2], skip_layer[2];
+  int n_wall;           // face operations executed by the blocks appended to this launch (edges = 2)
+  unsigned nb_bulk, wall_blocks0;
+  WallOpDev wall[2];
 };
 
 template <int DIM, bool USED> struct MrtMats { Matrix<Lat<DIM>::Q> A, B; };

@@ -278,7 +278,7 @@ class Stepper:
     def _count_launches(self, n_bc):
         n = 1
         if n_bc:
-            n += n_bc if self.edge_fused else 2 + self._args.n_post
+            n += 0 if self.edge_fused else 2 + self._args.n_post
         if self.ib is not None:
             if self.overlap:
                 n += 1                                    # second launch of the fused kernel (window x-range)
@@ -353,7 +353,7 @@ class Stepper:
         lib = L.lib()
         has_ops = a.n_post > 0 and do_stream
         with_ib = self.ib is not None and do_collide
-        a.edges = 1 if (has_ops and self.edge_fused) else 0
+        a.edges = 2 if (has_ops and self.edge_fused) else 0     # wall layers ride in the fused kernel's launch
         a.band = 0
         main = torch.cuda.current_stream()
         st_main = C.c_void_p(main.cuda_stream)
@@ -374,8 +374,6 @@ class Stepper:
             if with_ib:
                 self._ib_part(st_main)
             L.check(lib.vsb_step(ref, st_main))
-            if a.edges and not pipelined:
-                L.check(lib.vsb_edge_fused(ref, st_main))
         else:
             s_ib, s_edge = self._side
             st_ib = C.c_void_p(s_ib.cuda_stream)
@@ -391,10 +389,6 @@ class Stepper:
             if not host_body:
                 a.band = 1                                     # everything but the window's x-range
                 L.check(lib.vsb_step(ref, st_main))
-            if a.edges and not pipelined:
-                s_edge.wait_stream(main)
-                L.check(lib.vsb_edge_fused(ref, C.c_void_p(s_edge.cuda_stream)))
-                main.wait_stream(s_edge)
             main.wait_stream(s_ib)
             a.band = 0
         if pipelined:
@@ -404,8 +398,6 @@ class Stepper:
             a.sub_begin, a.sub_end, a.edge_rows_only = 0, 0, 1
             L.check(lib.vsb_step(ref, st_halo))
             a.edge_rows_only = 0
-            if a.edges:
-                L.check(lib.vsb_edge_fused(ref, st_halo))
             halo.send(dst_index, st_halo)
             main.wait_stream(s_halo)
         elif halo is not None:
