@@ -159,6 +159,8 @@ typedef struct {
   float* marker_u;
   float* marker_force;
   VsbBodyState* body;
+  void* barrier;   /* optional 8-byte device counter (zero-initialised once): lets small bodies (<= 120 CTAs) run all
+                      iterations in one launch separated by grid barriers instead of one launch per iteration */
 } VsbMdfArgs;
 
 /* ---- fused time step ------------------------------------------------------------------- *

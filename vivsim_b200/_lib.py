@@ -63,7 +63,7 @@ class VsbMdfArgs(C.Structure):
                 ("ds_ptr", C.c_void_p), ("ds_value", C.c_float), ("u_win", C.c_void_p), ("g_win", C.c_void_p),
                 ("g_win_next", C.c_void_p),
                 ("scratch", C.c_void_p), ("scratch_next", C.c_void_p), ("marker_u", C.c_void_p),
-                ("marker_force", C.c_void_p), ("body", C.c_void_p)]
+                ("marker_force", C.c_void_p), ("body", C.c_void_p), ("barrier", C.c_void_p)]
 
 
 class VsbStepArgs(C.Structure):

@@ -67,7 +67,8 @@ __global__ void k_spread(int ncomp, long long ncell, float* __restrict__ grid, l
 
 // ----------------------------------------------------------------------------- MDF stage chain
 struct MdfParams {
-  int delta_kind, n_iter, stage, parity;
+  int delta_kind, n_iter, stage, stage_end, parity;
+  unsigned long long* barrier;
   long long n_markers;
   int origin0[3], wsize[3];
   const float* markers0;
@@ -95,12 +96,27 @@ struct MdfParams {
 //               interpolate are skipped)
 // Buffers are double-buffered by step parity: while this step accumulates into its own set, every stage clears the
 // matching buffer of the other set, so no memset is needed and nothing is cleared while it may still be read.
+// Barrier across the (small, co-resident) grid of the fused MDF launch.  Monotonic 64-bit ticket counter: never reset.
+__device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long t = atomicAdd(bar, 1ull);
+    const unsigned long long target = (t / nblocks + 1ull) * nblocks;
+    while (*reinterpret_cast<volatile unsigned long long*>(bar) < target) __nanosleep(32);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
 template <int DIM>
 __global__ void k_mdf_stage(const StepParams<DIM> sp, const MdfParams p, const BodyUpdate bu) {
   using L = Lat<DIM>;
   constexpr int NS = (DIM == 2) ? 16 : 64;   // 4^D stencil points
   constexpr int G = (DIM == 2) ? 16 : 32;    // lanes per marker
   constexpr int PPL = NS / G;                // stencil points per lane
+  constexpr int NC = WinVec<DIM>::NC;
+  using VecF = typename std::conditional<DIM == 2, float2, float4>::type;
   __shared__ float s_force[3];
   if (threadIdx.x < 3) s_force[threadIdx.x] = 0.f;
   __syncthreads();
@@ -111,25 +127,18 @@ __global__ void k_mdf_stage(const StepParams<DIM> sp, const MdfParams p, const B
   const int gl = (int)(gthread % G);
   const bool active = m < p.n_markers;
   const long long wcells = (long long)p.wsize[0] * p.wsize[1] * (DIM == 3 ? p.wsize[2] : 1);
-  const bool last = p.stage == p.n_iter - 1;
-
-  constexpr int NC = WinVec<DIM>::NC;
-  using VecF = typename std::conditional<DIM == 2, float2, float4>::type;
-  // clear the other parity's buffers for the next step
-  if (p.stage == 0)
-    for (long long i = gthread; i < NC * wcells; i += nthreads) p.g_win_next[i] = 0.f;
-  if (p.stage < p.n_iter - 1) {
-    float* z = p.scratch_next + (long long)p.stage * NC * wcells;
-    for (long long i = gthread; i < NC * wcells; i += nthreads) z[i] = 0.f;
-  }
 
   int org[3] = {p.origin0[0], p.origin0[1], p.origin0[2]};
   if (p.body) { org[0] = p.body->origin2[p.parity][0]; org[1] = p.body->origin2[p.parity][1]; org[2] = p.body->origin2[p.parity][2]; }
 
+  // stencil of this lane's marker: the same for every iteration
   float w[PPL];
   long long idx[PPL];
   int node[PPL][DIM];
   bool ok[PPL];
+  float ds2 = 0.f, tgt[DIM], u_m[DIM], F[DIM];
+#pragma unroll
+  for (int c = 0; c < DIM; ++c) { tgt[c] = 0.f; u_m[c] = 0.f; F[c] = 0.f; }
   if (active) {
     float x[DIM];
     int base[DIM];
@@ -157,80 +166,93 @@ __global__ void k_mdf_stage(const StepParams<DIM> sp, const MdfParams p, const B
       idx[j] = (DIM == 2) ? (long long)node[j][0] * p.wsize[1] + node[j][1]
                           : ((long long)node[j][0] * p.wsize[1] + node[j][1]) * p.wsize[2] + node[j][2];
     }
+    ds2 = (p.ds_ptr ? p.ds_ptr[m] : p.ds_value) * 2.0f;
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) {
+      tgt[c] = p.u_target ? p.u_target[m * DIM + c] : (p.body ? p.body->v[c] : 0.f);
+      if (p.stage > 0) { u_m[c] = p.marker_u[m * DIM + c]; F[c] = p.marker_force[m * DIM + c]; }   // from the previous launch
+    }
   } else {
 #pragma unroll
     for (int j = 0; j < PPL; ++j) { w[j] = 0.f; ok[j] = false; idx[j] = 0; }
   }
 
-  float um[DIM];
-#pragma unroll
-  for (int c = 0; c < DIM; ++c) um[c] = 0.f;
-  if (p.stage == 0 && p.u_win == nullptr) {
-#pragma unroll
-    for (int j = 0; j < PPL; ++j)
-      if (ok[j]) {
-        int cell[3] = {0, 0, 0};
-#pragma unroll
-        for (int d = 0; d < DIM; ++d) cell[d + L::A0] = org[d] + node[j][d];
-        float f[L::Q], rho, u[DIM];
-        pull_cell<DIM>(sp, cell[0], cell[1], cell[2], f, true);
-        moments<DIM>(f, rho, u);
-#pragma unroll
-        for (int c = 0; c < DIM; ++c) um[c] += w[j] * u[c];
-      }
-  } else {
-    const VecF* src = reinterpret_cast<const VecF*>(p.stage == 0 ? p.u_win : p.scratch + (long long)(p.stage - 1) * NC * wcells);
-#pragma unroll
-    for (int j = 0; j < PPL; ++j)
-      if (ok[j]) {
-        const VecF v = src[idx[j]];
-        um[0] += w[j] * v.x;
-        um[1] += w[j] * v.y;
-        if constexpr (DIM == 3) um[2] += w[j] * v.z;
-      }
-  }
-#pragma unroll
-  for (int c = 0; c < DIM; ++c) {
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) um[c] += __shfl_xor_sync(0xffffffffu, um[c], o);
-  }
+  // iterations [stage, stage_end): one per launch, or all of them in one launch separated by grid barriers
+  for (int stage = p.stage; stage < p.stage_end; ++stage) {
+    const bool last = stage == p.n_iter - 1;
+    // clear the other parity's buffers for the next step
+    if (stage == 0)
+      for (long long i = gthread; i < NC * wcells; i += nthreads) p.g_win_next[i] = 0.f;
+    if (stage < p.n_iter - 1) {
+      float* z = p.scratch_next + (long long)stage * NC * wcells;
+      for (long long i = gthread; i < NC * wcells; i += nthreads) z[i] = 0.f;
+    }
 
-  float spread_val[DIM];
-  if (active) {
-    const float ds2 = (p.ds_ptr ? p.ds_ptr[m] : p.ds_value) * 2.0f;
-    float u_new[DIM], f_new[DIM];
+    float um[DIM];
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) um[c] = 0.f;
+    if (stage == 0 && p.u_win == nullptr) {
+#pragma unroll
+      for (int j = 0; j < PPL; ++j)
+        if (ok[j]) {
+          int cell[3] = {0, 0, 0};
+#pragma unroll
+          for (int d = 0; d < DIM; ++d) cell[d + L::A0] = org[d] + node[j][d];
+          float f[L::Q], rho, u[DIM];
+          pull_cell<DIM>(sp, cell[0], cell[1], cell[2], f, true);
+          moments<DIM>(f, rho, u);
+#pragma unroll
+          for (int c = 0; c < DIM; ++c) um[c] += w[j] * u[c];
+        }
+    } else {
+      const VecF* src = reinterpret_cast<const VecF*>(stage == 0 ? p.u_win : p.scratch + (long long)(stage - 1) * NC * wcells);
+#pragma unroll
+      for (int j = 0; j < PPL; ++j)
+        if (ok[j]) {
+          const VecF v = __ldcg(src + idx[j]);   // written by other SMs' reductions: read at L2
+          um[0] += w[j] * v.x;
+          um[1] += w[j] * v.y;
+          if constexpr (DIM == 3) um[2] += w[j] * v.z;
+        }
+    }
 #pragma unroll
     for (int c = 0; c < DIM; ++c) {
-      // every lane of the group reads the previous stage's marker state before lane 0 overwrites it
-      const float u_m = (p.stage == 0) ? um[c] : p.marker_u[m * DIM + c] + 0.5f * um[c];
-      const float tgt = p.u_target ? p.u_target[m * DIM + c] : (p.body ? p.body->v[c] : 0.f);
-      const float dF = (tgt - u_m) * ds2;
-      const float F = (p.stage == 0 ? 0.f : p.marker_force[m * DIM + c]) + dF;
-      u_new[c] = u_m;
-      f_new[c] = F;
-      spread_val[c] = last ? F : dF;
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) um[c] += __shfl_xor_sync(0xffffffffu, um[c], o);
     }
-    __syncwarp(__activemask());
-    if (gl == 0) {
+
+    if (active) {
+      float spread_val[DIM];
 #pragma unroll
       for (int c = 0; c < DIM; ++c) {
-        p.marker_u[m * DIM + c] = u_new[c];
-        p.marker_force[m * DIM + c] = f_new[c];
+        u_m[c] = (stage == 0) ? um[c] : u_m[c] + 0.5f * um[c];
+        const float dF = (tgt[c] - u_m[c]) * ds2;
+        F[c] = (stage == 0 ? 0.f : F[c]) + dF;
+        spread_val[c] = last ? F[c] : dF;
+      }
+      if (gl == 0) {
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) {
+          p.marker_u[m * DIM + c] = u_m[c];
+          p.marker_force[m * DIM + c] = F[c];
+        }
+      }
+      VecF* dst = reinterpret_cast<VecF*>(last ? p.g_win : p.scratch + (long long)stage * NC * wcells);
+#pragma unroll
+      for (int j = 0; j < PPL; ++j)
+        if (ok[j]) {   // one vector reduction (red.global.add.v2/v4.f32) per stencil point
+          if constexpr (DIM == 2) atomicAdd(dst + idx[j], make_float2(spread_val[0] * w[j], spread_val[1] * w[j]));
+          else atomicAdd(dst + idx[j], make_float4(spread_val[0] * w[j], spread_val[1] * w[j], spread_val[2] * w[j], 0.f));
+        }
+      if (last && p.body && gl == 0) {
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) atomicAdd(&s_force[c], spread_val[c]);
       }
     }
-    VecF* dst = reinterpret_cast<VecF*>(last ? p.g_win : p.scratch + (long long)p.stage * NC * wcells);
-#pragma unroll
-    for (int j = 0; j < PPL; ++j)
-      if (ok[j]) {   // one vector reduction (red.global.add.v2/v4.f32) per stencil point
-        if constexpr (DIM == 2) atomicAdd(dst + idx[j], make_float2(spread_val[0] * w[j], spread_val[1] * w[j]));
-        else atomicAdd(dst + idx[j], make_float4(spread_val[0] * w[j], spread_val[1] * w[j], spread_val[2] * w[j], 0.f));
-      }
-    if (last && p.body && gl == 0) {
-#pragma unroll
-      for (int c = 0; c < DIM; ++c) atomicAdd(&s_force[c], spread_val[c]);
-    }
+    if (stage + 1 < p.stage_end) grid_barrier(p.barrier, gridDim.x);
   }
-  if (last && p.body) {
+
+  if (p.stage_end == p.n_iter && p.body) {
     __syncthreads();
     if (threadIdx.x < DIM) atomicAdd(&p.body->force_sum[threadIdx.x], s_force[threadIdx.x]);
     if (p.update_body) {   // the last CTA to arrive sees every contribution and advances the body
@@ -273,9 +295,17 @@ static int mdf_impl(const VsbStepArgs& sa, const VsbMdfArgs& a, const VsbBodyPar
   if (p.update_body) bu = make_body_update(*bp, DIM);
   const int lanes = (DIM == 2) ? 16 : 32;
   const unsigned nb = blocks_for(a.n_markers * lanes, kBlock);
-  for (int k = 0; k < a.n_iter; ++k) {
-    p.stage = k;
+  p.barrier = reinterpret_cast<unsigned long long*>(a.barrier);
+  // Small bodies: every iteration in ONE launch, separated by grid barriers (all CTAs are co-resident: at most 120 of
+  // 128 threads).  Large bodies: one launch per iteration.
+  if (a.barrier && nb <= 120) {
+    p.stage = 0; p.stage_end = a.n_iter;
     k_mdf_stage<DIM><<<nb, kBlock, 0, stream>>>(sp, p, bu);
+  } else {
+    for (int k = 0; k < a.n_iter; ++k) {
+      p.stage = k; p.stage_end = k + 1;
+      k_mdf_stage<DIM><<<nb, kBlock, 0, stream>>>(sp, p, bu);
+    }
   }
   VSB_LAUNCH_CHECK("vsb_ib_mdf");
   return VSB_OK;

@@ -216,6 +216,10 @@ class Stepper:
             a.win_size[d] = self.win_size[d]
         m.markers0 = self._markers.data_ptr()
         m.u_target = self._u_target.data_ptr() if self._u_target is not None else None
+        self._mdf_barrier = torch.zeros(2, dtype=torch.int64, device=dev)
+        m.barrier = self._mdf_barrier.data_ptr()
+        lanes = 16 if dim == 2 else 32
+        self._mdf_one_launch = (self.n_markers * lanes + 127) // 128 <= 120
         m.marker_u = self._marker_u.data_ptr()
         m.marker_force = self.marker_force.data_ptr()
         a.g_win = self._g_win.data_ptr()
@@ -282,7 +286,8 @@ class Stepper:
         if self.ib is not None:
             if self.overlap:
                 n += 1                                    # second launch of the fused kernel (window x-range)
-            n += 1 if self.ib_fused else self.n_iter + (1 if self._use_uwin else 0)
+            n += 1 if (self.ib_fused or self._mdf_one_launch) else self.n_iter
+            n += 1 if (self._use_uwin and not self.ib_fused) else 0
         return n
 
     def attach_halo(self, halo):
