@@ -149,6 +149,35 @@ class PeerHalo:
         return bool(self.counter[2].item())
 
 
+class LocalHalo:
+    """Single-rank stand-in for PeerHalo: the "neighbours" are the slab itself (periodic wrap), so `send` copies the
+    edge layers into the slab's own ghost layers and `wait` has nothing to wait for.  Exercises the pipelined step
+    (interior rows / wait / edge rows / send) on one GPU."""
+
+    def __init__(self, slab, buffers):
+        self.slab, self._bufs = slab, buffers
+
+    def buffers(self):
+        return self._bufs
+
+    def _copy(self, index, st):
+        stream = torch.cuda.ExternalStream(st.value) if st is not None and st.value else torch.cuda.current_stream()
+        with torch.cuda.stream(stream):
+            exchange_halo(self._bufs[index], self.slab)
+
+    def push(self, index, st=None):
+        self._copy(index, st)
+
+    def send(self, index, st=None):
+        self._copy(index, st)
+
+    def wait(self, st=None):
+        pass
+
+    def timed_out(self):
+        return False
+
+
 def localize_spec(spec, slab, local_ib=None):
     """Per-rank step description: local extent with ghost layers, x-face operations only on the owning rank,
     immersed body (``spec['ib']`` or ``local_ib(slab)``, global coordinates) shifted to local coordinates."""
@@ -227,6 +256,9 @@ class SlabStepper:
         buffers = self.peer.buffers() if self.peer is not None else None
         self.stepper = Stepper(self.local_spec, rows=self.slab.rows, body=body if has_body else None, buffers=buffers, **kw)
         self.owns_body = has_body
+        if world == 1 and halo == "pipelined-local":   # one rank, but through the same pipelined pass as peer mode
+            self.peer = LocalHalo(self.slab, self.stepper._bufs)
+            self.halo = "pipelined-local"
         if self.peer is not None:
             self.stepper.attach_halo(self.peer)     # the halo kernels become part of every pass of the stepper
         self.n_launch_per_step = self.stepper.n_launch_per_step
