@@ -40,15 +40,15 @@ __device__ __forceinline__ void store_vec(float* __restrict__ p, const float (&v
 }
 
 template <int DIM, int COLL>
-__device__ __forceinline__ void edge_block(const StepParams<DIM>& p, const MrtMats<DIM, COLL == VSB_COLL_MRT>& mm);
+__device__ __forceinline__ void edge_block(const StepParams<DIM>& p, const MrtMats<DIM, is_mrt(COLL)>& mm);
 
 // register budget: 128 (2 CTAs / SM) in 3-D; in 2-D 64 (4 CTAs) for BGK / regularised, 85 (3 CTAs) for KBC / MRT
 template <int DIM, int COLL> constexpr int step_min_ctas() {
-  return DIM == 3 ? 2 : ((COLL == VSB_COLL_KBC || COLL == VSB_COLL_MRT) ? 3 : 4);
+  return DIM == 3 ? 2 : ((COLL == VSB_COLL_KBC || is_mrt(COLL)) ? 3 : 4);
 }
 
 template <int DIM, int COLL, int VEC>
-__global__ void __launch_bounds__(256, step_min_ctas<DIM, COLL>()) k_step(const StepParams<DIM> p, const MrtMats<DIM, COLL == VSB_COLL_MRT> mm) {
+__global__ void __launch_bounds__(256, step_min_ctas<DIM, COLL>()) k_step(const StepParams<DIM> p, const MrtMats<DIM, is_mrt(COLL)> mm) {
   using L = Lat<DIM>;
   constexpr int Q = L::Q;
   if (blockIdx.x >= p.nb_bulk) {   // blocks appended after the bulk: wall layers of the face operations (edges = 2)
@@ -63,65 +63,85 @@ __global__ void __launch_bounds__(256, step_min_ctas<DIM, COLL>()) k_step(const 
   const int band_lo = max(p.s_begin, worg[0]), band_hi = min(p.s_end, worg[0] + p.wsz[0]);
   const int row0 = (p.band == 2) ? band_lo : p.s_begin;
   const int nrow = p.edge_rows ? 2 : ((p.band == 2) ? max(band_hi - band_lo, 0) : p.s_end - p.s_begin);
-  const long long rows = (DIM == 2) ? (long long)nrow : (long long)nrow * p.n1;
-  const long long total = rows * nv;
-  long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned total = (unsigned)((DIM == 2) ? nrow : nrow * p.n1) * (unsigned)nv;   // < 2^31, checked by the host
+  unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
   bool active = gid < total;
   if (!active) gid = 0;          // the lane stays in the shuffles; it loads and stores nothing
-  const int j = (int)(gid % nv);
-  const long long row = gid / nv;
-  const int rx = (DIM == 2) ? (int)row : (int)(row / p.n1);          // row counter along the slowest axis
+  const unsigned row = fast_div(gid, p.div_nv);
+  const int j = (int)(gid - row * (unsigned)nv);
+  const int rx = (DIM == 2) ? (int)row : (int)fast_div(row, p.div_n1);   // row counter along the slowest axis
   const int ix0 = p.edge_rows ? (rx == 0 ? p.r_begin : p.r_end - 1) : row0 + rx;
   const int i0 = (DIM == 2) ? 0 : ix0;
-  const int i1 = (DIM == 2) ? ix0 : (int)(row % p.n1);
+  const int i1 = (DIM == 2) ? ix0 : (int)row - rx * p.n1;
   const int i2 = j * VEC;
   const int lane = threadIdx.x & 31;
-  const long long ncell = (long long)p.n0 * p.n1 * p.n2;
-  const long long cell = ((long long)i0 * p.n1 + i1) * p.n2 + i2;
+  const int n12 = p.n1 * p.n2;
+  const long long ncell = (long long)p.n0 * n12;
+  const long long cell = (long long)i0 * n12 + (i1 * p.n2 + i2);
   {
     const int ix = (DIM == 2) ? i1 : i0;
     if (p.band == 1 && ix >= band_lo && ix < band_hi) active = false;
-    const int coord[2] = {i0, i1};
-    for (int e = 0; e < p.n_skip; ++e)   // wall layers owned by the fused wall kernel
-      if (coord[p.skip_axis[e]] == p.skip_layer[e]) active = false;
+    // wall layers owned by the fused wall kernel (at most two)
+    if (p.n_skip > 0 && (p.skip_axis[0] ? i1 : i0) == p.skip_layer[0]) active = false;
+    if (p.n_skip > 1 && (p.skip_axis[1] ? i1 : i0) == p.skip_layer[1]) active = false;
   }
 
   float f[VEC][Q];
   if (p.do_stream) {
-    static_for<Q>([&](auto qc) {
-      constexpr int q = decltype(qc)::value;
-      constexpr int c2 = L::c(q, 2);
-      const int s0 = (DIM == 2) ? 0 : wrap(i0 - L::c(q, 0), p.n0);
-      const int s1 = wrap(i1 - L::c(q, 1), p.n1);
-      const float* __restrict__ src = p.fin + q * ncell + ((long long)s0 * p.n1 + s1) * p.n2;
-      if constexpr (VEC == 1) {
-        f[0][q] = active ? __ldg(src + wrap(i2 - c2, p.n2)) : 1.0f;
-      } else {
-        float v[VEC];
-        if (active) {
-          load_vec<VEC>(src + i2, v);
-        } else {
+    // Element offsets of the pulled rows relative to this thread's own cells, periodic in the array extents:
+    // index 0 for c = +1 (source row i - 1), 1 for c = 0, 2 for c = -1 (source row i + 1).  |offset| < ncell < 2^31.
+    int d0[3] = {0, 0, 0}, d1[3];
+    d1[0] = (i1 == 0 ? p.n1 - 1 : -1) * p.n2;
+    d1[1] = 0;
+    d1[2] = (i1 == p.n1 - 1 ? 1 - p.n1 : 1) * p.n2;
+    if constexpr (DIM == 3) {
+      d0[0] = (i0 == 0 ? p.n0 - 1 : -1) * n12;
+      d0[2] = (i0 == p.n0 - 1 ? 1 - p.n0 : 1) * n12;
+    }
+    const float* __restrict__ own = p.fin + cell;
+    if (!active) {   // idle lanes still take part in the shuffles: they all read the first cells of each plane (cached)
+      own = p.fin;
 #pragma unroll
-          for (int k = 0; k < VEC; ++k) v[k] = 1.0f;
-        }
+      for (int k = 0; k < 3; ++k) { d0[k] = 0; d1[k] = 0; }
+    }
+    auto source = [&](auto qc) -> const float* {
+      constexpr int q = decltype(qc)::value;
+      return own + q * ncell + (d0[1 - L::c(q, 0)] + d1[1 - L::c(q, 1)]);
+    };
+    if constexpr (VEC == 1) {
+      static_for<Q>([&](auto qc) {
+        constexpr int q = decltype(qc)::value;
+        constexpr int c2 = L::c(q, 2);
+        const int sh = (c2 > 0) ? (i2 == 0 ? p.n2 - 1 : -1) : ((c2 < 0) ? (i2 == p.n2 - 1 ? 1 - p.n2 : 1) : 0);
+        f[0][q] = __ldg(source(qc) + (active ? sh : 0));
+      });
+    } else {
+      // all aligned vector loads first (one predicated block), then the one-element shifts of the populations that
+      // move along the contiguous axis
+      float v[Q][VEC];
+      static_for<Q>([&](auto qc) { load_vec<VEC>(source(qc), v[decltype(qc)::value]); });
+      const bool first = active && (lane == 0 || j == 0), last = active && (lane == 31 || j == nv - 1);
+      static_for<Q>([&](auto qc) {
+        constexpr int q = decltype(qc)::value;
+        constexpr int c2 = L::c(q, 2);
         if constexpr (c2 == 0) {
 #pragma unroll
-          for (int k = 0; k < VEC; ++k) f[k][q] = v[k];
+          for (int k = 0; k < VEC; ++k) f[k][q] = v[q][k];
         } else if constexpr (c2 > 0) {  // new[i2 + k] = old[i2 + k - 1]
-          float left = __shfl_up_sync(0xffffffffu, v[VEC - 1], 1);
-          if (active && (lane == 0 || j == 0)) left = __ldg(src + (i2 == 0 ? p.n2 - 1 : i2 - 1));
+          float left = __shfl_up_sync(0xffffffffu, v[q][VEC - 1], 1);
+          if (first) left = __ldg(source(qc) + (i2 == 0 ? p.n2 - 1 : -1));
           f[0][q] = left;
 #pragma unroll
-          for (int k = 1; k < VEC; ++k) f[k][q] = v[k - 1];
+          for (int k = 1; k < VEC; ++k) f[k][q] = v[q][k - 1];
         } else {                        // new[i2 + k] = old[i2 + k + 1]
-          float right = __shfl_down_sync(0xffffffffu, v[0], 1);
-          if (active && (lane == 31 || j == nv - 1)) right = __ldg(src + (i2 + VEC == p.n2 ? 0 : i2 + VEC));
+          float right = __shfl_down_sync(0xffffffffu, v[q][0], 1);
+          if (last) right = __ldg(source(qc) + (i2 + VEC == p.n2 ? VEC - p.n2 : VEC));
           f[VEC - 1][q] = right;
 #pragma unroll
-          for (int k = 0; k < VEC - 1; ++k) f[k][q] = v[k + 1];
+          for (int k = 0; k < VEC - 1; ++k) f[k][q] = v[q][k + 1];
         }
-      }
-    });
+      });
+    }
     if (p.mask && active) {  // obstacle_bounce_back on the streamed populations (lbm/boundary/bb.py:110)
 #pragma unroll
       for (int k = 0; k < VEC; ++k) {
@@ -135,15 +155,11 @@ __global__ void __launch_bounds__(256, step_min_ctas<DIM, COLL>()) k_step(const 
       }
     }
   } else {
+    const float* __restrict__ own = p.fin + (active ? cell : 0);
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
       float v[VEC];
-      if (active) {
-        load_vec<VEC>(p.fin + q * ncell + cell, v);
-      } else {
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) v[k] = 1.0f;
-      }
+      load_vec<VEC>(own + q * ncell, v);
 #pragma unroll
       for (int k = 0; k < VEC; ++k) f[k][q] = v[k];
     }
@@ -228,7 +244,7 @@ __global__ void k_lines_mask(const StepParams<DIM> p, const LineSet ls, const ui
 }
 
 template <int DIM, int COLL>
-__global__ void k_lines_collide(const StepParams<DIM> p, const MrtMats<DIM, COLL == VSB_COLL_MRT> mm, const LineSet ls) {
+__global__ void k_lines_collide(const StepParams<DIM> p, const MrtMats<DIM, is_mrt(COLL)> mm, const LineSet ls) {
   using L = Lat<DIM>;
   int c[3];
   if (!line_cell<DIM>(p, ls, blockIdx.y, (long long)blockIdx.x * blockDim.x + threadIdx.x, c)) return;
@@ -276,7 +292,7 @@ __global__ void k_window_moments(const StepParams<DIM> p, float* __restrict__ u_
 // One wall cell: pull, face operation, (mask), collide, store.  Face operations handled this way are independent of
 // each other (see vsb_edge_fused_supported), so no ordering between them is needed.
 template <int DIM, int COLL, int LOC>
-__device__ __forceinline__ void edge_cell(const StepParams<DIM>& p, const MrtMats<DIM, COLL == VSB_COLL_MRT>& mm, int wall_layer,
+__device__ __forceinline__ void edge_cell(const StepParams<DIM>& p, const MrtMats<DIM, is_mrt(COLL)>& mm, int wall_layer,
                                           int kind, int wrap_kind, const WallVals& w, int mask_before, long long k) {
   using L = Lat<DIM>;
   using G = FaceGeom<DIM, LOC>;
@@ -335,13 +351,13 @@ __device__ __forceinline__ void edge_cell(const StepParams<DIM>& p, const MrtMat
 
 // Wall layer of one face as a kernel of its own (vsb_edge_fused).
 template <int DIM, int COLL, int LOC>
-__global__ void k_edge_fused(const StepParams<DIM> p, const MrtMats<DIM, COLL == VSB_COLL_MRT> mm, int wall_layer, int kind,
+__global__ void k_edge_fused(const StepParams<DIM> p, const MrtMats<DIM, is_mrt(COLL)> mm, int wall_layer, int kind,
                              int wrap_kind, WallVals w, int mask_before) {
   edge_cell<DIM, COLL, LOC>(p, mm, wall_layer, kind, wrap_kind, w, mask_before, (long long)blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 template <int DIM, int COLL>
-__device__ __forceinline__ void edge_block(const StepParams<DIM>& p, const MrtMats<DIM, COLL == VSB_COLL_MRT>& mm) {
+__device__ __forceinline__ void edge_block(const StepParams<DIM>& p, const MrtMats<DIM, is_mrt(COLL)>& mm) {
   unsigned b = blockIdx.x - p.nb_bulk;
   int e = 0;
   if (p.n_wall > 1 && b >= p.wall_blocks0) { e = 1; b -= p.wall_blocks0; }
@@ -402,14 +418,30 @@ template int fill_params<2>(const VsbStepArgs&, StepParams<2>&);
 template int fill_params<3>(const VsbStepArgs&, StepParams<3>&);
 
 template <int DIM, int COLL>
-static void fill_mats(const VsbStepArgs& a, MrtMats<DIM, COLL == VSB_COLL_MRT>& mm) {
-  if constexpr (COLL == VSB_COLL_MRT) {
+static void fill_mats(const VsbStepArgs& a, MrtMats<DIM, is_mrt(COLL)>& mm) {
+  if constexpr (is_mrt(COLL)) {
     constexpr int Q = Lat<DIM>::Q;
     for (int i = 0; i < Q * Q; ++i) {
       mm.A.a[i] = a.mrt_op_host ? a.mrt_op_host[i] : 0.f;
       mm.B.a[i] = a.mrt_fop_host ? a.mrt_fop_host[i] : 0.f;
     }
+    if constexpr (COLL == VSB_COLL_MRT_SPLIT) {
+      make_split_op<DIM>(mm.A.a, mm.As);
+      make_split_op<DIM>(mm.B.a, mm.Bs);
+    }
   }
+}
+
+// True when the MRT operators of this call commute with the reflection c -> -c (see SplitOp).
+template <int DIM>
+static bool mrt_is_split(const VsbStepArgs& a) {
+  constexpr int Q = Lat<DIM>::Q;
+  if (!a.mrt_op_host) return false;
+  SplitOp<DIM> tmp;
+  if (!make_split_op<DIM>(a.mrt_op_host, tmp)) return false;
+  if (a.mrt_fop_host) return make_split_op<DIM>(a.mrt_fop_host, tmp);
+  float zero[Q * Q] = {};
+  return make_split_op<DIM>(zero, tmp);
 }
 
 static int check_mrt(const VsbStepArgs& a) {
@@ -460,7 +492,7 @@ static bool edges_independent(const VsbStepArgs& a, const StepParams<DIM>& p, in
 }
 
 template <int DIM, int COLL, int LOC>
-static int launch_edge(const StepParams<DIM>& p, const MrtMats<DIM, COLL == VSB_COLL_MRT>& mm, const VsbPostOp& op,
+static int launch_edge(const StepParams<DIM>& p, const MrtMats<DIM, is_mrt(COLL)>& mm, const VsbPostOp& op,
                        int mask_before, cudaStream_t s) {
   using G = FaceGeom<DIM, LOC>;
   const int n[3] = {p.n0, p.n1, p.n2};
@@ -485,7 +517,7 @@ static int edge_impl(const VsbStepArgs& a, cudaStream_t s, bool query_only, int*
   if (query_only) return VSB_OK;
   VSB_REQUIRE(ok, "vsb_edge_fused: the face operations are not independent; use the ordered fix-up (edges = 0)");
   if (int rc = check_mrt(a)) return rc;
-  MrtMats<DIM, COLL == VSB_COLL_MRT> mm;
+  MrtMats<DIM, is_mrt(COLL)> mm;
   fill_mats<DIM, COLL>(a, mm);
   for (int i = 0; i < a.n_post; ++i) {
     const VsbPostOp& op = a.post[i];
@@ -511,7 +543,7 @@ static int step_impl(const VsbStepArgs& a, cudaStream_t s) {
   StepParams<DIM> p;
   if (int rc = fill_params<DIM>(a, p)) return rc;
   if (int rc = check_mrt(a)) return rc;
-  MrtMats<DIM, COLL == VSB_COLL_MRT> mm;
+  MrtMats<DIM, is_mrt(COLL)> mm;
   fill_mats<DIM, COLL>(a, mm);
   const bool have_ops = a.n_post > 0 && a.do_stream;
   if ((a.edges == 1 || a.edges == 2) && have_ops) {
@@ -535,14 +567,18 @@ static int step_impl(const VsbStepArgs& a, cudaStream_t s) {
     }
   }
   int vec = a.vec;
-  // measured on B200 (scripts/vec_sweep.py): 4 cells per thread (128-bit accesses) is fastest for every lattice and
-  // collision model once the kernel is held to 128 registers
-  if (vec == 0) vec = 4;
+  // measured on B200 (scripts/vec_sweep.py, profiles/r01_summary.md section 4): D2Q9 is fastest with 4 cells per
+  // thread (128-bit accesses); D3Q19 with 2 (64-bit accesses, 38 instead of 76 population registers per thread)
+  if (vec == 0) vec = (DIM == 3) ? 2 : 4;
   while (vec > 1 && (p.n2 % vec != 0 || ((uintptr_t)a.f_in % (4 * vec)) || ((uintptr_t)a.f_out % (4 * vec)))) vec >>= 1;
   VSB_REQUIRE(vec == 1 || vec == 2 || vec == 4, "vsb_step: vec must be 0, 1, 2 or 4");
   const int nrow = p.edge_rows ? 2 : ((p.band == 2) ? std::min(p.wsz[0], p.s_end - p.s_begin) : p.s_end - p.s_begin);
   const long long rows = (DIM == 2) ? (long long)nrow : (long long)nrow * p.n1;
   const long long total = rows * (p.n2 / vec);
+  VSB_REQUIRE(total < (1ll << 31) && (long long)p.n0 * p.n1 * p.n2 < (1ll << 31),
+              "vsb_step: more than 2^31 cells in one launch; split the rows (sub_begin / sub_end)");
+  p.div_nv = make_fast_div((unsigned)(p.n2 / vec));
+  p.div_n1 = make_fast_div((unsigned)p.n1);
   // Block size: for grids of only a few waves (e.g. 1024^2 = 1.73 waves of 256-thread blocks) the partly filled last
   // wave costs up to a whole wave; choose the multiple of 32 in [128, 256] that fills the last wave best.
   auto launch = [&](auto kernel) {
@@ -635,7 +671,10 @@ static int step_dispatch(const VsbStepArgs& a, cudaStream_t s, int what, int* su
   // what: 0 step, 1 fused wall kernel, 2 query support of the fused wall kernel
   switch (a.collision) {
     case VSB_COLL_BGK: return what ? edge_impl<DIM, VSB_COLL_BGK>(a, s, what == 2, supported) : step_impl<DIM, VSB_COLL_BGK>(a, s);
-    case VSB_COLL_MRT: return what ? edge_impl<DIM, VSB_COLL_MRT>(a, s, what == 2, supported) : step_impl<DIM, VSB_COLL_MRT>(a, s);
+    case VSB_COLL_MRT:
+      if (mrt_is_split<DIM>(a))
+        return what ? edge_impl<DIM, VSB_COLL_MRT_SPLIT>(a, s, what == 2, supported) : step_impl<DIM, VSB_COLL_MRT_SPLIT>(a, s);
+      return what ? edge_impl<DIM, VSB_COLL_MRT>(a, s, what == 2, supported) : step_impl<DIM, VSB_COLL_MRT>(a, s);
     case VSB_COLL_KBC: return what ? edge_impl<DIM, VSB_COLL_KBC>(a, s, what == 2, supported) : step_impl<DIM, VSB_COLL_KBC>(a, s);
     case VSB_COLL_REG: return what ? edge_impl<DIM, VSB_COLL_REG>(a, s, what == 2, supported) : step_impl<DIM, VSB_COLL_REG>(a, s);
     default: VSB_REQUIRE(false, "vsb_step: unknown collision %d", a.collision);

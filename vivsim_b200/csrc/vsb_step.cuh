@@ -18,6 +18,24 @@ __device__ __forceinline__ void static_for(F&& body) {
   static_for_impl(body, std::make_integer_sequence<int, N>{});
 }
 
+// Division of an index n < 2^31 by a launch constant: quotient = umulhi(n, mul) >> shr (divisor 1: mul = 0).
+struct FastDiv { unsigned mul, shr; };
+
+inline FastDiv make_fast_div(unsigned d) {
+  FastDiv f{0u, 0u};
+  if (d <= 1) return f;
+  unsigned lg = 0;
+  while ((1ull << lg) < d) ++lg;                       // ceil(log2 d)
+  const unsigned p = 31 + lg;
+  f.mul = (unsigned)(((1ull << p) + d - 1) / d);
+  f.shr = p - 32;
+  return f;
+}
+
+__device__ __forceinline__ unsigned fast_div(unsigned n, const FastDiv& f) {
+  return f.mul ? (__umulhi(n, f.mul) >> f.shr) : n;
+}
+
 // One face operation handled inside the fused kernel's launch (extra blocks after the bulk blocks).
 struct WallOpDev {
   int kind, wrap, loc, layer, mask_before;
@@ -45,9 +63,19 @@ template <int DIM> struct StepParams {
   int n_wall;           // face operations executed by the blocks appended to this launch (edges = 2)
   unsigned nb_bulk, wall_blocks0;
   WallOpDev wall[2];
+  FastDiv div_nv, div_n1;   // thread index -> (row, vector column), row -> (i0, i1)
 };
 
-template <int DIM, bool USED> struct MrtMats { Matrix<Lat<DIM>::Q> A, B; };
+// MRT operators: collision A and Guo source B (lbm/collision/mrt.py:88, lbm/forcing/guo.py:60-75) as dense matrices
+// and in parity-split form.  Operators that commute with the reflection c -> -c (every M^-1 S M does) run the
+// kernels instantiated for VSB_COLL_MRT_SPLIT, which use only As / Bs; any other matrix runs the dense kernels.
+constexpr int VSB_COLL_MRT_SPLIT = 100;   // internal collision id, never crosses the ABI
+__host__ __device__ constexpr bool is_mrt(int coll) { return coll == VSB_COLL_MRT || coll == VSB_COLL_MRT_SPLIT; }
+
+template <int DIM, bool USED> struct MrtMats {
+  Matrix<Lat<DIM>::Q> A, B;
+  SplitOp<DIM> As, Bs;
+};
 template <int DIM> struct MrtMats<DIM, false> {};
 
 __device__ __forceinline__ int wrap(int i, int n) {
@@ -181,9 +209,10 @@ template <int DIM> struct WinVec { static constexpr int NC = (DIM == 2) ? 2 : 4;
 // Guo shifts u by g/(2 rho) before the equilibrium).
 template <int DIM, int COLL>
 __device__ __forceinline__ void collide_cell(float (&f)[Lat<DIM>::Q], const float (&g)[Lat<DIM>::D], int forcing,
-                                             const Relax& rx, const MrtMats<DIM, COLL == VSB_COLL_MRT>& mm) {
+                                             const Relax& rx, const MrtMats<DIM, is_mrt(COLL)>& mm) {
   using L = Lat<DIM>;
-  float rho, u[L::D], feq[L::Q];
+  float rho, u[L::D];
+  [[maybe_unused]] float feq[L::Q];
   moments<DIM>(f, rho, u);
   // a zero force contributes exactly nothing (u + 0, f + w*0): skip the work -- bit-identical
   bool has_g = false;
@@ -194,11 +223,22 @@ __device__ __forceinline__ void collide_cell(float (&f)[Lat<DIM>::Q], const floa
 #pragma unroll
     for (int d = 0; d < L::D; ++d) u[d] += g[d] * 0.5f / rho;
   }
-  equilibrium<DIM>(rho, u, feq);
-  if constexpr (COLL == VSB_COLL_BGK) collide_bgk<DIM>(f, feq, rx);
-  if constexpr (COLL == VSB_COLL_KBC) collide_kbc<DIM>(f, feq, rx);
-  if constexpr (COLL == VSB_COLL_REG) collide_reg<DIM>(f, feq, rx);
-  if constexpr (COLL == VSB_COLL_MRT) collide_mrt<DIM>(f, feq, mm.A);
+  if constexpr (COLL == VSB_COLL_KBC) {
+    float feq0, A[Pairs<DIM>::NP], B[Pairs<DIM>::NP];
+    equilibrium_pairs<DIM>(rho, u, feq0, A, B);
+    collide_kbc_pairs<DIM>(f, feq0, A, B, rx);
+  } else if constexpr (COLL == VSB_COLL_MRT_SPLIT) {
+    float feq0, A[Pairs<DIM>::NP], B[Pairs<DIM>::NP];
+    equilibrium_pairs<DIM>(rho, u, feq0, A, B);
+    collide_mrt_split<DIM>(f, feq0, A, B, mm.As);
+  } else if constexpr (COLL == VSB_COLL_MRT) {
+    equilibrium<DIM>(rho, u, feq);
+    collide_mrt<DIM>(f, feq, mm.A);
+  } else {
+    equilibrium<DIM>(rho, u, feq);
+    if constexpr (COLL == VSB_COLL_BGK) collide_bgk<DIM>(f, feq, rx);
+    if constexpr (COLL == VSB_COLL_REG) collide_reg<DIM>(f, feq, rx);
+  }
   if (forcing != VSB_FORCE_NONE) {
     float G[L::Q];
     guo_term<DIM>(g, u, G);
@@ -206,7 +246,16 @@ __device__ __forceinline__ void collide_cell(float (&f)[Lat<DIM>::Q], const floa
 #pragma unroll
       for (int q = 0; q < L::Q; ++q) f[q] += G[q];
     } else {
-      if constexpr (COLL == VSB_COLL_MRT) {
+      if constexpr (COLL == VSB_COLL_MRT_SPLIT) {
+        float xs[Pairs<DIM>::NP], xa[Pairs<DIM>::NP];
+#pragma unroll
+        for (int k = 0; k < Pairs<DIM>::NP; ++k) {
+          const int q = Pairs<DIM>::q(k), o = L::opp(q);
+          xs[k] = G[q] + G[o];
+          xa[k] = G[q] - G[o];
+        }
+        split_matvec_add<DIM>(f, mm.Bs, G[0], xs, xa);
+      } else if constexpr (COLL == VSB_COLL_MRT) {
         matvec_add<DIM>(f, mm.B, G);
       } else {
 #pragma unroll
