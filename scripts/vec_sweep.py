@@ -17,7 +17,14 @@ def run(tag, spec, bpc, vecs=(1, 2, 4), steps=20):
         print(f"{tag:28s} vec={vec} {ms*1e3:9.1f} us/step  {cells/ms/1e3:9.0f} MLUPS  {cells*bpc/ms/1e6/6452.8:5.3f} of HBM")
         del st
 
+if "quick" in sys.argv:
+    for coll in ("bgk", "kbc", "mrt"):
+        run(f"D3Q19 {coll} 256^3", dict(dim=3, shape=(256, 256, 256), collision=coll, omega=1.7, forcing=None, post=[], u0=0.05), 152, vecs=(2, 4))
+    for coll in ("bgk", "kbc"):
+        run(f"D2Q9 {coll} 8192^2", dict(dim=2, shape=(8192, 8192), collision=coll, omega=1.7, forcing=None, post=[], u0=0.05), 72, vecs=(4,), steps=8)
+    sys.exit(0)
 for coll in ("bgk", "kbc", "reg", "mrt"):
     run(f"D3Q19 {coll} 256^3", dict(dim=3, shape=(256, 256, 256), collision=coll, omega=1.7, forcing=None, post=[], u0=0.05), 152)
+if "3d" in sys.argv: sys.exit(0)
 for coll in ("bgk", "kbc", "reg", "mrt"):
     run(f"D2Q9 {coll} 8192^2", dict(dim=2, shape=(8192, 8192), collision=coll, omega=1.7, forcing=None, post=[], u0=0.05), 72, steps=8)

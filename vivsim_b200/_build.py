@@ -31,8 +31,9 @@ def _deps_mtime():
     return max(os.path.getmtime(h) for h in hdrs)
 
 
-def build(force=False, verbose=False):
-    bdir = os.path.join(CSRC, "build")
+def build(force=False, verbose=False, out=OUT, defines=()):
+    """`out` / `defines` build a tuning variant next to the product library (scripts/tune_variants.py)."""
+    bdir = os.path.join(CSRC, "build") if out == OUT else out + ".obj"
     os.makedirs(bdir, exist_ok=True)
     dep = _deps_mtime()
     jobs = []
@@ -41,7 +42,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(bdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), dep):
-            cmd = [NVCC, *ARCH, *FLAGS, "-c", src, "-o", obj]
+            cmd = [NVCC, *ARCH, *FLAGS, *["-D" + d for d in defines], "-c", src, "-o", obj]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             jobs.append(cmd)
@@ -58,13 +59,13 @@ def build(force=False, verbose=False):
             failed |= r.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed (see output above)")
-    if jobs or force or not os.path.exists(OUT):
-        cmd = [NVCC, *ARCH, "-shared", "-o", OUT, *objs, "-lcudart"]
+    if jobs or force or not os.path.exists(out):
+        cmd = [NVCC, *ARCH, "-shared", "-o", out, *objs, "-lcudart"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

@@ -10,7 +10,8 @@ import numpy as np
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvivsim_b200.so")
+# VIVSIM_B200_LIB selects a tuning variant of the same library (scripts/tune_variants.py); there is no other backend
+LIB_PATH = os.environ.get("VIVSIM_B200_LIB") or os.path.join(HERE, "libvivsim_b200.so")
 
 OK = 0
 COLL = {"bgk": 0, "mrt": 1, "kbc": 2, "reg": 3}

@@ -8,6 +8,7 @@
 // missing element comes from the neighbouring lane by warp shuffle; only lanes at a warp or row
 // edge issue one extra scalar load (which also performs the periodic wrap).  Shifts along the
 // other axes only change the row that is read, so every access stays aligned and coalesced.
+#include <cstdlib>
 #include <algorithm>
 #include <cmath>
 
@@ -42,13 +43,29 @@ __device__ __forceinline__ void store_vec(float* __restrict__ p, const float (&v
 template <int DIM, int COLL>
 __device__ __forceinline__ void edge_block(const StepParams<DIM>& p, const MrtMats<DIM, is_mrt(COLL)>& mm);
 
-// register budget: 128 (2 CTAs / SM) in 3-D; in 2-D 64 (4 CTAs) for BGK / regularised, 85 (3 CTAs) for KBC / MRT
-template <int DIM, int COLL> constexpr int step_min_ctas() {
-  return DIM == 3 ? 2 : ((COLL == VSB_COLL_KBC || is_mrt(COLL)) ? 3 : 4);
+// Block size and register budget per lattice and collision model, measured on B200 (scripts/tune_variants.py,
+// profiles/r01_summary.md section 4):
+//   D3Q19: 128 registers either way; BGK / KBC / regularised run best as 4 CTAs of 128 threads with 2 cells per thread,
+//          MRT as 2 CTAs of 256 threads with 4 cells per thread.
+//   D2Q9:  256 threads, 4 cells per thread; 64 registers (4 CTAs) for BGK / regularised, 80 (3 CTAs) for KBC / MRT.
+// VSB_STEP3D_THREADS / VSB_STEP3D_CTAS override the D3Q19 choice for the tuning builds.
+template <int DIM, int COLL> constexpr int step_max_threads() {
+#ifdef VSB_STEP3D_THREADS
+  return DIM == 3 ? VSB_STEP3D_THREADS : 256;
+#else
+  return (DIM == 3 && !is_mrt(COLL)) ? 128 : 256;
+#endif
 }
+template <int DIM, int COLL> constexpr int step_min_ctas() {
+#ifdef VSB_STEP3D_CTAS
+  if (DIM == 3) return VSB_STEP3D_CTAS;
+#endif
+  return DIM == 3 ? (is_mrt(COLL) ? 2 : 4) : ((COLL == VSB_COLL_KBC || is_mrt(COLL)) ? 3 : 4);
+}
+template <int DIM, int COLL> constexpr int step_default_vec() { return (DIM == 3 && !is_mrt(COLL)) ? 2 : 4; }
 
 template <int DIM, int COLL, int VEC>
-__global__ void __launch_bounds__(256, step_min_ctas<DIM, COLL>()) k_step(const StepParams<DIM> p, const MrtMats<DIM, is_mrt(COLL)> mm) {
+__global__ void __launch_bounds__(step_max_threads<DIM, COLL>(), step_min_ctas<DIM, COLL>()) k_step(const StepParams<DIM> p, const MrtMats<DIM, is_mrt(COLL)> mm) {
   using L = Lat<DIM>;
   constexpr int Q = L::Q;
   if (blockIdx.x >= p.nb_bulk) {   // blocks appended after the bulk: wall layers of the face operations (edges = 2)
@@ -108,6 +125,18 @@ __global__ void __launch_bounds__(256, step_min_ctas<DIM, COLL>()) k_step(const 
       constexpr int q = decltype(qc)::value;
       return own + q * ncell + (d0[1 - L::c(q, 0)] + d1[1 - L::c(q, 1)]);
     };
+    if (p.prefetch_blocks > 0) {
+      // The block that will follow this one on the SM is about one resident grid ahead; its cells lie (nearly always)
+      // at the same relative offsets.  Asking L2 for them now turns its DRAM latency into L2 latency.
+      const unsigned ahead = (unsigned)p.prefetch_blocks * blockDim.x;
+      if (gid + ahead < total) {
+        const float* __restrict__ nxt = own + (long long)ahead * VEC;
+        static_for<Q>([&](auto qc) {
+          constexpr int q = decltype(qc)::value;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + q * ncell + (d0[1 - L::c(q, 0)] + d1[1 - L::c(q, 1)])));
+        });
+      }
+    }
     if constexpr (VEC == 1) {
       static_for<Q>([&](auto qc) {
         constexpr int q = decltype(qc)::value;
@@ -404,6 +433,7 @@ int fill_params(const VsbStepArgs& a, StepParams<DIM>& p) {
   VSB_REQUIRE(a.band == 0 || a.win_size[0] > 0, "vsb_step: band mode needs a force window");
   p.band = a.band;
   p.n_skip = 0;
+  p.prefetch_blocks = 0;
   p.n_wall = 0;
   p.nb_bulk = 0xffffffffu;
   p.wall_blocks0 = 0;
@@ -567,9 +597,7 @@ static int step_impl(const VsbStepArgs& a, cudaStream_t s) {
     }
   }
   int vec = a.vec;
-  // measured on B200 (scripts/vec_sweep.py, profiles/r01_summary.md section 4): D2Q9 is fastest with 4 cells per
-  // thread (128-bit accesses); D3Q19 with 2 (64-bit accesses, 38 instead of 76 population registers per thread)
-  if (vec == 0) vec = (DIM == 3) ? 2 : 4;
+  if (vec == 0) vec = step_default_vec<DIM, COLL>();
   while (vec > 1 && (p.n2 % vec != 0 || ((uintptr_t)a.f_in % (4 * vec)) || ((uintptr_t)a.f_out % (4 * vec)))) vec >>= 1;
   VSB_REQUIRE(vec == 1 || vec == 2 || vec == 4, "vsb_step: vec must be 0, 1, 2 or 4");
   const int nrow = p.edge_rows ? 2 : ((p.band == 2) ? std::min(p.wsz[0], p.s_end - p.s_begin) : p.s_end - p.s_begin);
@@ -592,19 +620,27 @@ static int step_impl(const VsbStepArgs& a, cudaStream_t s) {
       if (regs <= 0) regs = 128;
       if (n_sm <= 0) n_sm = 148;
     }
-    int best_bs = 256;
+    constexpr int max_bs = step_max_threads<DIM, COLL>();
+    int best_bs = max_bs;
     double best = -1.0;
-    for (int bs = 256; bs >= 128; bs -= 32) {
+    for (int bs = max_bs; bs >= max_bs / 2; bs -= 32) {
       const long long nb = (total + bs - 1) / bs;
       const int warps = bs / 32;
       const int per_sm = std::max(1, std::min(std::min(65536 / (((regs + 7) / 8 * 8) * 32) / warps, 2048 / bs), 32));
       const double waves = (double)nb / ((double)per_sm * n_sm);
       const double fill = waves / std::ceil(waves);                       // how full the average wave is
       const double occ = std::min(1.0, per_sm * bs / 768.0);              // mild preference for >= 768 threads / SM
-      const double score = fill * (0.9 + 0.1 * occ) + (bs == 256 ? 1e-3 : 0.0);
+      const double score = fill * (0.9 + 0.1 * occ) + (bs == max_bs ? 1e-3 : 0.0);
       if (score > best) { best = score; best_bs = bs; }
     }
     p.nb_bulk = blocks_for(total, best_bs);
+    {
+      // L2 prefetch distance: about 5.5 MB of populations ahead of the block (measured optimum on B200 for both
+      // lattices, scripts/prefetch_sweep.py; beyond ~2x that the lines are evicted again before use)
+      static const double pf_bytes = [] { const char* e = getenv("VSB_PREFETCH_KB"); return (e ? atof(e) : 5632.0) * 1024.0; }();
+      const double block_bytes = (double)best_bs * vec * Lat<DIM>::Q * 4.0;
+      p.prefetch_blocks = pf_bytes > 0 ? std::max(1, (int)(pf_bytes / block_bytes + 0.5)) : 0;
+    }
     unsigned extra = 0;
     for (int e = 0; e < p.n_wall; ++e) {
       const int n[3] = {p.n0, p.n1, p.n2};

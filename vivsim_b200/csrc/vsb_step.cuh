@@ -64,6 +64,7 @@ template <int DIM> struct StepParams {
   unsigned nb_bulk, wall_blocks0;
   WallOpDev wall[2];
   FastDiv div_nv, div_n1;   // thread index -> (row, vector column), row -> (i0, i1)
+  int prefetch_blocks;      // > 0: pull the lines of the block that many blocks ahead into L2
 };
 
 // MRT operators: collision A and Guo source B (lbm/collision/mrt.py:88, lbm/forcing/guo.py:60-75) as dense matrices
