@@ -87,6 +87,42 @@ int vsb_post_op(const VsbGrid* grid, const VsbPostOp* op, const float* f_pre, fl
 int vsb_boundary_characteristic(const VsbGrid* grid, int loc, const float* rho, const float* u, float* rho_out,
                                 float* u_out, vsb_stream_t stream);
 
+/* ---- field diagnostics and grid-refinement transfers ------------ */
+
+/* One diagnostic of reference vivsim/post.py per kind.  Gradients are jnp.gradient's: central differences inside,
+ * one-sided at the array edges, unit spacing (post.py:17-29); every axis then needs >= 2 cells. */
+enum {
+  VSB_DIAG_VELOCITY_MAGNITUDE = 0,    /* post.py:6-14      u (dim, S) -> (S)                  */
+  VSB_DIAG_VELOCITY_GRADIENT = 1,     /* post.py:17-29     -> (dim, dim, S), [i][j] = du_i/dx_j */
+  VSB_DIAG_VORTICITY = 2,             /* post.py:32-55     -> (S) in 2-D, (3, S) in 3-D       */
+  VSB_DIAG_VORTICITY_MAGNITUDE = 3,   /* post.py:58-66                                        */
+  VSB_DIAG_DIVERGENCE = 4,            /* post.py:70-80                                        */
+  VSB_DIAG_STRAIN_RATE = 5,           /* post.py:83-92     -> (dim, dim, S)                   */
+  VSB_DIAG_STRAIN_RATE_MAGNITUDE = 6, /* post.py:95-103                                       */
+  VSB_DIAG_KINETIC_ENERGY = 7,        /* post.py:106-114                                      */
+  VSB_DIAG_PRESSURE = 8,              /* post.py:129-139   in = rho (S), param = cs2          */
+  VSB_DIAG_ENSTROPHY = 9,             /* post.py:142-152                                      */
+  VSB_DIAG_Q_CRITERION = 10           /* post.py:163-177                                      */
+};
+/* in: u (dim, S) (rho (S) for VSB_DIAG_PRESSURE); out: shape per kind above.  One pass, no temporaries. */
+int vsb_post_field(const VsbGrid* grid, int kind, const float* in, float param, float* out, vsb_stream_t stream);
+/* Domain mean of a scalar diagnostic without materialising it: mean_kinetic_energy (post.py:117-126),
+ * mean_enstrophy (post.py:155-160).  workspace: one device double (cleared by the call); out: one device float. */
+int vsb_post_mean(const VsbGrid* grid, int kind, const float* in, float param, double* workspace, float* out,
+                  vsb_stream_t stream);
+
+/* Grid-refinement transfers between D2Q9 blocks whose spacing differs by 2 (reference vivsim/multigrid.py).
+ * dir names the side on which the populations travel: left (3,7,6), right (1,5,8), up (2,5,6), down (4,7,8). */
+enum { VSB_MG_LEFT = 0, VSB_MG_RIGHT = 1, VSB_MG_UP = 2, VSB_MG_DOWN = 3 };
+/* fine_to_coarse: multigrid.py:58-101.  IN PLACE on f_coarse (9, nx_c, ny_c): its receiving edge line <- mean of
+ * the 2 x 2 fine cells of the two outermost fine layers.  Needs ny_f = 2 ny_c (left/right) or nx_f = 2 nx_c. */
+int vsb_mg_fine_to_coarse(int nx_f, int ny_f, const float* f_fine, int nx_c, int ny_c, float* f_coarse, int dir,
+                          vsb_stream_t stream);
+/* coarse_to_fine: multigrid.py:103-131.  IN PLACE on f_fine (9, nx_f, ny_f): piecewise-constant copy of the coarse
+ * edge line into the fine receiving line. */
+int vsb_mg_coarse_to_fine(int nx_c, int ny_c, const float* f_coarse, int nx_f, int ny_f, float* f_fine, int dir,
+                          vsb_stream_t stream);
+
 /* ---- immersed boundary (reference vivsim/ib, vivsim/ib3d) ------------------------------ */
 
 /* kernel_peskin_3pt / _4pt / kernel_cosine_4pt: ib/kernels.py:4-61 (+ 2-point hat, not in the reference). */

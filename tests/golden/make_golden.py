@@ -426,12 +426,75 @@ def recipes_fixture():
     save("recipes", out)
 
 
+# ---------------------------------------------------------------- post.py diagnostics
+def post_fixture():
+    from vivsim import post
+    out = {}
+    rng = np.random.default_rng(21)
+    for tag, shape in (("2d", (13, 10)), ("2d_thin", (2, 9)), ("3d", (7, 6, 5)), ("3d_thin", (2, 2, 3))):
+        dim = len(shape)
+        # smooth part + noise so that gradients are neither trivial nor pure noise
+        grids = np.meshgrid(*[np.arange(n) for n in shape], indexing="ij")
+        u = np.stack([0.05 * np.sin(0.7 * grids[d] + 0.3 * grids[(d + 1) % dim] + d) for d in range(dim)])
+        u = (u + 0.01 * rng.standard_normal(u.shape)).astype(F32)
+        rho = (1 + 0.02 * rng.standard_normal(shape)).astype(F32)
+        out[f"{tag}_u"], out[f"{tag}_rho"] = u, rho
+        for name in ("velocity_magnitude", "velocity_gradient", "vorticity", "vorticity_magnitude", "divergence",
+                     "strain_rate", "strain_rate_magnitude", "kinetic_energy", "mean_kinetic_energy", "enstrophy",
+                     "mean_enstrophy", "q_criterion", "calculate_curl", "calculate_vorticity",
+                     "calculate_velocity_magnitude"):
+            out[f"{tag}_{name}"] = getattr(post, name)(J(u))
+        out[f"{tag}_pressure"] = post.pressure(J(rho))
+        out[f"{tag}_pressure_cs2"] = post.pressure(J(rho), 0.25)
+        out[f"{tag}_vorticity_dimensionless"] = post.calculate_vorticity_dimensionless(J(u), 20.0, 0.05)
+    save("post", out)
+
+
+# ---------------------------------------------------------------- multigrid.py transfers
+def multigrid_fixture():
+    from vivsim import multigrid
+    out = {}
+    rng = np.random.default_rng(22)
+    # left/right: the edge line runs along y (fine ny = 2 coarse ny); up/down: along x
+    for tag, fine_shape, coarse_shape in (("lr", (5, 12), (4, 6)), ("ud", (14, 6), (7, 3)), ("lr_min", (2, 2), (1, 1)),
+                                          ("ud_min", (2, 2), (1, 1))):
+        ff = rng.standard_normal((9,) + fine_shape).astype(F32)
+        fc = rng.standard_normal((9,) + coarse_shape).astype(F32)
+        out[f"{tag}_fine"], out[f"{tag}_coarse"] = ff, fc
+        for d in (("left", "right") if tag.startswith("lr") else ("up", "down")):
+            out[f"{tag}_f2c_{d}"] = multigrid.fine_to_coarse(J(ff), J(fc), d)
+            out[f"{tag}_c2f_{d}"] = multigrid.coarse_to_fine(J(fc), J(ff), d)
+        out[f"{tag}_f2c_other"] = multigrid.fine_to_coarse(J(ff), J(fc), "top")     # unknown dir: unchanged
+    out["omega"] = np.array([[nu, lv, multigrid.get_omega(nu, lv)] for nu in (0.01, 0.1) for lv in (-1, 0, 1, 2)])
+    out["coord"] = np.array([multigrid.coord_to_indices(13.5, 7.25, 4, 2, lv) for lv in (-1, 0, 1, 2)])
+    for i, (w, h, lv, bx, by) in enumerate(((8, 6, 0, 0, 0), (8, 6, 1, 2, 0), (8, 6, -1, 0, 1))):
+        f, rho, u = multigrid.init_grid(w, h, lv, bx, by)
+        out[f"init{i}_args"] = np.array([w, h, lv, bx, by])
+        out[f"init{i}_shapes"] = np.array(A(f).shape + A(rho).shape + A(u).shape)
+        out[f"init{i}_sums"] = np.array([A(f).sum(), A(rho).mean(), A(u).sum()])
+    save("multigrid", out)
+
+
 if __name__ == "__main__":
     sys.path.insert(0, ROOT)
     np.seterr(invalid="ignore")
-    lattice_fixture()
-    ops_fixture("ops2d", lbm, (12, 8), ("left", "right", "top", "bottom"), seed=1)
-    ops_fixture("ops3d", lbm3d, (7, 6, 5), ("left", "right", "bottom", "top", "back", "front"), seed=2)
-    ib_fixture()
-    dyn_fixture()
-    recipes_fixture()
+    which = sys.argv[1:]   # e.g. `make_golden.py post multigrid` regenerates only those files
+
+    def want(name):
+        return not which or name in which
+    if want("lattice"):
+        lattice_fixture()
+    if want("ops2d"):
+        ops_fixture("ops2d", lbm, (12, 8), ("left", "right", "top", "bottom"), seed=1)
+    if want("ops3d"):
+        ops_fixture("ops3d", lbm3d, (7, 6, 5), ("left", "right", "bottom", "top", "back", "front"), seed=2)
+    if want("ib"):
+        ib_fixture()
+    if want("dyn"):
+        dyn_fixture()
+    if want("recipes"):
+        recipes_fixture()
+    if want("post"):
+        post_fixture()
+    if want("multigrid"):
+        multigrid_fixture()

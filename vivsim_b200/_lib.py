@@ -20,6 +20,10 @@ BC = {"nee": 0, "nebb": 1, "equilibrium": 2, "bounce_back": 3, "specular_reflect
 WRAP = {"": 0, "velocity": 1, "pressure": 2, "force_corrected": 3}
 LOC = {"left": 0, "right": 1, "bottom": 2, "top": 3, "back": 4, "front": 5}
 DELTA = {"peskin3": 0, "peskin4": 1, "cosine4": 2, "hat2": 3}
+DIAG = {"velocity_magnitude": 0, "velocity_gradient": 1, "vorticity": 2, "vorticity_magnitude": 3, "divergence": 4,
+        "strain_rate": 5, "strain_rate_magnitude": 6, "kinetic_energy": 7, "pressure": 8, "enstrophy": 9,
+        "q_criterion": 10}
+MG_DIR = {"left": 0, "right": 1, "up": 2, "down": 3}
 
 EXPORTS = [
     "vsb_abi_version", "vsb_last_error", "vsb_streaming", "vsb_macroscopic", "vsb_equilibrium", "vsb_collision",
@@ -27,6 +31,7 @@ EXPORTS = [
     "vsb_ib_stencil", "vsb_ib_interpolate", "vsb_ib_spread", "vsb_ib_mdf", "vsb_step", "vsb_ib_window_moments",
     "vsb_body_newmark", "vsb_edge_fused", "vsb_edge_fused_supported", "vsb_ib_fused", "vsb_ib_fused_supported",
     "vsb_halo_push", "vsb_body_newmark_host", "vsb_halo_send", "vsb_halo_wait", "vsb_step_host_ode",
+    "vsb_post_field", "vsb_post_mean", "vsb_mg_fine_to_coarse", "vsb_mg_coarse_to_fine",
 ]
 
 
