@@ -149,6 +149,7 @@ typedef struct {
   float force_sum[3];     /* accumulator: sum over markers of +F; cleared by the body update             */
   int origin2[2][3];      /* integer IB-window origin for step parity 0 / 1                               */
   int ticket;             /* CTA arrival counter of the last MDF stage (0 between steps)                  */
+  int step;               /* number of body updates performed so far (index of the next history row)     */
 } VsbBodyState;
 
 /* Structural parameters and window rule of a translating rigid body (reference dyn.py:5-51 with gamma = 1/2,
@@ -160,6 +161,11 @@ typedef struct {
   float origin0[3];       /* window origin for d = 0                                                       */
   int grid_size[3], win_size[3];
   double m, k, c, added_mass;
+  float* history;         /* optional ring of `history_capacity` rows of 6 floats: after the update of step n, row
+                             (n mod capacity) <- d[0..2], h[0..2] -- the per-step (d, h) record the reference's
+                             update_chunk returns (examples/2d/vortex_induced_vibration.py:150-157).  DEVICE memory for
+                             the device update, HOST memory for vsb_body_newmark_host / vsb_step_host_ode             */
+  int history_capacity;
 } VsbBodyParams;
 
 /* multi_direct_forcing with the stencil computed on the fly (ib/mdf.py:10-64 + ib/stencil.py:27-51 /

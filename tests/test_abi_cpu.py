@@ -38,7 +38,7 @@ def test_header_symbols_exported(lib):
 
 def test_struct_layouts_match_header(lib):
     from vivsim_b200 import _lib
-    assert ctypes.sizeof(_lib.VsbBodyState) == 88
+    assert ctypes.sizeof(_lib.VsbBodyState) == 92
     assert ctypes.sizeof(_lib.VsbGrid) == 16
     assert ctypes.sizeof(_lib.VsbWallValue) == 16
 

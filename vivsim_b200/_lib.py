@@ -50,16 +50,17 @@ class VsbPostOp(C.Structure):
 
 class VsbBodyState(C.Structure):
     _fields_ = [("d", C.c_float * 3), ("v", C.c_float * 3), ("a", C.c_float * 3), ("h", C.c_float * 3),
-                ("force_sum", C.c_float * 3), ("origin2", (C.c_int * 3) * 2), ("ticket", C.c_int)]
+                ("force_sum", C.c_float * 3), ("origin2", (C.c_int * 3) * 2), ("ticket", C.c_int),
+                ("step", C.c_int)]
 
 
-BODY_BYTES = C.sizeof(VsbBodyState)   # 15 fp32 + 7 int32 = 88 bytes
+BODY_BYTES = C.sizeof(VsbBodyState)   # 15 fp32 + 8 int32 = 92 bytes
 
 
 class VsbBodyParams(C.Structure):
     _fields_ = [("n_dof", C.c_int), ("follow", C.c_int), ("origin0", C.c_float * 3), ("grid_size", C.c_int * 3),
                 ("win_size", C.c_int * 3), ("m", C.c_double), ("k", C.c_double), ("c", C.c_double),
-                ("added_mass", C.c_double)]
+                ("added_mass", C.c_double), ("history", C.c_void_p), ("history_capacity", C.c_int)]
 
 
 class VsbMdfArgs(C.Structure):

@@ -402,6 +402,11 @@ int vsb_body_newmark_host(VsbBodyState* body, VsbBodyState* pinned, const VsbBod
   const int dim = bp->grid_size[2] <= 1 ? 2 : 3;
   for (int d = 0; d < dim; ++d)
     pinned->origin2[(parity & 1) ^ 1][d] = origin_rule(bp->follow, bp->origin0[d], pinned->d[d], bp->grid_size[d], bp->win_size[d]);
+  if (bp->history && bp->history_capacity > 0) {   // HOST ring in this mode
+    float* row = bp->history + 6 * (pinned->step % bp->history_capacity);
+    for (int i = 0; i < 3; ++i) { row[i] = pinned->d[i]; row[3 + i] = pinned->h[i]; }
+  }
+  pinned->step += 1;
   e = cudaMemcpyAsync(body, pinned, sizeof(VsbBodyState), cudaMemcpyHostToDevice, s);
   if (e != cudaSuccess) return cuda_fail(e, "vsb_body_newmark_host (host -> device)");
   return VSB_OK;

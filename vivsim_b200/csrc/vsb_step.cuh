@@ -115,6 +115,8 @@ struct BodyUpdate {
   float origin0[3];
   int grid_size[3], win_size[3];
   float denom, k, c, added_mass;   // denom = m + c/2 + k/4 evaluated in double on the host
+  float* history;                  // optional (capacity, 6) ring of (d, h) per step
+  int history_capacity;
 };
 
 inline BodyUpdate make_body_update(const VsbBodyParams& bp, int dim) {
@@ -123,6 +125,8 @@ inline BodyUpdate make_body_update(const VsbBodyParams& bp, int dim) {
   for (int d = 0; d < 3; ++d) { u.origin0[d] = bp.origin0[d]; u.grid_size[d] = bp.grid_size[d]; u.win_size[d] = bp.win_size[d]; }
   u.denom = (float)(bp.m + 0.5 * bp.c + 0.25 * bp.k);
   u.k = (float)bp.k; u.c = (float)bp.c; u.added_mass = (float)bp.added_mass;
+  u.history = bp.history_capacity > 0 ? bp.history : nullptr;
+  u.history_capacity = bp.history_capacity;
   return u;
 }
 
@@ -140,6 +144,11 @@ __device__ __forceinline__ void body_update(VsbBodyState* b, const BodyUpdate& u
   for (int i = 0; i < 3; ++i) b->force_sum[i] = 0.f;
   for (int d = 0; d < u.dim; ++d)
     b->origin2[parity ^ 1][d] = origin_rule(u.follow, u.origin0[d], b->d[d], u.grid_size[d], u.win_size[d]);
+  if (u.history) {   // per-step record of (d, h), like the scan outputs of the reference's update_chunk
+    float* row = u.history + 6 * (b->step % u.history_capacity);
+    for (int i = 0; i < 3; ++i) { row[i] = b->d[i]; row[3 + i] = b->h[i]; }
+  }
+  b->step += 1;
 }
 
 // Streamed (pulled) and masked populations of one cell; scalar loads.  With do_stream = 0 the cell itself.

@@ -70,6 +70,7 @@ class Stepper:
                 if tuple(b.shape) != (self.q,) + self.shape or b.dtype != torch.float32 or not b.is_cuda or not b.is_contiguous():
                     raise ValueError("buffers must be two contiguous fp32 CUDA tensors of shape (Q, *shape)")
         self._cur = 0
+        self.n_steps = 0           # reference time steps taken since set_f / restore
         self._kind = None          # 'F' (reference state) or 'S' (post-collision state)
         self._tmp = None
         self._graph = None
@@ -116,6 +117,7 @@ class Stepper:
         self.ib = spec.get("ib")
         self.body = None
         self._body_dev = None
+        self._hist = None
         if self.ib is not None:
             if not a.forcing:
                 raise ValueError("an immersed boundary needs forcing='edm' or 'guo'")
@@ -240,6 +242,16 @@ class Stepper:
                 bp.grid_size[d] = self.shape[d] if d < dim else 1
                 bp.win_size[d] = self.win_size[d] if d < dim else 1
             self._bparams = bp
+            # optional per-step record of (d, h) (what the reference's update_chunk scan returns): a ring written by
+            # the body update itself -- device memory for the device ODE, page-locked host memory for the host ODE
+            self._hist_cap = int(body.get("history", 0))
+            self._hist = None
+            if self._hist_cap > 0:
+                if dyn_mode == "device":
+                    self._hist = torch.zeros((self._hist_cap, 6), device=dev, dtype=torch.float32)
+                else:
+                    self._hist = torch.zeros((self._hist_cap, 6), dtype=torch.float32).pin_memory()
+                bp.history, bp.history_capacity = self._hist.data_ptr(), self._hist_cap
             hp = L.VsbBodyParams.from_buffer_copy(bp)      # host-ODE variant: same numbers, n_dof always set
             hp.n_dof = self.n_dof
             self._hparams = hp
@@ -311,6 +323,7 @@ class Stepper:
             raise ValueError(f"f must have shape {(self.q,) + self.shape}, got {tuple(f.shape)}")
         self._bufs[self._cur].copy_(f.to(torch.float32))
         self._kind = "F"
+        self.n_steps = 0
         return self
 
     def get_f(self):
@@ -332,6 +345,85 @@ class Stepper:
         st = self._body_dev.cpu().numpy()
         n = self.n_dof
         return st[0:n].copy(), st[3:3 + n].copy(), st[6:6 + n].copy(), st[9:9 + n].copy()
+
+    def body_steps(self):
+        """Number of body updates performed so far (synchronises)."""
+        return int(self._body_dev.cpu().numpy().view(np.int32)[22])
+
+    def body_history(self, n=None):
+        """(d, h) of the last n steps, each of shape (n, n_dof), oldest first -- the per-step record the reference's
+        update_chunk returns (examples/2d/vortex_induced_vibration.py:150-157).  Needs body['history'] = capacity."""
+        if self._body_dev is None or self._hist is None:
+            raise L.VsbError("no history: pass body=dict(..., history=capacity)")
+        done = self.body_steps()          # also synchronises the device-side writes
+        if self._hist.is_cuda:
+            ring = self._hist.cpu().numpy()
+        else:
+            torch.cuda.synchronize(self.device)
+            ring = self._hist.numpy().copy()
+        n = min(done, self._hist_cap) if n is None else int(n)
+        if n > min(done, self._hist_cap):
+            raise ValueError(f"only {min(done, self._hist_cap)} steps are recorded (capacity {self._hist_cap})")
+        rows = ring[[(done - n + i) % self._hist_cap for i in range(n)]]
+        return rows[:, 0:self.n_dof].copy(), rows[:, 3:3 + self.n_dof].copy()
+
+    # ------------------------------------------------------------------ dump / restore
+    def checkpoint(self):
+        """Everything needed to resume bit-identically, as a dict of NumPy arrays: the raw population buffer and its
+        convention, the step parity, the rigid-body state and the marker arrays.  (The reference's examples carry
+        (f, d, v, a) between chunks, examples/2d/vortex_induced_vibration.py:150-157,196-205.)"""
+        self._require_state()
+        torch.cuda.synchronize(self.device)
+        ck = {"populations": self._bufs[self._cur].cpu().numpy(), "kind": np.array(self._kind),
+              "parity": np.array(self._parity, dtype=np.int32), "n_steps": np.array(self.n_steps, dtype=np.int64),
+              "shape": np.array(self.shape, dtype=np.int64)}
+        if self.ib is not None:
+            ck["marker_force"] = self.marker_force.cpu().numpy()
+            ck["marker_u"] = self._marker_u.cpu().numpy()
+        if self._body_dev is not None:
+            ck["body"] = self._body_dev.cpu().numpy().view(np.uint8).copy()
+            if self._hist is not None:
+                ck["history"] = self._hist.cpu().numpy()
+        return ck
+
+    def restore(self, ck):
+        """Load a checkpoint() into a Stepper built from the same spec."""
+        if tuple(int(n) for n in ck["shape"]) != self.shape or ck["populations"].shape[0] != self.q:
+            raise ValueError(f"checkpoint is for a {tuple(ck['shape'])} grid, this stepper is {self.shape}")
+        if (self._body_dev is not None) != ("body" in ck) or (self.ib is not None) != ("marker_force" in ck):
+            raise ValueError("checkpoint and stepper disagree about the immersed body")
+        self._bufs[self._cur].copy_(torch.as_tensor(np.ascontiguousarray(ck["populations"])))
+        self._kind = str(ck["kind"])
+        self.n_steps = int(ck["n_steps"])
+        if self.ib is not None:
+            self._parity = int(ck["parity"])
+            self.marker_force.copy_(torch.as_tensor(ck["marker_force"]))
+            self._marker_u.copy_(torch.as_tensor(ck["marker_u"]))
+            # between steps the set the next step accumulates into is zero and the other one is cleared by the next
+            # step before it is used again, so starting from all-zero work fields is equivalent
+            self._ib_buf.zero_()
+        if self._body_dev is not None:
+            raw = np.ascontiguousarray(ck["body"]).view(np.float32)
+            if raw.size != self._body_dev.numel():
+                raise ValueError("checkpoint holds a body state of another ABI version")
+            self._body_dev.copy_(torch.as_tensor(raw))
+            if self._hist is not None and "history" in ck and ck["history"].shape == tuple(self._hist.shape):
+                self._hist.copy_(torch.as_tensor(ck["history"]))
+        torch.cuda.synchronize(self.device)
+        return self
+
+    def save(self, path):
+        """checkpoint() to an .npz file."""
+        np.savez(path, **self.checkpoint())
+
+    def load(self, path):
+        """restore() from a file written by save()."""
+        with np.load(path) as z:
+            return self.restore({k: z[k] for k in z.files})
+
+    def macroscopic(self):
+        """(rho, u) of the reference-convention state F_n (two passes: epilogue, moments)."""
+        return _api.get_macroscopic(self.dim, self.get_f())
 
     def window_origin(self):
         """Integer IB-window origin that the next step will use."""
@@ -450,7 +542,7 @@ class Stepper:
                 m.u_win = self._u_win.data_ptr()
             L.check(lib.vsb_ib_mdf(C.byref(a), C.byref(m), bp, st))
         if self.body is not None and self.dyn_mode == "host":
-            # rigid-body ODE on the host (north_star): 88 B device -> host, Newmark-beta on the CPU, 88 B back
+            # rigid-body ODE on the host (north_star): 92 B device -> host, Newmark-beta on the CPU, 92 B back
             L.check(lib.vsb_body_newmark_host(C.c_void_p(self._body_dev.data_ptr()), C.c_void_p(self._body_pin.data_ptr()),
                                               C.byref(self._hparams), par, st))
 
@@ -466,6 +558,7 @@ class Stepper:
             raise L.VsbError("advance_raw needs the internal state: call set_f(f) and step(1) first")
         for _ in range(int(n)):
             self._advance()
+        self.n_steps += int(n)
         return self
 
     def step(self, n=1):
@@ -474,6 +567,7 @@ class Stepper:
         n = int(n)
         if n <= 0:
             return self
+        self.n_steps += n
         if self._kind == "F":   # prologue: S_0 = collide(F_0)
             src, dst = self._bufs[self._cur], self._bufs[1 - self._cur]
             self._launch(src, dst, do_stream=0, do_collide=1)
