@@ -311,7 +311,7 @@ def run_ours(args):
     ke = max(10, min(K, 3000))
     if world == 1:
         # host-side rigid-body ODE as north_star prescribes: every step one device->host read of the body force and
-        # one host->device write of the kinematics (88 B each way, synchronous)
+        # one host->device write of the kinematics (16-byte mailbox up, 92-byte body state down, every step)
         st = Stepper(spec, body=dict(body), dyn_mode="host")
         st.set_f(f_host); st.step(5); st.get_f()
         torch.cuda.synchronize()
@@ -322,8 +322,10 @@ def run_ours(args):
         torch.cuda.synchronize()
         te = time.perf_counter() - t0
         per_step_io = _lib.BODY_BYTES
-        e2e_note = ("pinned f -> device once, per step: device->host read of the body force + host Newmark + "
-                    "host->device kinematics (88 B each way, synchronous), f -> host once; single L2-resident domain")
+        per_step_up = 16                      # VsbHostMail: force[3] + seq written by the device into pinned host memory
+        e2e_note = ("pinned f -> device once; per step the device posts the body force into a 16-byte host mailbox, the "
+                    "host polls it, advances the Newmark ODE on the CPU and sends the 92-byte body state back "
+                    "(vsb_run_host_ode, every step, inside the timed region); f -> host once; single L2-resident domain")
         del st
         # for context: the same chunk with the ODE on the device (what the reference does inside its jitted scan):
         # host transfers only at the chunk boundaries
@@ -356,11 +358,12 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         te = float(t)
         per_step_io = 0
+        per_step_up = 0
         e2e_note = ("per rank: pinned slab -> device once, steps with NCCL halo exchange and the body ODE on the device, "
                     "slab -> host once; max over ranks")
     assert bool(torch.isfinite(f_back).all())
     e2e = {"value": cells * ke * world / te / 1e6, "unit": "MLUPS", "steps": ke,
-           "h2d_bytes_per_step": state_bytes / ke + per_step_io, "d2h_bytes_per_step": state_bytes / ke + per_step_io,
+           "h2d_bytes_per_step": state_bytes / ke + per_step_io, "d2h_bytes_per_step": state_bytes / ke + per_step_up,
            "note": e2e_note}
     if world == 1:
         e2e["chunked_device_ode"] = e2e_device_ode

@@ -168,6 +168,13 @@ typedef struct {
   int history_capacity;
 } VsbBodyParams;
 
+/* Mailbox in page-locked host memory (reachable from the device under unified addressing). */
+typedef struct VsbHostMail {
+  float force[3];   /* sum over markers of +F for the step `seq`                               */
+  int seq;          /* written last by the device                                              */
+  int next;         /* host side only: sequence number the next step will use (monotonic)     */
+} VsbHostMail;
+
 /* multi_direct_forcing with the stencil computed on the fly (ib/mdf.py:10-64 + ib/stencil.py:27-51 /
  * ib3d/stencil.py:36-57), marker-parallel over many CTAs, on a window of the grid: n_iter launches.
  * The velocity at the stencil points comes straight from the streamed populations of `args` (f_in, do_stream, mask),
@@ -203,6 +210,10 @@ typedef struct {
   VsbBodyState* body;
   void* barrier;   /* optional 8-byte device counter (zero-initialised once): lets small bodies (<= 120 CTAs) run all
                       iterations in one launch separated by grid barriers instead of one launch per iteration */
+  struct VsbHostMail* host_mail;   /* optional, host-ODE mode: page-locked HOST memory the last CTA of the last stage
+                      writes the total marker force to (force[0..2], then seq = mail_seq, system-scope release), so
+                      that the host can pick it up by polling instead of a copy + stream synchronisation */
+  int mail_seq;
 } VsbMdfArgs;
 
 /* ---- fused time step ------------------------------------------------------------------- *
@@ -290,6 +301,17 @@ typedef struct {
 
 int vsb_step_host_ode(VsbStepArgs* args, const VsbMdfArgs* mdf, const VsbBodyParams* params, VsbBodyState* pinned,
                       const VsbHostPlan* plan);
+
+/* n_steps whole time steps with the rigid-body ODE on the host, in ONE call: no per-step cost in the host language,
+ * no stream synchronisation and no device->host copy.  Per step: bulk rows on `main`; on `ib` the MDF chain, whose
+ * last CTA posts the total force into mdf->host_mail; the host polls the mailbox, advances (a, v, d) on the CPU
+ * (dyn.py:5-51; `pinned` is the master copy of the body state), sends the 92-byte state back with one asynchronous
+ * host->device copy and launches the window's x-range behind it.  args / mdf must be set up as for
+ * vsb_step_host_ode for the first step (f_in = current state, f_out = the other buffer, parity, g_win / scratch
+ * pairs); they are advanced in place (buffers and parity swapped every step), so after the call args->f_in is the
+ * current state.  Returns VSB_ERR_CUDA if the device does not answer within ~10 s. */
+int vsb_run_host_ode(VsbStepArgs* args, VsbMdfArgs* mdf, const VsbBodyParams* params, VsbBodyState* pinned,
+                     const VsbHostPlan* plan, int n_steps);
 
 /* ---- multi-GPU: halo exchange over peer memory ----------------------------------------- *
  * Slab decomposition along x, one ghost layer per side (local extent grid.nx = nx_local + 2).  Replaces the

@@ -31,7 +31,7 @@ EXPORTS = [
     "vsb_ib_stencil", "vsb_ib_interpolate", "vsb_ib_spread", "vsb_ib_mdf", "vsb_step", "vsb_ib_window_moments",
     "vsb_body_newmark", "vsb_edge_fused", "vsb_edge_fused_supported", "vsb_ib_fused", "vsb_ib_fused_supported",
     "vsb_halo_push", "vsb_body_newmark_host", "vsb_halo_send", "vsb_halo_wait", "vsb_step_host_ode",
-    "vsb_post_field", "vsb_post_mean", "vsb_mg_fine_to_coarse", "vsb_mg_coarse_to_fine",
+    "vsb_post_field", "vsb_post_mean", "vsb_mg_fine_to_coarse", "vsb_mg_coarse_to_fine", "vsb_run_host_ode",
 ]
 
 
@@ -54,6 +54,10 @@ class VsbBodyState(C.Structure):
                 ("step", C.c_int)]
 
 
+class VsbHostMail(C.Structure):
+    _fields_ = [("force", C.c_float * 3), ("seq", C.c_int), ("next", C.c_int)]
+
+
 BODY_BYTES = C.sizeof(VsbBodyState)   # 15 fp32 + 8 int32 = 92 bytes
 
 
@@ -70,7 +74,8 @@ class VsbMdfArgs(C.Structure):
                 ("ds_ptr", C.c_void_p), ("ds_value", C.c_float), ("u_win", C.c_void_p), ("g_win", C.c_void_p),
                 ("g_win_next", C.c_void_p),
                 ("scratch", C.c_void_p), ("scratch_next", C.c_void_p), ("marker_u", C.c_void_p),
-                ("marker_force", C.c_void_p), ("body", C.c_void_p), ("barrier", C.c_void_p)]
+                ("marker_force", C.c_void_p), ("body", C.c_void_p), ("barrier", C.c_void_p),
+                ("host_mail", C.c_void_p), ("mail_seq", C.c_int)]
 
 
 class VsbStepArgs(C.Structure):

@@ -4,6 +4,8 @@
 // with warp shuffles; spreading uses fp32 atomics (REDG) into window-sized buffers.
 #include <type_traits>
 
+#include <chrono>
+
 #include "vsb_step.cuh"
 
 namespace vsb {
@@ -84,6 +86,8 @@ struct MdfParams {
   float* marker_force;
   VsbBodyState* body;
   int update_body;
+  VsbHostMail* host_mail;   // host-ODE mode: post the total force to page-locked host memory
+  int mail_seq;
 };
 
 // Stage k of multi_direct_forcing (ib/mdf.py:31-64), one launch per iteration, markers spread over many CTAs:
@@ -255,7 +259,7 @@ __global__ void k_mdf_stage(const StepParams<DIM> sp, const MdfParams p, const B
   if (p.stage_end == p.n_iter && p.body) {
     __syncthreads();
     if (threadIdx.x < DIM) atomicAdd(&p.body->force_sum[threadIdx.x], s_force[threadIdx.x]);
-    if (p.update_body) {   // the last CTA to arrive sees every contribution and advances the body
+    if (p.update_body || p.host_mail) {   // the last CTA to arrive sees every contribution
       __shared__ int s_last;
       __syncthreads();
       if (threadIdx.x == 0) {
@@ -266,7 +270,14 @@ __global__ void k_mdf_stage(const StepParams<DIM> sp, const MdfParams p, const B
       if (s_last && threadIdx.x == 0) {
         __threadfence();
         p.body->ticket = 0;
-        body_update(p.body, bu, p.parity);
+        if (p.update_body) {
+          body_update(p.body, bu, p.parity);          // ODE on the device
+        } else {                                      // ODE on the host: post the force, the host polls for seq
+          volatile VsbHostMail* mail = p.host_mail;
+          for (int c = 0; c < 3; ++c) mail->force[c] = __ldcg(&p.body->force_sum[c]);
+          __threadfence_system();
+          mail->seq = p.mail_seq;
+        }
       }
     }
   }
@@ -291,6 +302,8 @@ static int mdf_impl(const VsbStepArgs& sa, const VsbMdfArgs& a, const VsbBodyPar
   p.u_win = a.u_win; p.g_win = a.g_win; p.g_win_next = a.g_win_next; p.scratch = a.scratch; p.scratch_next = a.scratch_next;
   p.marker_u = a.marker_u; p.marker_force = a.marker_force; p.body = a.body;
   p.update_body = (a.body && bp && bp->n_dof > 0) ? 1 : 0;
+  p.host_mail = (a.body && !p.update_body) ? a.host_mail : nullptr;
+  p.mail_seq = a.mail_seq;
   BodyUpdate bu{};
   if (p.update_body) bu = make_body_update(*bp, DIM);
   const int lanes = (DIM == 2) ? 16 : 32;
@@ -376,6 +389,9 @@ int vsb_ib_mdf(const VsbStepArgs* args, const VsbMdfArgs* a, const VsbBodyParams
   return a->dim == 2 ? mdf_impl<2>(*args, *a, params, (cudaStream_t)stream) : mdf_impl<3>(*args, *a, params, (cudaStream_t)stream);
 }
 
+// dyn.py:27-51 on the host copy of the body state (shared by the two host-ODE entry points)
+static void host_body_update(VsbBodyState* pinned, const VsbBodyParams* bp, int parity);
+
 int vsb_body_newmark_host(VsbBodyState* body, VsbBodyState* pinned, const VsbBodyParams* bp, int parity,
                           vsb_stream_t stream) {
   VSB_REQUIRE(body && pinned && bp, "vsb_body_newmark_host: null argument");
@@ -384,6 +400,13 @@ int vsb_body_newmark_host(VsbBodyState* body, VsbBodyState* pinned, const VsbBod
   cudaError_t e = cudaMemcpyAsync(pinned, body, sizeof(VsbBodyState), cudaMemcpyDeviceToHost, s);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   if (e != cudaSuccess) return cuda_fail(e, "vsb_body_newmark_host (device -> host)");
+  host_body_update(pinned, bp, parity);
+  e = cudaMemcpyAsync(body, pinned, sizeof(VsbBodyState), cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return cuda_fail(e, "vsb_body_newmark_host (host -> device)");
+  return VSB_OK;
+}
+
+static void host_body_update(VsbBodyState* pinned, const VsbBodyParams* bp, int parity) {
   // dyn.py:27-51 with gamma = 1/2, beta = 1/4, dt = 1, in fp32 like the reference's jnp arithmetic;
   // h = sum(-F) + a * added_mass (examples/2d/vortex_induced_vibration.py:135-136)
   const float denom = (float)(bp->m + 0.5 * bp->c + 0.25 * bp->k);
@@ -407,8 +430,77 @@ int vsb_body_newmark_host(VsbBodyState* body, VsbBodyState* pinned, const VsbBod
     for (int i = 0; i < 3; ++i) { row[i] = pinned->d[i]; row[3 + i] = pinned->h[i]; }
   }
   pinned->step += 1;
-  e = cudaMemcpyAsync(body, pinned, sizeof(VsbBodyState), cudaMemcpyHostToDevice, s);
-  if (e != cudaSuccess) return cuda_fail(e, "vsb_body_newmark_host (host -> device)");
+}
+
+int vsb_run_host_ode(VsbStepArgs* a, VsbMdfArgs* mdf, const VsbBodyParams* bp, VsbBodyState* pinned,
+                     const VsbHostPlan* plan, int n_steps) {
+  VSB_REQUIRE(a && mdf && bp && pinned && plan, "vsb_run_host_ode: null argument");
+  VSB_REQUIRE(mdf->body != nullptr && mdf->host_mail != nullptr, "vsb_run_host_ode: needs a body state and a host mailbox");
+  VSB_REQUIRE(bp->n_dof >= 1 && bp->n_dof <= 3, "n_dof must be 1..3, got %d", bp->n_dof);
+  VSB_REQUIRE(a->do_stream && a->do_collide, "vsb_run_host_ode: full steps only");
+  cudaStream_t main = (cudaStream_t)plan->main, ib = (cudaStream_t)plan->ib, edge = (cudaStream_t)plan->edge;
+  cudaEvent_t fork = (cudaEvent_t)plan->ev_fork, ib_done = (cudaEvent_t)plan->ev_ib, edge_done = (cudaEvent_t)plan->ev_edge;
+  VSB_REQUIRE(ib && fork && ib_done, "vsb_run_host_ode: plan needs the ib stream and the fork / ib events");
+  const int has_edges = a->edges == 1 && a->n_post > 0;
+  if (has_edges) VSB_REQUIRE(edge && edge_done, "vsb_run_host_ode: plan needs the edge stream / event");
+  VsbHostMail* mail = mdf->host_mail;
+  volatile int* seq = &mail->seq;
+  cudaError_t e;
+  int rc;
+  for (int n = 0; n < n_steps; ++n) {
+    const int par = mdf->parity & 1;
+    a->parity = par;
+    a->g_win = mdf->g_win;
+    mdf->mail_seq = mail->next;
+    if ((e = cudaEventRecord(fork, main)) != cudaSuccess) return cuda_fail(e, "vsb_run_host_ode (fork)");
+    if ((e = cudaStreamWaitEvent(ib, fork, 0)) != cudaSuccess) return cuda_fail(e, "vsb_run_host_ode (fork)");
+    if ((rc = vsb_ib_mdf(a, mdf, nullptr, ib))) return rc;        // first: the host waits for this chain
+    a->band = 1;                                                   // the bulk runs while the host advances the body
+    if ((rc = vsb_step(a, main))) return rc;
+    if (has_edges) {
+      if ((e = cudaStreamWaitEvent(edge, fork, 0)) != cudaSuccess) return cuda_fail(e, "vsb_run_host_ode (edge fork)");
+      if ((rc = vsb_edge_fused(a, edge))) return rc;
+      if ((e = cudaEventRecord(edge_done, edge)) != cudaSuccess) return cuda_fail(e, "vsb_run_host_ode (edge join)");
+    }
+    // wait for the force of this step (posted by the last CTA of the MDF chain)
+    const int want = mdf->mail_seq;
+    unsigned long long spins = 0;
+    std::chrono::steady_clock::time_point t0;
+    while (*seq != want) {
+      __builtin_ia32_pause();
+      if ((++spins & 0xffff) == 0) {             // every 64 K polls: is the device still alive, are we out of time?
+        if (spins == 0x10000) t0 = std::chrono::steady_clock::now();
+        e = cudaStreamQuery(ib);
+        if (e != cudaSuccess && e != cudaErrorNotReady) return cuda_fail(e, "vsb_run_host_ode (waiting for the IB force)");
+        if (e == cudaSuccess && *seq != want) {
+          set_error("vsb_run_host_ode: the IB chain finished without posting the force");
+          return VSB_ERR_CUDA;
+        }
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(10)) {
+          set_error("vsb_run_host_ode: timed out waiting for the IB force");
+          return VSB_ERR_CUDA;
+        }
+      }
+    }
+    mail->next = want + 1;
+    for (int c = 0; c < 3; ++c) pinned->force_sum[c] = mail->force[c];
+    host_body_update(pinned, bp, par);
+    if ((e = cudaMemcpyAsync(mdf->body, pinned, sizeof(VsbBodyState), cudaMemcpyHostToDevice, ib)) != cudaSuccess)
+      return cuda_fail(e, "vsb_run_host_ode (host -> device)");
+    a->band = 2;
+    if ((rc = vsb_step(a, ib))) return rc;
+    a->band = 0;
+    if ((e = cudaEventRecord(ib_done, ib)) != cudaSuccess) return cuda_fail(e, "vsb_run_host_ode (ib join)");
+    if ((e = cudaStreamWaitEvent(main, ib_done, 0)) != cudaSuccess) return cuda_fail(e, "vsb_run_host_ode (join)");
+    if (has_edges && (e = cudaStreamWaitEvent(main, edge_done, 0)) != cudaSuccess) return cuda_fail(e, "vsb_run_host_ode (join)");
+    // next step: swap the population buffers and the parity-double-buffered IB fields
+    const float* fi = a->f_in; a->f_in = a->f_out; a->f_out = const_cast<float*>(fi);
+    float* t = mdf->g_win; mdf->g_win = mdf->g_win_next; mdf->g_win_next = t;
+    t = mdf->scratch; mdf->scratch = mdf->scratch_next; mdf->scratch_next = t;
+    mdf->parity = par ^ 1;
+  }
+  a->parity = mdf->parity;
+  a->g_win = mdf->g_win;
   return VSB_OK;
 }
 

@@ -266,6 +266,12 @@ class Stepper:
             ints[15:18] = org
             ints[18:21] = org
             self._body_dev.copy_(self._body_pin, non_blocking=True)
+            if dyn_mode == "host":
+                # mailbox in page-locked host memory: the last CTA of the MDF chain posts the total force there and
+                # the host polls it (vsb_run_host_ode) -- no device->host copy, no stream synchronisation per step
+                self._mail = torch.zeros(8, dtype=torch.int32).pin_memory()
+                self._mail[4] = 1                      # VsbHostMail.next
+                m.host_mail = self._mail.data_ptr()
             m.body = self._body_dev.data_ptr()
             a.body = self._body_dev.data_ptr()
         self._mdf = m
@@ -407,6 +413,7 @@ class Stepper:
             if raw.size != self._body_dev.numel():
                 raise ValueError("checkpoint holds a body state of another ABI version")
             self._body_dev.copy_(torch.as_tensor(raw))
+            self._body_pin.copy_(torch.as_tensor(raw))          # the host-ODE path keeps its master copy here
             if self._hist is not None and "history" in ck and ck["history"].shape == tuple(self._hist.shape):
                 self._hist.copy_(torch.as_tensor(ck["history"]))
         torch.cuda.synchronize(self.device)
@@ -523,6 +530,44 @@ class Stepper:
         L.check(L.lib().vsb_step_host_ode(C.byref(a), C.byref(m), C.byref(self._hparams),
                                           C.c_void_p(self._body_pin.data_ptr()), C.byref(self._plan)))
 
+    def _host_ode_eligible(self):
+        a = self._args
+        return (self.overlap and self.ib is not None and self.body is not None and self.dyn_mode == "host"
+                and self.halo is None and not self.ib_fused and (a.n_post == 0 or self.edge_fused))
+
+    def _run_host_ode(self, n):
+        """n whole steps with the rigid-body ODE on the host in one C call (vsb_run_host_ode): the host loop, the
+        mailbox polling and the Newmark update all happen in C; Python only flips its buffer / parity bookkeeping."""
+        a, m = self._args, self._mdf
+        main = torch.cuda.current_stream()
+        src, dst = self._bufs[self._cur], self._bufs[1 - self._cur]
+        a.f_in, a.f_out = src.data_ptr(), dst.data_ptr()
+        a.do_stream, a.do_collide = 1, 1
+        a.edges = 2 if (a.n_post > 0 and self.edge_fused) else 0
+        a.band = 0
+        a.sub_begin, a.sub_end, a.edge_rows_only = 0, 0, 0
+        if getattr(self, "_plan", None) is None:
+            self._plan_events = [torch.cuda.Event() for _ in range(3)]
+            for ev in self._plan_events:
+                ev.record(main)                                # materialise the cudaEvent_t handles
+            self._plan = L.VsbHostPlan()
+            self._plan.ib, self._plan.edge = self._side[0].cuda_stream, self._side[1].cuda_stream
+            self._plan.ev_fork, self._plan.ev_ib, self._plan.ev_edge = (ev.cuda_event for ev in self._plan_events)
+        self._plan.main = main.cuda_stream
+        par = self._parity
+        a.parity = m.parity = par
+        buf = self._ib_buf
+        m.g_win, m.g_win_next = buf[par, 0].data_ptr(), buf[par ^ 1, 0].data_ptr()
+        if self.n_iter > 1:
+            m.scratch, m.scratch_next = buf[par, 1].data_ptr(), buf[par ^ 1, 1].data_ptr()
+        m.u_win = None
+        a.g_win = m.g_win
+        L.check(L.lib().vsb_run_host_ode(C.byref(a), C.byref(m), C.byref(self._hparams),
+                                         C.c_void_p(self._body_pin.data_ptr()), C.byref(self._plan), int(n)))
+        self._cur = (self._cur + n) % 2
+        self._parity = (par + n) % 2
+        self._g_win = self._ib_buf[self._parity, 0]
+
     def _ib_part(self, st):
         """Immersed-boundary force of this pass on stream `st`, then the body update."""
         lib, a, m = L.lib(), self._args, self._mdf
@@ -574,6 +619,9 @@ class Stepper:
             self._cur = 1 - self._cur
             self._kind = "S"
             n -= 1
+        if n > 0 and self._host_ode_eligible():
+            self._run_host_ode(n)
+            return self
         graphable = self.use_graph and not (self.body is not None and self.dyn_mode == "host")
         if graphable and n >= 2:
             if self._graph is None:
