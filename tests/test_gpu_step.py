@@ -344,3 +344,52 @@ def test_checkpoint_restore_resumes_identically(golden, tmp_path):
         assert_bitexact(N(st2.get_f()), N(full.get_f()), f"resume after {k} steps")
     with pytest.raises(ValueError):
         Stepper(dict(spec, shape=(40, 40))).restore(ck)
+
+
+def test_tiled_mdf_dense_body_3d(monkeypatch):
+    """A finely meshed 3-D surface (the C5 kind of body, scaled down) takes the shared-memory tiled MDF stages with the
+    markers stored in spatial order.  Against the oracle, against the untiled kernel, with the caller's marker order
+    preserved in the outputs, and with a shuffled marker order that forces the kernel's per-CTA fallback."""
+    from vivsim_b200 import Stepper, configs
+    spec, body = configs.oscillating_cylinder_3d(nx=48, ny=32, nz=36, diameter=8.0, moving=True)
+    spec["ib"]["markers"] = spec["ib"]["markers"] + np.float32(0.37)      # off the lattice nodes
+    M = spec["ib"]["markers"].shape[0]
+    assert M > 1000
+    f0 = recipes.uniform_init(spec, noise=1e-3, seed=2)
+    f_ref, h_ref = recipes.run(spec, f0, 4)                                 # fixed body in the oracle
+
+    st = Stepper(spec).set_f(f0)
+    assert st._use_uwin and st._perm is not None and not st._mdf_one_launch and not st.ib_fused
+    st.step(4)
+    f_tiled, force_tiled = N(st.get_f()), N(st.marker_force)
+    assert_close(f_tiled, f_ref, what="tiled MDF: populations vs oracle")
+    assert_close(-force_tiled, h_ref, rtol=3e-5, what="tiled MDF: marker forces in the caller's order")
+
+    monkeypatch.setenv("VSB_MDF_UNTILED", "1")
+    st = Stepper(spec).set_f(f0); st.step(4)
+    assert_close(N(st.get_f()), f_tiled, what="untiled kernel agrees")
+    assert_close(N(st.marker_force), force_tiled, rtol=3e-5, what="untiled kernel: forces")
+    monkeypatch.delenv("VSB_MDF_UNTILED")
+
+    # shuffled storage order, no sorting: most chunks' bounding boxes exceed the tile -> global fallback inside the kernel
+    rng = np.random.default_rng(0)
+    shuffle = rng.permutation(M)
+    sp2 = dict(spec, ib=dict(spec["ib"], markers=spec["ib"]["markers"][shuffle], ds=np.asarray(spec["ib"]["ds"])[shuffle],
+                             sort_markers=False))
+    st = Stepper(sp2).set_f(f0); st.step(4)
+    assert st._perm is None
+    assert_close(N(st.get_f()), f_tiled, what="fallback chunks agree")
+    assert_close(N(st.marker_force), force_tiled[shuffle], rtol=3e-5, what="fallback chunks: forces")
+
+    # moving body, ODE on the device: tiled and untiled chains give the same trajectory
+    out = []
+    for untiled in (False, True):
+        if untiled:
+            monkeypatch.setenv("VSB_MDF_UNTILED", "1")
+        st = Stepper(spec, body=dict(body, history=16), dyn_mode="device", follow=2).set_f(f0)
+        st.step(10)
+        out.append((N(st.get_f()), st.body_history()))
+    monkeypatch.delenv("VSB_MDF_UNTILED")
+    assert_close(out[1][0], out[0][0], what="moving dense body: populations")
+    assert_close(out[1][1][0], out[0][1][0], rtol=1e-4, what="moving dense body: displacement history")
+    assert_close(out[1][1][1], out[0][1][1], rtol=1e-4, what="moving dense body: force history")

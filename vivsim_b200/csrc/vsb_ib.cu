@@ -5,6 +5,8 @@
 #include <type_traits>
 
 #include <chrono>
+#include <climits>
+#include <cstdlib>
 
 #include "vsb_step.cuh"
 
@@ -283,6 +285,197 @@ __global__ void k_mdf_stage(const StepParams<DIM> sp, const MdfParams p, const B
   }
 }
 
+
+// ----------------------------------------------------------------------------- tiled MDF stage (dense bodies)
+// Same arithmetic as k_mdf_stage for stages that read a window field (u_win at stage 0, scratch[k-1] after), but a
+// CTA owns a chunk of kTiledChunk CONSECUTIVE markers and privatises the part of the window they touch in shared
+// memory: the source field is staged once (coalesced), every marker gathers from it and spreads with shared-memory
+// atomics into a second tile, and the tile is flushed with one coalesced vector reduction per touched cell.  A finely
+// meshed surface puts ~20 stencil points on every window cell; this turns ~64 global reductions per marker into
+// ~8 per marker (measured on the 695 k-marker cylinder: see profiles/).  Chunks whose bounding box does not fit the
+// tile (markers not stored in a spatially coherent order) fall back to global gathers / reductions, CTA by CTA.
+constexpr int kTiledChunk = 256;      // markers per CTA = threads per CTA
+constexpr int kTileCells = 2304;      // cells per tile: 2 tiles x 2304 x 16 B = 72 KB -> 3 CTAs per SM
+
+template <int DIM>
+__global__ void __launch_bounds__(kTiledChunk) k_mdf_stage_tiled(const MdfParams p, const BodyUpdate bu) {
+  static_assert(DIM == 3, "the tiled stage is instantiated for D3Q19 bodies only");
+  constexpr int NS = 64, G = 32, PPL = NS / G, NC = 4;
+  extern __shared__ float4 s_tiles[];            // [0, kTileCells): source tile, [kTileCells, 2 kTileCells): accumulator
+  float4* s_src = s_tiles;
+  float* s_acc = reinterpret_cast<float*>(s_tiles + kTileCells);
+  __shared__ int s_lo[3], s_hi[3];
+  __shared__ float s_force[3];
+  const int tid = threadIdx.x;
+  if (tid < 3) { s_lo[tid] = INT_MAX; s_hi[tid] = INT_MIN; s_force[tid] = 0.f; }
+  __syncthreads();
+
+  const long long gthread = (long long)blockIdx.x * blockDim.x + tid;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  const long long wcells = (long long)p.wsize[0] * p.wsize[1] * p.wsize[2];
+  const int stage = p.stage;
+  const bool last = stage == p.n_iter - 1;
+  int org[3] = {p.origin0[0], p.origin0[1], p.origin0[2]};
+  float disp[3] = {0.f, 0.f, 0.f};
+  if (p.body) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { org[d] = p.body->origin2[p.parity][d]; disp[d] = p.body->d[d]; }
+  }
+  // clear the other parity's buffers for the next step (as k_mdf_stage does)
+  if (stage == 0)
+    for (long long i = gthread; i < NC * wcells; i += nthreads) p.g_win_next[i] = 0.f;
+  if (stage < p.n_iter - 1) {
+    float* z = p.scratch_next + (long long)stage * NC * wcells;
+    for (long long i = gthread; i < NC * wcells; i += nthreads) z[i] = 0.f;
+  }
+
+  const long long m_begin = (long long)blockIdx.x * kTiledChunk;
+  const int n_here = (int)min((long long)kTiledChunk, p.n_markers - m_begin);
+  // bounding box of the chunk's stencils (window-local cells), clipped to the window
+  if (tid < n_here) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float x = p.markers0[(m_begin + tid) * 3 + d] + disp[d] - (float)org[d];
+      const int b = (int)floorf(x);
+      atomicMin(&s_lo[d], b - 1);
+      atomicMax(&s_hi[d], b + 2);
+    }
+  }
+  __syncthreads();
+  int lo[3], ext[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    lo[d] = max(s_lo[d], 0);
+    ext[d] = max(min(s_hi[d], p.wsize[d] - 1) - lo[d] + 1, 0);
+  }
+  const int tile_cells = ext[0] * ext[1] * ext[2];
+  const bool tiled = tile_cells > 0 && (long long)ext[0] * ext[1] * ext[2] <= kTileCells;
+
+  const float4* src = reinterpret_cast<const float4*>(stage == 0 ? p.u_win : p.scratch + (long long)(stage - 1) * NC * wcells);
+  float4* dst = reinterpret_cast<float4*>(last ? p.g_win : p.scratch + (long long)stage * NC * wcells);
+  if (tiled) {
+    for (int i = tid; i < tile_cells; i += kTiledChunk) {
+      const int tz = i % ext[2], r = i / ext[2];
+      const int ty = r % ext[1], tx = r / ext[1];
+      s_src[i] = __ldcg(src + ((long long)(lo[0] + tx) * p.wsize[1] + (lo[1] + ty)) * p.wsize[2] + (lo[2] + tz));
+    }
+    for (int i = tid; i < 4 * tile_cells; i += kTiledChunk) s_acc[i] = 0.f;
+  }
+  __syncthreads();
+
+  const int gl = tid & (G - 1);
+  for (int pass = 0; pass < kTiledChunk / (kTiledChunk / G); ++pass) {   // 8 markers per pass, 32 passes
+    const int mi = pass * (kTiledChunk / G) + tid / G;
+    const bool active = mi < n_here;                                   // warp-uniform: a warp owns one marker
+    if (!active) continue;
+    const long long m = m_begin + mi;
+    float x[3];
+    int base[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      x[d] = p.markers0[m * 3 + d] + disp[d] - (float)org[d];
+      base[d] = (int)floorf(x[d]);
+    }
+    float w[PPL];
+    int node[PPL][3];
+    bool ok[PPL];
+#pragma unroll
+    for (int j = 0; j < PPL; ++j) {
+      int sidx = gl * PPL + j;
+      float wt = 1.f;
+      bool inside = true;
+#pragma unroll
+      for (int d = 2; d >= 0; --d) {
+        node[j][d] = base[d] + (sidx & 3) - 1;
+        sidx >>= 2;
+        wt *= delta(p.delta_kind, (float)node[j][d] - x[d]);
+        inside = inside && node[j][d] >= 0 && node[j][d] < p.wsize[d];
+      }
+      w[j] = wt;
+      ok[j] = inside;
+    }
+    float um[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < PPL; ++j)
+      if (ok[j]) {
+        float4 v;
+        if (tiled) v = s_src[((node[j][0] - lo[0]) * ext[1] + (node[j][1] - lo[1])) * ext[2] + (node[j][2] - lo[2])];
+        else v = __ldcg(src + ((long long)node[j][0] * p.wsize[1] + node[j][1]) * p.wsize[2] + node[j][2]);
+        um[0] += w[j] * v.x; um[1] += w[j] * v.y; um[2] += w[j] * v.z;
+      }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) um[c] += __shfl_xor_sync(0xffffffffu, um[c], o);
+
+    const float ds2 = (p.ds_ptr ? p.ds_ptr[m] : p.ds_value) * 2.0f;
+    float spread_val[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float tgt = p.u_target ? p.u_target[m * 3 + c] : (p.body ? p.body->v[c] : 0.f);
+      const float u_prev = stage > 0 ? p.marker_u[m * 3 + c] : 0.f;
+      const float F_prev = stage > 0 ? p.marker_force[m * 3 + c] : 0.f;
+      const float u_m = (stage == 0) ? um[c] : u_prev + 0.5f * um[c];
+      const float dF = (tgt - u_m) * ds2;
+      const float F = F_prev + dF;
+      spread_val[c] = last ? F : dF;
+      if (gl == 0) { p.marker_u[m * 3 + c] = u_m; p.marker_force[m * 3 + c] = F; }
+    }
+#pragma unroll
+    for (int j = 0; j < PPL; ++j)
+      if (ok[j]) {
+        if (tiled) {
+          float* a = s_acc + 4 * (((node[j][0] - lo[0]) * ext[1] + (node[j][1] - lo[1])) * ext[2] + (node[j][2] - lo[2]));
+          atomicAdd(a + 0, spread_val[0] * w[j]);
+          atomicAdd(a + 1, spread_val[1] * w[j]);
+          atomicAdd(a + 2, spread_val[2] * w[j]);
+        } else {
+          atomicAdd(dst + ((long long)node[j][0] * p.wsize[1] + node[j][1]) * p.wsize[2] + node[j][2],
+                    make_float4(spread_val[0] * w[j], spread_val[1] * w[j], spread_val[2] * w[j], 0.f));
+        }
+      }
+    if (last && p.body && gl == 0) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) atomicAdd(&s_force[c], spread_val[c]);
+    }
+  }
+  __syncthreads();
+  if (tiled) {   // flush: one vector reduction per touched cell, rows along z are contiguous
+    for (int i = tid; i < tile_cells; i += kTiledChunk) {
+      const float4 v = reinterpret_cast<const float4*>(s_acc)[i];
+      if (v.x != 0.f || v.y != 0.f || v.z != 0.f) {
+        const int tz = i % ext[2], r = i / ext[2];
+        const int ty = r % ext[1], tx = r / ext[1];
+        atomicAdd(dst + ((long long)(lo[0] + tx) * p.wsize[1] + (lo[1] + ty)) * p.wsize[2] + (lo[2] + tz), v);
+      }
+    }
+  }
+  if (last && p.body) {
+    if (tid < 3) atomicAdd(&p.body->force_sum[tid], s_force[tid]);
+    if (p.update_body || p.host_mail) {
+      __shared__ int s_last;
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        s_last = (atomicAdd(&p.body->ticket, 1) == (int)gridDim.x - 1);
+      }
+      __syncthreads();
+      if (s_last && tid == 0) {
+        __threadfence();
+        p.body->ticket = 0;
+        if (p.update_body) {
+          body_update(p.body, bu, p.parity);
+        } else {
+          volatile VsbHostMail* mail = p.host_mail;
+          for (int c = 0; c < 3; ++c) mail->force[c] = __ldcg(&p.body->force_sum[c]);
+          __threadfence_system();
+          mail->seq = p.mail_seq;
+        }
+      }
+    }
+  }
+}
+
 // body update by one thread (see body_update in vsb_step.cuh)
 __global__ void k_body_newmark(VsbBodyState* b, BodyUpdate u, int parity) {
   if (threadIdx.x == 0 && blockIdx.x == 0) body_update(b, u, parity);
@@ -314,6 +507,22 @@ static int mdf_impl(const VsbStepArgs& sa, const VsbMdfArgs& a, const VsbBodyPar
   if (a.barrier && nb <= 120) {
     p.stage = 0; p.stage_end = a.n_iter;
     k_mdf_stage<DIM><<<nb, kBlock, 0, stream>>>(sp, p, bu);
+  } else if (DIM == 3 && a.u_win != nullptr && !getenv("VSB_MDF_UNTILED")) {
+    // dense body with a precomputed window velocity: every stage reads a window field -> shared-memory tiles
+    if constexpr (DIM == 3) {
+      constexpr size_t smem = 2 * (size_t)kTileCells * sizeof(float4);
+      static bool configured = false;
+      if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_mdf_stage_tiled<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "vsb_ib_mdf (shared-memory opt-in)");
+        configured = true;
+      }
+      const unsigned nbt = blocks_for(a.n_markers, kTiledChunk);
+      for (int k = 0; k < a.n_iter; ++k) {
+        p.stage = k; p.stage_end = k + 1;
+        k_mdf_stage_tiled<3><<<nbt, kTiledChunk, smem, stream>>>(p, bu);
+      }
+    }
   } else {
     for (int k = 0; k < a.n_iter; ++k) {
       p.stage = k; p.stage_end = k + 1;

@@ -118,6 +118,7 @@ class Stepper:
         self.body = None
         self._body_dev = None
         self._hist = None
+        self._perm = self._inv_perm = None
         if self.ib is not None:
             if not a.forcing:
                 raise ValueError("an immersed boundary needs forcing='edm' or 'guo'")
@@ -183,6 +184,22 @@ class Stepper:
                                  "out-of-range stencil indices undefined)")
         self.n_markers = markers.shape[0]
         self.n_iter = int(ib.get("n_iter", 5))
+        # dense marker sets (many stencil points per window cell, e.g. a finely meshed 3-D surface) interpolate a
+        # precomputed window velocity; sparse ones take it from the streamed populations at their stencil points
+        wcells = int(np.prod(self.win_size))
+        self._use_uwin = self.n_markers * 4 ** dim > 2 * wcells
+        # The tiled MDF kernel (dense 3-D bodies) gives each CTA 256 consecutive markers and privatises their part of
+        # the window in shared memory, so consecutive markers must be close in space: store them sorted by
+        # (x column of 4 cells, y column of 4 cells, z).  Outputs are handed back in the caller's order.
+        self._perm = self._inv_perm = None
+        if dim == 3 and self._use_uwin and self.n_markers > 480 and ib.get("sort_markers", True):
+            col = np.floor(markers[:, :2] / 4.0).astype(np.int64)
+            perm = np.lexsort((markers[:, 2], col[:, 1], col[:, 0]))
+            inv = np.empty_like(perm)
+            inv[perm] = np.arange(perm.size)
+            markers = np.ascontiguousarray(markers[perm])
+            self._perm = torch.as_tensor(perm, device=dev)
+            self._inv_perm = torch.as_tensor(inv, device=dev)
         self._markers = torch.as_tensor(markers, device=dev)
         # force field [0] and per-iteration work fields [1:], double-buffered by step parity: each step clears the
         # set the next step will accumulate into (see vsb_ib_mdf), so there is no memset on the step path
@@ -190,14 +207,12 @@ class Stepper:
         nc = 2 if dim == 2 else 4
         self._ib_buf = torch.zeros((2, self.n_iter) + self.win_size + (nc,), device=dev)
         self._g_win = self._ib_buf[0, 0]
-        # dense marker sets (many stencil points per window cell, e.g. a finely meshed 3-D surface) interpolate a
-        # precomputed window velocity; sparse ones take it from the streamed populations at their stencil points
-        wcells = int(np.prod(self.win_size))
-        self._use_uwin = self.n_markers * 4 ** dim > 2 * wcells
         self._u_win = torch.zeros(self.win_size + (nc,), device=dev) if self._use_uwin else None
         self._marker_u = torch.zeros((self.n_markers, dim), device=dev)
-        self.marker_force = torch.zeros((self.n_markers, dim), device=dev)   # +F; reaction on the body is -F
+        self._marker_force = torch.zeros((self.n_markers, dim), device=dev)   # +F; reaction on the body is -F
         tgt = ib.get("u_target")
+        if tgt is not None and self._perm is not None:
+            tgt = np.asarray(tgt, dtype=np.float32)[self._perm.cpu().numpy()]
         self._u_target = None if tgt is None else torch.as_tensor(np.asarray(tgt, dtype=np.float32), device=dev)
         ds = ib["ds"]
         self._ds = None
@@ -205,6 +220,9 @@ class Stepper:
         m.dim, m.delta_kind, m.n_iter = dim, L.DELTA[ib.get("kernel", "peskin4")], self.n_iter
         m.n_markers = self.n_markers
         if np.ndim(ds) > 0:
+            ds = np.asarray(ds, dtype=np.float32)
+            if self._perm is not None and ds.shape == (self.n_markers,):
+                ds = ds[self._perm.cpu().numpy()]
             self._ds = torch.as_tensor(np.asarray(ds, dtype=np.float32), device=dev)
             if self._ds.shape != (self.n_markers,):
                 raise ValueError("ib['ds'] must be a scalar or have shape (M,)")
@@ -223,7 +241,7 @@ class Stepper:
         lanes = 16 if dim == 2 else 32
         self._mdf_one_launch = (self.n_markers * lanes + 127) // 128 <= 120
         m.marker_u = self._marker_u.data_ptr()
-        m.marker_force = self.marker_force.data_ptr()
+        m.marker_force = self._marker_force.data_ptr()
         a.g_win = self._g_win.data_ptr()
         self.follow = 0
         self._bparams = None
@@ -342,6 +360,13 @@ class Stepper:
         return out
 
     @property
+    def marker_force(self):
+        """+F on every marker, shape (M, dim), in the order the markers were given (the reaction on the body is -F)."""
+        if self._inv_perm is None:
+            return self._marker_force
+        return self._marker_force.index_select(0, self._inv_perm)
+
+    @property
     def state(self):
         """The internal buffer (S_n after the first step, F_0 before).  For halo exchange and tests."""
         return self._bufs[self._cur]
@@ -384,7 +409,7 @@ class Stepper:
               "parity": np.array(self._parity, dtype=np.int32), "n_steps": np.array(self.n_steps, dtype=np.int64),
               "shape": np.array(self.shape, dtype=np.int64)}
         if self.ib is not None:
-            ck["marker_force"] = self.marker_force.cpu().numpy()
+            ck["marker_force"] = self._marker_force.cpu().numpy()
             ck["marker_u"] = self._marker_u.cpu().numpy()
         if self._body_dev is not None:
             ck["body"] = self._body_dev.cpu().numpy().view(np.uint8).copy()
@@ -403,7 +428,7 @@ class Stepper:
         self.n_steps = int(ck["n_steps"])
         if self.ib is not None:
             self._parity = int(ck["parity"])
-            self.marker_force.copy_(torch.as_tensor(ck["marker_force"]))
+            self._marker_force.copy_(torch.as_tensor(ck["marker_force"]))
             self._marker_u.copy_(torch.as_tensor(ck["marker_u"]))
             # between steps the set the next step accumulates into is zero and the other one is cleared by the next
             # step before it is used again, so starting from all-zero work fields is equivalent
@@ -642,7 +667,7 @@ class Stepper:
         keep = [b.clone() for b in self._bufs]
         ib_keep = None
         if self.ib is not None:
-            ib_keep = [t.clone() for t in (self._marker_u, self.marker_force)] + (
+            ib_keep = [t.clone() for t in (self._marker_u, self._marker_force)] + (
                 [self._body_dev.clone()] if self._body_dev is not None else [])
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -659,7 +684,7 @@ class Stepper:
         for b, k in zip(self._bufs, keep):   # capture does not execute, but the warm-up did: restore
             b.copy_(k)
         if ib_keep is not None:
-            self._marker_u.copy_(ib_keep[0]); self.marker_force.copy_(ib_keep[1])
+            self._marker_u.copy_(ib_keep[0]); self._marker_force.copy_(ib_keep[1])
             if self._body_dev is not None:
                 self._body_dev.copy_(ib_keep[2])
         self._graph = g
