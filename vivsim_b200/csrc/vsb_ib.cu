@@ -291,19 +291,18 @@ __global__ void k_mdf_stage(const StepParams<DIM> sp, const MdfParams p, const B
 // CTA owns a chunk of kTiledChunk CONSECUTIVE markers and works on the part of the window they touch in shared
 // memory:
 //   1. the source field of the chunk's bounding box is staged once (coalesced);
-//   2. marker-centric pass (one warp per marker): the 12 one-dimensional delta weights are evaluated once per
-//      marker (the 64 stencil weights are their products), u_m is gathered from the staged tile, dF and F follow;
-//      base cell, weights and the value to spread are parked in shared memory;
-//   3. cell-centric pass: every thread owns a few cells of the box and sums the contributions of the chunk's markers
-//      in registers, in marker order -- no shared-memory atomics (fp32 shared atomics run at ~2 cycles per lane and
-//      made an atomic version of this kernel only 1.6x faster than the untiled one);
+//   2. marker-centric pass (one thread per marker, no global-memory latency inside it): the 12 one-dimensional delta
+//      weights are evaluated once per marker (the 64 stencil weights are their products), u_m is gathered from the
+//      staged box, dF and F follow; base cell, weights and the value to spread are parked in shared memory;
+//   3. cell-centric pass: every thread owns four consecutive z cells of one row of the box and sums the
+//      contributions of the chunk's markers in registers, in marker order -- no shared-memory atomics (a first
+//      version with fp32 shared atomics and one warp per marker was only 1.6x faster than the untiled kernel);
 //   4. one coalesced vector reduction per touched cell adds the box to the window field.
 // A finely meshed surface puts ~20 stencil points on every window cell, so ~64 global reductions per marker become
 // ~3 per marker.  Chunks whose bounding box does not fit (markers not stored in a spatially coherent order) fall back
 // to global gathers / reductions, CTA by CTA.
 constexpr int kTiledChunk = 256;      // markers per CTA = threads per CTA
 constexpr int kTileCells = 2304;      // cells of the staged box: 2304 x 16 B = 36 KB
-constexpr int kCellsPerRound = 3;     // cells a thread accumulates at a time in pass 3
 
 struct TiledShared {
   int base[kTiledChunk][3];           // first stencil node (floor(x) - 1) per axis
@@ -312,7 +311,7 @@ struct TiledShared {
 };
 
 template <int DIM>
-__global__ void __launch_bounds__(kTiledChunk) k_mdf_stage_tiled(const MdfParams p, const BodyUpdate bu) {
+__global__ void __launch_bounds__(kTiledChunk, 3) k_mdf_stage_tiled(const MdfParams p, const BodyUpdate bu) {
   static_assert(DIM == 3, "the tiled stage is instantiated for D3Q19 bodies only");
   constexpr int NC = 4;
   extern __shared__ float4 s_dyn[];
@@ -375,47 +374,42 @@ __global__ void __launch_bounds__(kTiledChunk) k_mdf_stage_tiled(const MdfParams
   }
   __syncthreads();
 
-  // ---- pass 2: one warp per marker, 8 markers at a time
-  const int gl = tid & 31;
-  for (int pass = 0; pass < 32; ++pass) {
-    const int mi = pass * (kTiledChunk / 32) + (tid >> 5);
-    if (mi >= n_here) continue;                       // warp-uniform
-    const long long m = m_begin + mi;
-    // lanes 0..11 evaluate one delta weight each: axis = lane / 4, node = base + lane % 4 - 1
-    const int ax = (gl < 12) ? (gl >> 2) : 0;
-    const float xa = p.markers0[m * 3 + ax] + disp[ax] - (float)org[ax];
-    const int ba = (int)floorf(xa) - 1;
-    const int na = ba + (gl & 3);
-    float wl = delta(p.delta_kind, (float)na - xa);
-    if (na < 0 || na >= p.wsize[ax]) wl = 0.f;        // node outside the window: the reference's stencil skips it
-    if (gl < 12) sm.w[mi][gl] = wl;
-    const int bx = __shfl_sync(0xffffffffu, ba, 0), by = __shfl_sync(0xffffffffu, ba, 4), bz = __shfl_sync(0xffffffffu, ba, 8);
-    if (gl == 0) { sm.base[mi][0] = bx; sm.base[mi][1] = by; sm.base[mi][2] = bz; }
-    float um[3] = {0.f, 0.f, 0.f};
-    float w[2];
-    int nx[2], ny[2], nz[2];
+  // ---- pass 2: one thread per marker -- weights, interpolation from the staged box, dF and F
+  if (tid < n_here) {
+    const long long m = m_begin + tid;
+    float x[3], wgt[3][4];
+    int b0[3];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int sidx = gl * 2 + j;                    // same point numbering as k_mdf_stage: x slowest, z fastest
-      const int jx = sidx >> 4, jy = (sidx >> 2) & 3, jz = sidx & 3;
-      const float wz = __shfl_sync(0xffffffffu, wl, 8 + jz), wy = __shfl_sync(0xffffffffu, wl, 4 + jy),
-                  wx = __shfl_sync(0xffffffffu, wl, jx);
-      w[j] = (wz * wy) * wx;                          // the product order of k_mdf_stage
-      nx[j] = bx + jx; ny[j] = by + jy; nz[j] = bz + jz;
-      const bool ok = nx[j] >= 0 && nx[j] < p.wsize[0] && ny[j] >= 0 && ny[j] < p.wsize[1] && nz[j] >= 0 && nz[j] < p.wsize[2];
-      if (!ok) { w[j] = 0.f; nx[j] = -1; }
-      if (ok) {
-        float4 v;
-        if (tiled) v = s_src[((nx[j] - lo[0]) * ext[1] + (ny[j] - lo[1])) * ext[2] + (nz[j] - lo[2])];
-        else v = __ldcg(src + ((long long)nx[j] * p.wsize[1] + ny[j]) * p.wsize[2] + nz[j]);
-        um[0] += w[j] * v.x; um[1] += w[j] * v.y; um[2] += w[j] * v.z;
+    for (int d = 0; d < 3; ++d) {
+      x[d] = p.markers0[m * 3 + d] + disp[d] - (float)org[d];
+      b0[d] = (int)floorf(x[d]) - 1;
+      sm.base[tid][d] = b0[d];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int node = b0[d] + k;
+        float wl = delta(p.delta_kind, (float)node - x[d]);
+        if (node < 0 || node >= p.wsize[d]) wl = 0.f;     // node outside the window: the reference's stencil skips it
+        wgt[d][k] = wl;
+        sm.w[tid][4 * d + k] = wl;
       }
     }
+    float um[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int jx = 0; jx < 4; ++jx) {                                // 16 points per trip keeps the register count down
+      const float wx = sm.w[tid][jx];
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
+      for (int jy = 0; jy < 4; ++jy)
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) um[c] += __shfl_xor_sync(0xffffffffu, um[c], o);
-
+        for (int jz = 0; jz < 4; ++jz) {
+          const float w = (wgt[2][jz] * wgt[1][jy]) * wx;           // the product order of k_mdf_stage
+          if (w != 0.f) {                                           // also excludes every node outside the window
+            float4 v;
+            if (tiled) v = s_src[((b0[0] + jx - lo[0]) * ext[1] + (b0[1] + jy - lo[1])) * ext[2] + (b0[2] + jz - lo[2])];
+            else v = __ldcg(src + ((long long)(b0[0] + jx) * p.wsize[1] + (b0[1] + jy)) * p.wsize[2] + (b0[2] + jz));
+            um[0] += w * v.x; um[1] += w * v.y; um[2] += w * v.z;
+          }
+        }
+    }
     const float ds2 = (p.ds_ptr ? p.ds_ptr[m] : p.ds_value) * 2.0f;
     float spread_val[3];
 #pragma unroll
@@ -427,53 +421,65 @@ __global__ void __launch_bounds__(kTiledChunk) k_mdf_stage_tiled(const MdfParams
       const float dF = (tgt - u_m) * ds2;
       const float F = F_prev + dF;
       spread_val[c] = last ? F : dF;
-      if (gl == 0) { p.marker_u[m * 3 + c] = u_m; p.marker_force[m * 3 + c] = F; sm.val[mi][c] = spread_val[c]; }
+      p.marker_u[m * 3 + c] = u_m;
+      p.marker_force[m * 3 + c] = F;
+      sm.val[tid][c] = spread_val[c];
     }
     if (!tiled) {                                     // box too large for the tile: global vector reductions
+#pragma unroll 1
+      for (int jx = 0; jx < 4; ++jx)
 #pragma unroll
-      for (int j = 0; j < 2; ++j)
-        if (nx[j] >= 0)
-          atomicAdd(dst + ((long long)nx[j] * p.wsize[1] + ny[j]) * p.wsize[2] + nz[j],
-                    make_float4(spread_val[0] * w[j], spread_val[1] * w[j], spread_val[2] * w[j], 0.f));
+        for (int jy = 0; jy < 4; ++jy)
+#pragma unroll
+          for (int jz = 0; jz < 4; ++jz) {
+            const float w = (wgt[2][jz] * wgt[1][jy]) * sm.w[tid][jx];
+            if (w != 0.f)
+              atomicAdd(dst + ((long long)(b0[0] + jx) * p.wsize[1] + (b0[1] + jy)) * p.wsize[2] + (b0[2] + jz),
+                        make_float4(spread_val[0] * w, spread_val[1] * w, spread_val[2] * w, 0.f));
+          }
     }
-    if (last && p.body && gl == 0) {
+    if (last && p.body) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) atomicAdd(&s_force[c], spread_val[c]);
     }
   }
   __syncthreads();
 
-  // ---- pass 3 + 4: cell-centric accumulation in registers, then one vector reduction per touched cell
-  for (int round = 0; round * kCellsPerRound * kTiledChunk < tile_cells; ++round) {
-    int cx[kCellsPerRound], cy[kCellsPerRound], cz[kCellsPerRound];
-    float acc[kCellsPerRound][3];
+  // ---- pass 3 + 4: cell-centric accumulation in registers (a thread owns 4 consecutive z cells of one (x, y) row of
+  // the box and sums the chunk's markers in marker order), then one vector reduction per touched cell
+  if (tiled) {
+    const int zg = (ext[2] + 3) >> 2;
+    const int n_units = ext[0] * ext[1] * zg;
+    for (int unit = tid; unit < n_units; unit += kTiledChunk) {
+      const int row = unit / zg;
+      const int cx = lo[0] + row / ext[1], cy = lo[1] + row % ext[1], cz0 = lo[2] + 4 * (unit - row * zg);
+      float acc[4][3];
 #pragma unroll
-    for (int k = 0; k < kCellsPerRound; ++k) {
-      const int i = tid + (round * kCellsPerRound + k) * kTiledChunk;
-      const int tz = i % ext[2], r = i / ext[2];
-      cx[k] = (i < tile_cells) ? lo[0] + r / ext[1] : INT_MIN / 2;   // an impossible coordinate: never matches a stencil
-      cy[k] = lo[1] + r % ext[1];
-      cz[k] = lo[2] + tz;
-      acc[k][0] = acc[k][1] = acc[k][2] = 0.f;
-    }
-    for (int mi = 0; mi < n_here; ++mi) {
-      const int bx = sm.base[mi][0], by = sm.base[mi][1], bz = sm.base[mi][2];   // broadcast reads
+      for (int k = 0; k < 4; ++k) acc[k][0] = acc[k][1] = acc[k][2] = 0.f;
+      for (int mi = 0; mi < n_here; ++mi) {
+        const unsigned jx = (unsigned)(cx - sm.base[mi][0]), jy = (unsigned)(cy - sm.base[mi][1]);   // broadcast reads
+        if (jx < 4u && jy < 4u) {
+          const int dz = cz0 - sm.base[mi][2];
+          if (dz > -4 && dz < 4) {
+            const float wy = sm.w[mi][4 + jy], wx = sm.w[mi][jx];
+            const float v0 = sm.val[mi][0], v1 = sm.val[mi][1], v2 = sm.val[mi][2];
 #pragma unroll
-      for (int k = 0; k < kCellsPerRound; ++k) {
-        const unsigned jx = (unsigned)(cx[k] - bx), jy = (unsigned)(cy[k] - by), jz = (unsigned)(cz[k] - bz);
-        if (jx < 4u && jy < 4u && jz < 4u) {
-          const float w = (sm.w[mi][8 + jz] * sm.w[mi][4 + jy]) * sm.w[mi][jx];
-          acc[k][0] += sm.val[mi][0] * w;
-          acc[k][1] += sm.val[mi][1] * w;
-          acc[k][2] += sm.val[mi][2] * w;
+            for (int k = 0; k < 4; ++k) {
+              const unsigned jz = (unsigned)(dz + k);
+              if (jz < 4u) {
+                const float w = (sm.w[mi][8 + jz] * wy) * wx;
+                acc[k][0] += v0 * w; acc[k][1] += v1 * w; acc[k][2] += v2 * w;
+              }
+            }
+          }
         }
       }
-    }
 #pragma unroll
-    for (int k = 0; k < kCellsPerRound; ++k)
-      if (cx[k] >= 0 && (acc[k][0] != 0.f || acc[k][1] != 0.f || acc[k][2] != 0.f))
-        atomicAdd(dst + ((long long)cx[k] * p.wsize[1] + cy[k]) * p.wsize[2] + cz[k],
-                  make_float4(acc[k][0], acc[k][1], acc[k][2], 0.f));
+      for (int k = 0; k < 4; ++k)
+        if (cz0 + k < lo[2] + ext[2] && (acc[k][0] != 0.f || acc[k][1] != 0.f || acc[k][2] != 0.f))
+          atomicAdd(dst + ((long long)cx * p.wsize[1] + cy) * p.wsize[2] + (cz0 + k),
+                    make_float4(acc[k][0], acc[k][1], acc[k][2], 0.f));
+    }
   }
 
   if (last && p.body) {
