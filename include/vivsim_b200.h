@@ -214,6 +214,13 @@ typedef struct {
                       writes the total marker force to (force[0..2], then seq = mail_seq, system-scope release), so
                       that the host can pick it up by polling instead of a copy + stream synchronisation */
   int mail_seq;
+  const int32_t* chunk_offsets;    /* optional, dense 3-D bodies (u_win != NULL): n_chunks + 1 device offsets into the
+                      marker arrays; chunk c = markers [offsets[c], offsets[c+1]) (at most 256) is handled by one CTA
+                      of the tiled kernel, which stages the chunk's bounding box of the window in shared memory.
+                      The caller orders the markers and cuts the chunks so that each box (+1 cell per axis for a moving
+                      body) holds at most 2304 cells; a chunk that does not fit falls back to global reductions.
+                      NULL: fixed chunks of 256 consecutive markers */
+  int n_chunks;
 } VsbMdfArgs;
 
 /* ---- fused time step ------------------------------------------------------------------- *

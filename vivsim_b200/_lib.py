@@ -75,7 +75,7 @@ class VsbMdfArgs(C.Structure):
                 ("g_win_next", C.c_void_p),
                 ("scratch", C.c_void_p), ("scratch_next", C.c_void_p), ("marker_u", C.c_void_p),
                 ("marker_force", C.c_void_p), ("body", C.c_void_p), ("barrier", C.c_void_p),
-                ("host_mail", C.c_void_p), ("mail_seq", C.c_int)]
+                ("host_mail", C.c_void_p), ("mail_seq", C.c_int), ("chunk_offsets", C.c_void_p), ("n_chunks", C.c_int)]
 
 
 class VsbStepArgs(C.Structure):

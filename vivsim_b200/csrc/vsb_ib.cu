@@ -90,6 +90,7 @@ struct MdfParams {
   int update_body;
   VsbHostMail* host_mail;   // host-ODE mode: post the total force to page-locked host memory
   int mail_seq;
+  const int* chunk_offsets; // tiled kernel: marker range of every CTA (NULL: 256 consecutive markers each)
 };
 
 // Stage k of multi_direct_forcing (ib/mdf.py:31-64), one launch per iteration, markers spread over many CTAs:
@@ -342,8 +343,9 @@ __global__ void __launch_bounds__(kTiledChunk, 3) k_mdf_stage_tiled(const MdfPar
     for (long long i = gthread; i < NC * wcells; i += nthreads) z[i] = 0.f;
   }
 
-  const long long m_begin = (long long)blockIdx.x * kTiledChunk;
-  const int n_here = (int)min((long long)kTiledChunk, p.n_markers - m_begin);
+  const long long m_begin = p.chunk_offsets ? (long long)p.chunk_offsets[blockIdx.x] : (long long)blockIdx.x * kTiledChunk;
+  const int n_here = p.chunk_offsets ? min(p.chunk_offsets[blockIdx.x + 1] - (int)m_begin, kTiledChunk)
+                                     : (int)min((long long)kTiledChunk, p.n_markers - m_begin);
   // bounding box of the chunk's stencils (window-local cells), clipped to the window
   if (tid < n_here) {
 #pragma unroll
@@ -529,6 +531,7 @@ static int mdf_impl(const VsbStepArgs& sa, const VsbMdfArgs& a, const VsbBodyPar
   p.update_body = (a.body && bp && bp->n_dof > 0) ? 1 : 0;
   p.host_mail = (a.body && !p.update_body) ? a.host_mail : nullptr;
   p.mail_seq = a.mail_seq;
+  p.chunk_offsets = nullptr;
   BodyUpdate bu{};
   if (p.update_body) bu = make_body_update(*bp, DIM);
   const int lanes = (DIM == 2) ? 16 : 32;
@@ -549,7 +552,9 @@ static int mdf_impl(const VsbStepArgs& sa, const VsbMdfArgs& a, const VsbBodyPar
         if (e != cudaSuccess) return cuda_fail(e, "vsb_ib_mdf (shared-memory opt-in)");
         configured = true;
       }
-      const unsigned nbt = blocks_for(a.n_markers, kTiledChunk);
+      const bool cut = a.chunk_offsets != nullptr && a.n_chunks > 0;
+      p.chunk_offsets = cut ? a.chunk_offsets : nullptr;
+      const unsigned nbt = cut ? (unsigned)a.n_chunks : blocks_for(a.n_markers, kTiledChunk);
       for (int k = 0; k < a.n_iter; ++k) {
         p.stage = k; p.stage_end = k + 1;
         k_mdf_stage_tiled<3><<<nbt, kTiledChunk, smem, stream>>>(p, bu);

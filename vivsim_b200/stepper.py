@@ -200,6 +200,23 @@ class Stepper:
             markers = np.ascontiguousarray(markers[perm])
             self._perm = torch.as_tensor(perm, device=dev)
             self._inv_perm = torch.as_tensor(inv, device=dev)
+            # cut the sorted list into chunks of <= 256 markers of ONE column whose z range keeps the chunk's bounding
+            # box (column 4 + stencil 3 + 1 for a moving body = 8 cells in x and y) within the 2304-cell tile
+            col = col[perm]
+            key = col[:, 0] * (1 << 32) + col[:, 1]
+            starts = np.flatnonzero(np.r_[True, key[1:] != key[:-1]])
+            ends = np.r_[starts[1:], key.size]
+            z_span = 2304 // 64 - 5                   # box z extent = span + 4 stencil cells + 1 margin
+            offsets = [0]
+            for s_, e_ in zip(starts, ends):
+                z = markers[s_:e_, 2]
+                pos = 0
+                while pos < e_ - s_:
+                    stop = min(pos + 256, int(np.searchsorted(z, z[pos] + z_span, side="left")))
+                    stop = max(stop, pos + 1)
+                    offsets.append(s_ + stop)
+                    pos = stop
+            self._chunk_offsets = torch.as_tensor(np.asarray(offsets, dtype=np.int32), device=dev)
         self._markers = torch.as_tensor(markers, device=dev)
         # force field [0] and per-iteration work fields [1:], double-buffered by step parity: each step clears the
         # set the next step will accumulate into (see vsb_ib_mdf), so there is no memset on the step path
@@ -234,6 +251,9 @@ class Stepper:
             m.win_size[d] = self.win_size[d]
             a.win_origin[d] = m.win_origin0[d]
             a.win_size[d] = self.win_size[d]
+        if self._perm is not None:
+            m.chunk_offsets = self._chunk_offsets.data_ptr()
+            m.n_chunks = self._chunk_offsets.numel() - 1
         m.markers0 = self._markers.data_ptr()
         m.u_target = self._u_target.data_ptr() if self._u_target is not None else None
         self._mdf_barrier = torch.zeros(2, dtype=torch.int64, device=dev)
