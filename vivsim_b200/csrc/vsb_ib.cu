@@ -347,13 +347,20 @@ __global__ void __launch_bounds__(kTiledChunk, 3) k_mdf_stage_tiled(const MdfPar
   const int n_here = p.chunk_offsets ? min(p.chunk_offsets[blockIdx.x + 1] - (int)m_begin, kTiledChunk)
                                      : (int)min((long long)kTiledChunk, p.n_markers - m_begin);
   // bounding box of the chunk's stencils (window-local cells), clipped to the window
-  if (tid < n_here) {
+  {
+    int bmin[3] = {INT_MAX, INT_MAX, INT_MAX}, bmax[3] = {INT_MIN, INT_MIN, INT_MIN};
+    if (tid < n_here) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const float x = p.markers0[(m_begin + tid) * 3 + d] + disp[d] - (float)org[d];
+        bmin[d] = bmax[d] = (int)floorf(x);
+      }
+    }
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      const float x = p.markers0[(m_begin + tid) * 3 + d] + disp[d] - (float)org[d];
-      const int b = (int)floorf(x);
-      atomicMin(&s_lo[d], b - 1);
-      atomicMax(&s_hi[d], b + 2);
+      bmin[d] = __reduce_min_sync(0xffffffffu, bmin[d]);
+      bmax[d] = __reduce_max_sync(0xffffffffu, bmax[d]);
+      if ((tid & 31) == 0 && bmin[d] != INT_MAX) { atomicMin(&s_lo[d], bmin[d] - 1); atomicMax(&s_hi[d], bmax[d] + 2); }
     }
   }
   __syncthreads();
@@ -377,6 +384,7 @@ __global__ void __launch_bounds__(kTiledChunk, 3) k_mdf_stage_tiled(const MdfPar
   __syncthreads();
 
   // ---- pass 2: one thread per marker -- weights, interpolation from the staged box, dF and F
+  float fsum[3] = {0.f, 0.f, 0.f};
   if (tid < n_here) {
     const long long m = m_begin + tid;
     float x[3], wgt[3][4];
@@ -442,27 +450,50 @@ __global__ void __launch_bounds__(kTiledChunk, 3) k_mdf_stage_tiled(const MdfPar
     }
     if (last && p.body) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) atomicAdd(&s_force[c], spread_val[c]);
+      for (int c = 0; c < 3; ++c) fsum[c] = spread_val[c];
+    }
+  }
+  if (last && p.body) {   // total force of the chunk: warp shuffles, then one shared atomic per warp and component
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) fsum[c] += __shfl_xor_sync(0xffffffffu, fsum[c], o);
+      if ((tid & 31) == 0) atomicAdd(&s_force[c], fsum[c]);
     }
   }
   __syncthreads();
 
   // ---- pass 3 + 4: cell-centric accumulation in registers (a thread owns 4 consecutive z cells of one (x, y) row of
-  // the box and sums the chunk's markers in marker order), then one vector reduction per touched cell
+  // the box and sums the chunk's markers in marker order), then one vector reduction per touched cell.  The lanes of a
+  // warp own different rows of the SAME z group, so the z test is warp-uniform; when the chunk's markers are sorted by
+  // z (they are, for chunks cut by the host) each unit only visits the markers whose stencil reaches its z group.
   if (tiled) {
+    const int my_bz = tid < n_here ? sm.base[tid][2] : INT_MAX;
+    const int next_bz = tid + 1 < n_here ? sm.base[tid + 1][2] : INT_MAX;
+    const bool z_sorted = __syncthreads_and(my_bz <= next_bz) != 0;
     const int zg = (ext[2] + 3) >> 2;
-    const int n_units = ext[0] * ext[1] * zg;
+    const int n_rows = ext[0] * ext[1];
+    const int n_units = n_rows * zg;
     for (int unit = tid; unit < n_units; unit += kTiledChunk) {
-      const int row = unit / zg;
-      const int cx = lo[0] + row / ext[1], cy = lo[1] + row % ext[1], cz0 = lo[2] + 4 * (unit - row * zg);
+      const int zgi = unit / n_rows, row = unit - zgi * n_rows;
+      const int cx = lo[0] + row / ext[1], cy = lo[1] + row % ext[1], cz0 = lo[2] + 4 * zgi;
+      int m_lo = 0, m_hi = n_here;
+      if (z_sorted) {          // markers with cz0 - 3 <= base_z <= cz0 + 3
+        int a = 0, b = n_here;
+        while (a < b) { const int mid = (a + b) >> 1; if (sm.base[mid][2] < cz0 - 3) a = mid + 1; else b = mid; }
+        m_lo = a;
+        b = n_here;
+        while (a < b) { const int mid = (a + b) >> 1; if (sm.base[mid][2] <= cz0 + 3) a = mid + 1; else b = mid; }
+        m_hi = a;
+      }
       float acc[4][3];
 #pragma unroll
       for (int k = 0; k < 4; ++k) acc[k][0] = acc[k][1] = acc[k][2] = 0.f;
-      for (int mi = 0; mi < n_here; ++mi) {
-        const unsigned jx = (unsigned)(cx - sm.base[mi][0]), jy = (unsigned)(cy - sm.base[mi][1]);   // broadcast reads
-        if (jx < 4u && jy < 4u) {
-          const int dz = cz0 - sm.base[mi][2];
-          if (dz > -4 && dz < 4) {
+      for (int mi = m_lo; mi < m_hi; ++mi) {
+        const int dz = cz0 - sm.base[mi][2];                                                         // broadcast reads
+        if (dz > -4 && dz < 4) {
+          const unsigned jx = (unsigned)(cx - sm.base[mi][0]), jy = (unsigned)(cy - sm.base[mi][1]);
+          if (jx < 4u && jy < 4u) {
             const float wy = sm.w[mi][4 + jy], wx = sm.w[mi][jx];
             const float v0 = sm.val[mi][0], v1 = sm.val[mi][1], v2 = sm.val[mi][2];
 #pragma unroll
