@@ -13,6 +13,7 @@
 namespace vsb {
 
 constexpr int kBlock = 128;
+constexpr int kMdfCtasPerSm = 0;   // cap of the per-iteration MDF grid in CTAs per SM (0: none); VSB_MDF_GRID_CAP overrides (CTAs)
 
 __global__ void k_delta(int kind, long long n, const float* __restrict__ r, float* __restrict__ out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -116,8 +117,11 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned n
   __syncthreads();
 }
 
+// 3-D: five CTAs of 128 threads per SM (<= 102 registers) = 740 resident CTAs, so that a body of up to ~2900 markers
+// (the 2562-marker sphere of the 256^3 case needs 641 CTAs) runs as ONE wave; at 110 registers the last 49 CTAs made
+// up a second wave that cost a whole CTA latency per stage.
 template <int DIM>
-__global__ void k_mdf_stage(const StepParams<DIM> sp, const MdfParams p, const BodyUpdate bu) {
+__global__ void __launch_bounds__(kBlock, DIM == 3 ? 5 : 8) k_mdf_stage(const StepParams<DIM> sp, const MdfParams p, const BodyUpdate bu) {
   using L = Lat<DIM>;
   constexpr int NS = (DIM == 2) ? 16 : 64;   // 4^D stencil points
   constexpr int G = (DIM == 2) ? 16 : 32;    // lanes per marker
@@ -130,13 +134,20 @@ __global__ void k_mdf_stage(const StepParams<DIM> sp, const MdfParams p, const B
 
   const long long gthread = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long nthreads = (long long)gridDim.x * blockDim.x;
-  const long long m = gthread / G;
   const int gl = (int)(gthread % G);
-  const bool active = m < p.n_markers;
   const long long wcells = (long long)p.wsize[0] * p.wsize[1] * (DIM == 3 ? p.wsize[2] : 1);
 
   int org[3] = {p.origin0[0], p.origin0[1], p.origin0[2]};
   if (p.body) { org[0] = p.body->origin2[p.parity][0]; org[1] = p.body->origin2[p.parity][1]; org[2] = p.body->origin2[p.parity][2]; }
+
+  // A launch of ONE stage may use fewer lane groups than markers (grid capped by the host so that the chain leaves
+  // most of every SM to the bulk kernel running beside it): the groups then walk the marker list in batches.  The
+  // trip count is the same for every thread, so the warp shuffles below stay converged.
+  const long long mstride = nthreads / G;
+  const long long n_batch = (p.n_markers + mstride - 1) / mstride;
+  for (long long batch = 0; batch < n_batch; ++batch) {
+  const long long m = batch * mstride + gthread / G;
+  const bool active = m < p.n_markers;
 
   // stencil of this lane's marker: the same for every iteration
   float w[PPL];
@@ -188,9 +199,9 @@ __global__ void k_mdf_stage(const StepParams<DIM> sp, const MdfParams p, const B
   for (int stage = p.stage; stage < p.stage_end; ++stage) {
     const bool last = stage == p.n_iter - 1;
     // clear the other parity's buffers for the next step
-    if (stage == 0)
+    if (stage == 0 && batch == 0)
       for (long long i = gthread; i < NC * wcells; i += nthreads) p.g_win_next[i] = 0.f;
-    if (stage < p.n_iter - 1) {
+    if (stage < p.n_iter - 1 && batch == 0) {
       float* z = p.scratch_next + (long long)stage * NC * wcells;
       for (long long i = gthread; i < NC * wcells; i += nthreads) z[i] = 0.f;
     }
@@ -258,6 +269,7 @@ __global__ void k_mdf_stage(const StepParams<DIM> sp, const MdfParams p, const B
     }
     if (stage + 1 < p.stage_end) grid_barrier(p.barrier, gridDim.x);
   }
+  }   // marker batches
 
   if (p.stage_end == p.n_iter && p.body) {
     __syncthreads();
@@ -570,7 +582,7 @@ static int mdf_impl(const VsbStepArgs& sa, const VsbMdfArgs& a, const VsbBodyPar
   p.barrier = reinterpret_cast<unsigned long long*>(a.barrier);
   // Small bodies: every iteration in ONE launch, separated by grid barriers (all CTAs are co-resident: at most 120 of
   // 128 threads).  Large bodies: one launch per iteration.
-  if (a.barrier && nb <= 120) {
+  if (a.barrier && nb <= 120) {   // (one marker per lane group: the kernel keeps u_m and F in registers across stages)
     p.stage = 0; p.stage_end = a.n_iter;
     k_mdf_stage<DIM><<<nb, kBlock, 0, stream>>>(sp, p, bu);
   } else if (DIM == 3 && a.u_win != nullptr && !getenv("VSB_MDF_UNTILED")) {
@@ -592,9 +604,21 @@ static int mdf_impl(const VsbStepArgs& sa, const VsbMdfArgs& a, const VsbBodyPar
       }
     }
   } else {
+    // One launch per iteration.  The chain is latency-bound and runs beside the bulk kernel; with one CTA per marker
+    // group it would take every SM's registers for itself (118 registers x 128 threads, four or more CTAs per SM)
+    // and stall the bulk.  Capped at kMdfCtasPerSm CTAs per SM, the groups walk the markers in batches instead.
+    static const int cap = [] {
+      const char* e = getenv("VSB_MDF_GRID_CAP");
+      if (e) return atoi(e);
+      int dev = 0, n_sm = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+      return kMdfCtasPerSm * n_sm;
+    }();
+    const unsigned nbc = (cap > 0 && nb > (unsigned)cap) ? (unsigned)cap : nb;
     for (int k = 0; k < a.n_iter; ++k) {
       p.stage = k; p.stage_end = k + 1;
-      k_mdf_stage<DIM><<<nb, kBlock, 0, stream>>>(sp, p, bu);
+      k_mdf_stage<DIM><<<nbc, kBlock, 0, stream>>>(sp, p, bu);
     }
   }
   VSB_LAUNCH_CHECK("vsb_ib_mdf");

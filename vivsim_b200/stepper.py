@@ -22,6 +22,7 @@ spec keys (same dict the CPU oracle's ``oracle.recipes`` accepts)
     post ordered list of (name, loc, kwargs) / ("mask", mask)
 """
 
+import os
 import ctypes as C
 
 import numpy as np
@@ -161,10 +162,17 @@ class Stepper:
         # concurrent branches need every kernel of a step to be independent of launch order
         self.overlap = (self._want["overlap"] and self.ib is not None and (n_bc == 0 or self.edge_fused))
         if self.overlap or (self.edge_fused and self._want["overlap"]):
-            self._side = [torch.cuda.Stream(device=self.device) for _ in range(2)]
+            self._side = self._side_streams()
         self.n_launch_per_step = self._count_launches(n_bc)
 
     # ------------------------------------------------------------------ setup helpers
+    def _side_streams(self):
+        """IB and wall-layer streams.  The IB chain is short, serial and latency-bound while the bulk kernel keeps every
+        SM full: a higher stream priority lets the chain's CTAs take freed slots first instead of queueing behind
+        the bulk's remaining blocks (VSB_IB_PRIORITY=0 switches it off)."""
+        prio = int(os.environ.get("VSB_IB_PRIORITY", "-1"))
+        return [torch.cuda.Stream(device=self.device, priority=prio), torch.cuda.Stream(device=self.device)]
+
     def _init_ib(self, a, body, dyn_mode, follow):
         ib, dim, dev = self.ib, self.dim, self.device
         markers = np.asarray(ib["markers"], dtype=np.float32)
@@ -355,7 +363,7 @@ class Stepper:
         x_only = all(loc in (L.LOC["left"], L.LOC["right"]) for loc in locs)
         self.halo_pipelined = (self.rows[1] - self.rows[0] >= 4) and (not locs or (self.edge_fused and x_only))
         if self._side is None:
-            self._side = [torch.cuda.Stream(device=self.device) for _ in range(2)]
+            self._side = self._side_streams()
         self._halo_stream = torch.cuda.Stream(device=self.device)
         self.n_launch_per_step += 3 if self.halo_pipelined else 1
 
