@@ -251,8 +251,9 @@ typedef struct {
   const VsbPostOp* post;      /* HOST array of ordered post-streaming operations (at most one
                                  VSB_POST_MASK; it is also applied to interior cells in the fused pass) */
   int vec;                    /* cells per thread along the contiguous axis: 0 = auto, 1, 2, 4 */
-  int band;                   /* 0: all rows; 1: all rows except the x-range of the force window;
-                                 2: only that x-range (lets the bulk run concurrently with the IB kernels) */
+  int band;                   /* 0: all cells; 1: all cells except the band of the force window; 2: only that
+                                 band (lets the bulk run concurrently with the IB kernels).  The band is the
+                                 window's x-range in 2-D and its (x, y) footprint over all z in 3-D */
   int edges;                  /* 0: ordered wall fix-up inside vsb_step; 1: none -- the caller runs
                                  vsb_edge_fused and the fused pass leaves those wall layers untouched;
                                  2: the wall layers are processed by extra blocks of the same launch

@@ -78,18 +78,21 @@ __global__ void __launch_bounds__(step_max_threads<DIM, COLL>(), step_min_ctas<D
   // rows of the slowest axis handled by this launch: all of [r_begin, r_end), or only / all but the x-range of
   // the force window (band), so that the bulk can run while the IB kernels still produce the window's force
   const int band_lo = max(p.s_begin, worg[0]), band_hi = min(p.s_end, worg[0] + p.wsz[0]);
+  // In 3-D the band is the window's (x, y) footprint over all z: band 2 enumerates wsz[1] lines per x plane.
+  const bool box = DIM == 3 && p.band == 2;
   const int row0 = (p.band == 2) ? band_lo : p.s_begin;
   const int nrow = p.edge_rows ? 2 : ((p.band == 2) ? max(band_hi - band_lo, 0) : p.s_end - p.s_begin);
-  const unsigned total = (unsigned)((DIM == 2) ? nrow : nrow * p.n1) * (unsigned)nv;   // < 2^31, checked by the host
+  const int lines = box ? p.wsz[1] : p.n1;            // z lines per x plane handled by this launch
+  const unsigned total = (unsigned)((DIM == 2) ? nrow : nrow * lines) * (unsigned)nv;   // < 2^31, checked by the host
   unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
   bool active = gid < total;
   if (!active) gid = 0;          // the lane stays in the shuffles; it loads and stores nothing
   const unsigned row = fast_div(gid, p.div_nv);
   const int j = (int)(gid - row * (unsigned)nv);
-  const int rx = (DIM == 2) ? (int)row : (int)fast_div(row, p.div_n1);   // row counter along the slowest axis
+  const int rx = (DIM == 2) ? (int)row : (int)fast_div(row, box ? p.div_w1 : p.div_n1);   // row counter along the slowest axis
   const int ix0 = p.edge_rows ? (rx == 0 ? p.r_begin : p.r_end - 1) : row0 + rx;
   const int i0 = (DIM == 2) ? 0 : ix0;
-  const int i1 = (DIM == 2) ? ix0 : (int)row - rx * p.n1;
+  const int i1 = (DIM == 2) ? ix0 : (int)row - rx * lines + (box ? worg[1] : 0);
   const int i2 = j * VEC;
   const int lane = threadIdx.x & 31;
   const int n12 = p.n1 * p.n2;
@@ -97,7 +100,7 @@ __global__ void __launch_bounds__(step_max_threads<DIM, COLL>(), step_min_ctas<D
   const long long cell = (long long)i0 * n12 + (i1 * p.n2 + i2);
   {
     const int ix = (DIM == 2) ? i1 : i0;
-    if (p.band == 1 && ix >= band_lo && ix < band_hi) active = false;
+    if (p.band == 1 && ix >= band_lo && ix < band_hi && (DIM == 2 || (unsigned)(i1 - worg[1]) < (unsigned)p.wsz[1])) active = false;
     // wall layers owned by the fused wall kernel (at most two)
     if (p.n_skip > 0 && (p.skip_axis[0] ? i1 : i0) == p.skip_layer[0]) active = false;
     if (p.n_skip > 1 && (p.skip_axis[1] ? i1 : i0) == p.skip_layer[1]) active = false;
@@ -606,12 +609,14 @@ static int step_impl(const VsbStepArgs& a, cudaStream_t s) {
   while (vec > 1 && (p.n2 % vec != 0 || ((uintptr_t)a.f_in % (4 * vec)) || ((uintptr_t)a.f_out % (4 * vec)))) vec >>= 1;
   VSB_REQUIRE(vec == 1 || vec == 2 || vec == 4, "vsb_step: vec must be 0, 1, 2 or 4");
   const int nrow = p.edge_rows ? 2 : ((p.band == 2) ? std::min(p.wsz[0], p.s_end - p.s_begin) : p.s_end - p.s_begin);
-  const long long rows = (DIM == 2) ? (long long)nrow : (long long)nrow * p.n1;
+  const bool box = DIM == 3 && p.band == 2;            // 3-D band 2: only the window's y-range of every x plane
+  const long long rows = (DIM == 2) ? (long long)nrow : (long long)nrow * (box ? p.wsz[1] : p.n1);
   const long long total = rows * (p.n2 / vec);
   VSB_REQUIRE(total < (1ll << 31) && (long long)p.n0 * p.n1 * p.n2 < (1ll << 31),
               "vsb_step: more than 2^31 cells in one launch; split the rows (sub_begin / sub_end)");
   p.div_nv = make_fast_div((unsigned)(p.n2 / vec));
   p.div_n1 = make_fast_div((unsigned)p.n1);
+  p.div_w1 = make_fast_div((unsigned)std::max(p.wsz[1], 1));
   // Block size: for grids of only a few waves (e.g. 1024^2 = 1.73 waves of 256-thread blocks) the partly filled last
   // wave costs up to a whole wave; choose the multiple of 32 in [128, 256] that fills the last wave best.
   auto launch = [&](auto kernel) {
@@ -644,7 +649,7 @@ static int step_impl(const VsbStepArgs& a, cudaStream_t s) {
       // lattices, scripts/prefetch_sweep.py; beyond ~2x that the lines are evicted again before use)
       static const double pf_bytes = [] { const char* e = getenv("VSB_PREFETCH_KB"); return (e ? atof(e) : 5632.0) * 1024.0; }();
       const double block_bytes = (double)best_bs * vec * Lat<DIM>::Q * 4.0;
-      p.prefetch_blocks = pf_bytes > 0 ? std::max(1, (int)(pf_bytes / block_bytes + 0.5)) : 0;
+      p.prefetch_blocks = (pf_bytes > 0 && !box) ? std::max(1, (int)(pf_bytes / block_bytes + 0.5)) : 0;   // (box rows are not contiguous)
     }
     unsigned extra = 0;
     for (int e = 0; e < p.n_wall; ++e) {
