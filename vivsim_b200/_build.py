@@ -41,7 +41,10 @@ def build(force=False, verbose=False, out=OUT, defines=()):
     for src in sources():
         obj = os.path.join(bdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), dep):
+        src_time = os.path.getmtime(src)
+        if os.path.basename(src).startswith("vsb_step_part"):      # these include vsb_step.cu
+            src_time = max(src_time, os.path.getmtime(os.path.join(CSRC, "vsb_step.cu")))
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(src_time, dep):
             cmd = [NVCC, *ARCH, *FLAGS, *["-D" + d for d in defines], "-c", src, "-o", obj]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")

@@ -452,8 +452,10 @@ int fill_params(const VsbStepArgs& a, StepParams<DIM>& p) {
   VSB_REQUIRE(n_mask == 0 || p.mask, "vsb_step: mask op without a mask");
   return VSB_OK;
 }
+#ifndef VSB_STEP_PART
 template int fill_params<2>(const VsbStepArgs&, StepParams<2>&);
 template int fill_params<3>(const VsbStepArgs&, StepParams<3>&);
+#endif
 
 template <int DIM, int COLL>
 static void fill_mats(const VsbStepArgs& a, MrtMats<DIM, is_mrt(COLL)>& mm) {
@@ -546,7 +548,7 @@ static int launch_edge(const StepParams<DIM>& p, const MrtMats<DIM, is_mrt(COLL)
 }
 
 template <int DIM, int COLL>
-static int edge_impl(const VsbStepArgs& a, cudaStream_t s, bool query_only, int* supported) {
+int edge_impl(const VsbStepArgs& a, cudaStream_t s, bool query_only, int* supported) {
   StepParams<DIM> p;
   if (int rc = fill_params<DIM>(a, p)) return rc;
   int mask_before = 0;
@@ -577,7 +579,7 @@ static int edge_impl(const VsbStepArgs& a, cudaStream_t s, bool query_only, int*
 }
 
 template <int DIM, int COLL>
-static int step_impl(const VsbStepArgs& a, cudaStream_t s) {
+int step_impl(const VsbStepArgs& a, cudaStream_t s) {
   StepParams<DIM> p;
   if (int rc = fill_params<DIM>(a, p)) return rc;
   if (int rc = check_mrt(a)) return rc;
@@ -712,6 +714,21 @@ static int step_impl(const VsbStepArgs& a, cudaStream_t s) {
   return VSB_OK;
 }
 
+// ----------------------------------------------------------------------------- build slicing
+// The (lattice, collision) instantiations of step_impl / edge_impl -- and with them every k_step / k_edge_fused
+// kernel -- live in the translation units vsb_step_part<k>.cu (each defines VSB_STEP_PART, includes this file and
+// instantiates its share explicitly), so that they compile in parallel.  This file alone keeps the dispatcher and the
+// C entry points and only declares the instantiations.
+#ifndef VSB_STEP_PART
+#define VSB_STEP_EXTERN(D, C)                                                           \
+  extern template int step_impl<D, C>(const VsbStepArgs&, cudaStream_t);              \
+  extern template int edge_impl<D, C>(const VsbStepArgs&, cudaStream_t, bool, int*);
+VSB_STEP_EXTERN(2, VSB_COLL_BGK) VSB_STEP_EXTERN(2, VSB_COLL_REG) VSB_STEP_EXTERN(2, VSB_COLL_KBC)
+VSB_STEP_EXTERN(2, VSB_COLL_MRT) VSB_STEP_EXTERN(2, VSB_COLL_MRT_SPLIT)
+VSB_STEP_EXTERN(3, VSB_COLL_BGK) VSB_STEP_EXTERN(3, VSB_COLL_REG) VSB_STEP_EXTERN(3, VSB_COLL_KBC)
+VSB_STEP_EXTERN(3, VSB_COLL_MRT) VSB_STEP_EXTERN(3, VSB_COLL_MRT_SPLIT)
+#undef VSB_STEP_EXTERN
+
 template <int DIM>
 static int step_dispatch(const VsbStepArgs& a, cudaStream_t s, int what, int* supported) {
   // what: 0 step, 1 fused wall kernel, 2 query support of the fused wall kernel
@@ -743,9 +760,11 @@ static int window_impl(const VsbStepArgs& a, float* u_win, cudaStream_t s) {
   VSB_LAUNCH_CHECK("vsb_ib_window_moments");
   return VSB_OK;
 }
+#endif  // !VSB_STEP_PART
 
 }  // namespace vsb
 
+#ifndef VSB_STEP_PART
 using namespace vsb;
 
 static int check_step_args(const VsbStepArgs* args, const char* who) {
@@ -784,3 +803,4 @@ int vsb_ib_window_moments(const VsbStepArgs* args, float* u_win, vsb_stream_t st
 }
 
 }  // extern "C"
+#endif  // !VSB_STEP_PART
