@@ -321,6 +321,19 @@ int vsb_step_host_ode(VsbStepArgs* args, const VsbMdfArgs* mdf, const VsbBodyPar
 int vsb_run_host_ode(VsbStepArgs* args, VsbMdfArgs* mdf, const VsbBodyParams* params, VsbBodyState* pinned,
                      const VsbHostPlan* plan, int n_steps);
 
+/* The same for n_domains (1..64) INDEPENDENT simulations on one GPU (an ensemble: e.g. the reduced-velocity sweep of a
+ * VIV study, each case being one run of examples/2d/vortex_induced_vibration.py), n_steps each, in one call.  Every
+ * domain brings its own argument blocks, body state, mailbox and streams (plans[i]->main / ib must differ between
+ * domains).  One host thread serves all mailboxes round-robin: whichever domain's force has arrived gets its body
+ * advanced (dyn.py:5-51), its state sent back and its next step enqueued, so the device always has other domains'
+ * kernels to run while one domain waits for the host -- the per-step host round trip is hidden instead of paid.
+ * Runs of >= 32 steps record each domain's step (both parities) as CUDA graphs after two kernel-by-kernel steps and
+ * replay them: two driver calls per step (graph launch, 92-byte state copy); VSB_HOST_ODE_GRAPH=0 switches that off,
+ * VSB_HOST_ODE_THREADS=T serves the domains from T host threads (kernel by kernel). */
+int vsb_run_host_ode_multi(int n_domains, VsbStepArgs* const* args, VsbMdfArgs* const* mdfs,
+                           const VsbBodyParams* const* params, VsbBodyState* const* pinned,
+                           const VsbHostPlan* const* plans, int n_steps);
+
 /* ---- multi-GPU: halo exchange over peer memory ----------------------------------------- *
  * Slab decomposition along x, one ghost layer per side (local extent grid.nx = nx_local + 2).  Replaces the
  * reference's vivsim/multidevice.py:13-38 (four lax.ppermute of the populations crossing a cut).  One kernel copies

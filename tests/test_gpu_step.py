@@ -313,6 +313,59 @@ def test_body_history_matches_reference_scan(golden):
         Stepper(spec, body=dict(body, n_dof=2), dyn_mode="device").set_f(f0).body_history()
 
 
+def test_host_ode_ensemble_matches_solo_runs(golden):
+    """Ensemble (vsb_run_host_ode_multi: several independent VIV domains, one host thread serving every body's ODE)
+    == each member run alone, and member 0 (the golden case) == the reference's per-step record."""
+    g = golden["recipes"]
+    spec, body, f0, (d, v, a), n = cases.viv(g)
+    from vivsim_b200 import Ensemble, Stepper
+    ref = g["viv_dvah"]
+    bodies = [dict(body, d0=d, v0=v, a0=a, n_dof=2, history=64),
+              dict(body, d0=d, v0=v, a0=a, n_dof=2, history=64, k=0.5 * body["k"]),          # other reduced velocity
+              dict(body, d0=(0.3, -0.2), v0=v, a0=a, n_dof=2, history=64, m=2.0 * body["m"])]
+    # (fuse_ib=False: the 64-marker test body would otherwise take the single-CTA IB kernel, which has no mailbox)
+    ens = Ensemble([Stepper(spec, body=dict(b), dyn_mode="host", follow=1, fuse_ib=False).set_f(f0) for b in bodies])
+    import os
+    ens.step(7)              # prologue + 6
+    os.environ["VSB_HOST_ODE_THREADS"] = "2"          # the rest with two host threads serving the three bodies
+    try:
+        ens.step(n - 7)
+    finally:
+        del os.environ["VSB_HOST_ODE_THREADS"]
+    for k, b in enumerate(bodies):
+        solo = Stepper(spec, body=dict(b), dyn_mode="host", follow=1, fuse_ib=False).set_f(f0)
+        solo.step(n)
+        st = ens.steppers[k]
+        assert st.n_steps == n and st.body_steps() == n
+        assert_close(N(st.get_f()), N(solo.get_f()), what=f"ensemble member {k} f")
+        for x, y, nm in zip(st.body_history(), solo.body_history(), ("d", "h")):
+            assert_close(x, y, rtol=1e-4, what=f"ensemble member {k} {nm} history")
+    dh, hh = ens.steppers[0].body_history()
+    assert_close(N(ens.steppers[0].get_f()), g["viv_f20"], what="ensemble member 0 vs golden f")
+    assert_close(dh, ref[:, 0:2], rtol=1e-4, what="ensemble member 0 vs golden d")
+    assert_close(hh, ref[:, 6:8], rtol=1e-4, what="ensemble member 0 vs golden h")
+    # runs of >= 32 steps replay each member's step as a CUDA graph: same result as launching kernel by kernel
+    long_n = 45
+    ens2 = Ensemble([Stepper(spec, body=dict(b), dyn_mode="host", follow=1, fuse_ib=False).set_f(f0) for b in bodies[:2]])
+    ens2.step(long_n)
+    os.environ["VSB_HOST_ODE_GRAPH"] = "0"
+    try:
+        for k in range(2):
+            solo = Stepper(spec, body=dict(bodies[k]), dyn_mode="host", follow=1, fuse_ib=False).set_f(f0)
+            solo.step(long_n)
+            assert ens2.steppers[k].body_steps() == long_n
+            assert_close(N(ens2.steppers[k].get_f()), N(solo.get_f()), what=f"graph replay member {k} f")
+            for x, y, nm in zip(ens2.steppers[k].body_history(), solo.body_history(), ("d", "h")):
+                assert_close(x, y, rtol=1e-4, what=f"graph replay member {k} {nm} history")
+    finally:
+        del os.environ["VSB_HOST_ODE_GRAPH"]
+    # members must be in the same state, eligible, and on distinct streams
+    with pytest.raises(ValueError):
+        Ensemble([Stepper(spec, body=dict(bodies[0]), dyn_mode="device", follow=1).set_f(f0)])
+    with pytest.raises(Exception):
+        Ensemble([ens.steppers[0], Stepper(spec, body=dict(bodies[0]), dyn_mode="host", follow=1, fuse_ib=False).set_f(f0)]).step(2)
+
+
 def test_checkpoint_restore_resumes_identically(golden, tmp_path):
     """Dump after 8 steps, restore into a fresh stepper (through a file), continue: same state as an uninterrupted run.
     Without a body the continuation is bit-identical; with one it agrees to the rounding of the fp32 atomics."""

@@ -6,6 +6,6 @@ there is no CPU fallback."""
 
 from . import dyn, ib, ib3d, lbm, lbm3d, multigrid, post  # noqa: F401
 from ._lib import LIB_PATH, VsbError, lib  # noqa: F401
-from .stepper import Stepper  # noqa: F401
+from .stepper import Ensemble, Stepper  # noqa: F401
 
 __version__ = "0.1.0"

@@ -7,6 +7,9 @@
 #include <chrono>
 #include <climits>
 #include <cstdlib>
+#include <string>
+#include <thread>
+#include <vector>
 
 #include "vsb_step.cuh"
 
@@ -291,7 +294,7 @@ __global__ void __launch_bounds__(kBlock, DIM == 3 ? 5 : 8) k_mdf_stage(const St
           volatile VsbHostMail* mail = p.host_mail;
           for (int c = 0; c < 3; ++c) mail->force[c] = __ldcg(&p.body->force_sum[c]);
           __threadfence_system();
-          mail->seq = p.mail_seq;
+          mail->seq = p.mail_seq >= 0 ? p.mail_seq : p.body->step + 1;   // < 0: the step being taken (graph replays)
         }
       }
     }
@@ -546,7 +549,7 @@ __global__ void __launch_bounds__(kTiledChunk, 3) k_mdf_stage_tiled(const MdfPar
           volatile VsbHostMail* mail = p.host_mail;
           for (int c = 0; c < 3; ++c) mail->force[c] = __ldcg(&p.body->force_sum[c]);
           __threadfence_system();
-          mail->seq = p.mail_seq;
+          mail->seq = p.mail_seq >= 0 ? p.mail_seq : p.body->step + 1;   // < 0: the step being taken (graph replays)
         }
       }
     }
@@ -733,76 +736,253 @@ static void host_body_update(VsbBodyState* pinned, const VsbBodyParams* bp, int 
   pinned->step += 1;
 }
 
-int vsb_run_host_ode(VsbStepArgs* a, VsbMdfArgs* mdf, const VsbBodyParams* bp, VsbBodyState* pinned,
-                     const VsbHostPlan* plan, int n_steps) {
-  VSB_REQUIRE(a && mdf && bp && pinned && plan, "vsb_run_host_ode: null argument");
-  VSB_REQUIRE(mdf->body != nullptr && mdf->host_mail != nullptr, "vsb_run_host_ode: needs a body state and a host mailbox");
-  VSB_REQUIRE(bp->n_dof >= 1 && bp->n_dof <= 3, "n_dof must be 1..3, got %d", bp->n_dof);
-  VSB_REQUIRE(a->do_stream && a->do_collide, "vsb_run_host_ode: full steps only");
-  cudaStream_t main = (cudaStream_t)plan->main, ib = (cudaStream_t)plan->ib, edge = (cudaStream_t)plan->edge;
-  cudaEvent_t fork = (cudaEvent_t)plan->ev_fork, ib_done = (cudaEvent_t)plan->ev_ib, edge_done = (cudaEvent_t)plan->ev_edge;
-  VSB_REQUIRE(ib && fork && ib_done, "vsb_run_host_ode: plan needs the ib stream and the fork / ib events");
-  const int has_edges = a->edges == 1 && a->n_post > 0;
-  if (has_edges) VSB_REQUIRE(edge && edge_done, "vsb_run_host_ode: plan needs the edge stream / event");
-  VsbHostMail* mail = mdf->host_mail;
-  volatile int* seq = &mail->seq;
+// One domain of vsb_run_host_ode_multi: what is enqueued for a step, and what happens when its force has arrived.
+namespace {
+struct HostOdeDomain {
+  VsbStepArgs* a; VsbMdfArgs* mdf; const VsbBodyParams* bp; VsbBodyState* pinned;
+  cudaStream_t main, ib, edge;
+  cudaEvent_t fork, ib_done, edge_done;
+  int has_edges, want, steps_done, in_flight;
+  cudaGraphExec_t graph[2];    // by step parity; null: launch kernel by kernel
+};
+
+// The device work of one step: IB chain (posts the force into the mailbox) and window band on `ib`, bulk on `main`,
+// wall layers on `edge`.  join = true (graph capture) also folds the side streams back into `main`.
+int host_ode_kernels(HostOdeDomain& d, bool join) {
+  VsbStepArgs* a = d.a; VsbMdfArgs* mdf = d.mdf;
   cudaError_t e;
   int rc;
-  for (int n = 0; n < n_steps; ++n) {
-    const int par = mdf->parity & 1;
-    a->parity = par;
-    a->g_win = mdf->g_win;
-    mdf->mail_seq = mail->next;
-    if ((e = cudaEventRecord(fork, main)) != cudaSuccess) return cuda_fail(e, "vsb_run_host_ode (fork)");
-    if ((e = cudaStreamWaitEvent(ib, fork, 0)) != cudaSuccess) return cuda_fail(e, "vsb_run_host_ode (fork)");
-    if ((rc = vsb_ib_mdf(a, mdf, nullptr, ib))) return rc;        // first: the host waits for this chain
-    a->band = 1;                                                   // the bulk runs while the host advances the body
-    if ((rc = vsb_step(a, main))) return rc;
-    if (has_edges) {
-      if ((e = cudaStreamWaitEvent(edge, fork, 0)) != cudaSuccess) return cuda_fail(e, "vsb_run_host_ode (edge fork)");
-      if ((rc = vsb_edge_fused(a, edge))) return rc;
-      if ((e = cudaEventRecord(edge_done, edge)) != cudaSuccess) return cuda_fail(e, "vsb_run_host_ode (edge join)");
+  const int par = mdf->parity & 1;
+  a->parity = par;
+  a->g_win = mdf->g_win;
+  if ((e = cudaEventRecord(d.fork, d.main)) != cudaSuccess) return cuda_fail(e, "vsb_run_host_ode (fork)");
+  if ((e = cudaStreamWaitEvent(d.ib, d.fork, 0)) != cudaSuccess) return cuda_fail(e, "vsb_run_host_ode (fork)");
+  if ((rc = vsb_ib_mdf(a, mdf, nullptr, d.ib))) return rc;        // first: the host waits for this chain
+  a->band = 1;                                                     // the bulk runs while the host advances the body
+  if ((rc = vsb_step(a, d.main))) return rc;
+  if (d.has_edges) {
+    if ((e = cudaStreamWaitEvent(d.edge, d.fork, 0)) != cudaSuccess) return cuda_fail(e, "vsb_run_host_ode (edge fork)");
+    if ((rc = vsb_edge_fused(a, d.edge))) return rc;
+    if ((e = cudaEventRecord(d.edge_done, d.edge)) != cudaSuccess) return cuda_fail(e, "vsb_run_host_ode (edge join)");
+  }
+  // The window band of THIS step needs the chain's force field but not the body update (the window origin it reads
+  // is the entry of this step's parity, written one step ago): enqueue it now, so that it runs while the force
+  // travels to the host and the new body state travels back.
+  a->band = 2;
+  if ((rc = vsb_step(a, d.ib))) return rc;
+  a->band = 0;
+  if (join) {
+    if ((e = cudaEventRecord(d.ib_done, d.ib)) != cudaSuccess) return cuda_fail(e, "vsb_run_host_ode (ib join)");
+    if ((e = cudaStreamWaitEvent(d.main, d.ib_done, 0)) != cudaSuccess) return cuda_fail(e, "vsb_run_host_ode (join)");
+    if (d.has_edges && (e = cudaStreamWaitEvent(d.main, d.edge_done, 0)) != cudaSuccess) return cuda_fail(e, "vsb_run_host_ode (join)");
+  }
+  return VSB_OK;
+}
+
+// next step: swap the population buffers and the parity-double-buffered IB fields
+void host_ode_flip(HostOdeDomain& d) {
+  VsbStepArgs* a = d.a; VsbMdfArgs* mdf = d.mdf;
+  const float* fi = a->f_in; a->f_in = a->f_out; a->f_out = const_cast<float*>(fi);
+  float* t = mdf->g_win; mdf->g_win = mdf->g_win_next; mdf->g_win_next = t;
+  t = mdf->scratch; mdf->scratch = mdf->scratch_next; mdf->scratch_next = t;
+  mdf->parity = (mdf->parity & 1) ^ 1;
+  a->parity = mdf->parity;
+  a->g_win = mdf->g_win;
+}
+
+int host_ode_enqueue(HostOdeDomain& d) {
+  VsbHostMail* mail = d.mdf->host_mail;
+  const int par = d.mdf->parity & 1;
+  if (d.graph[par]) {
+    // graph replay: the kernels post the number of the step being taken (device copy of the step counter + 1)
+    d.want = d.pinned->step + 1;
+    *reinterpret_cast<volatile int*>(&mail->seq) = -1;      // nothing in flight for this domain: no race with the device
+    cudaError_t e = cudaGraphLaunch(d.graph[par], d.main);
+    if (e != cudaSuccess) return cuda_fail(e, "vsb_run_host_ode (graph launch)");
+  } else {
+    d.mdf->mail_seq = mail->next;
+    d.want = d.mdf->mail_seq;
+    *reinterpret_cast<volatile int*>(&mail->seq) = -1;
+    if (int rc = host_ode_kernels(d, false)) return rc;
+  }
+  d.in_flight = 1;
+  return VSB_OK;
+}
+
+// The force of the step in flight has been posted: advance the body on the CPU, send the state back, close the step.
+int host_ode_complete(HostOdeDomain& d) {
+  VsbMdfArgs* mdf = d.mdf;
+  VsbHostMail* mail = mdf->host_mail;
+  cudaError_t e;
+  const int par = mdf->parity & 1;
+  mail->next = d.want + 1;
+  for (int c = 0; c < 3; ++c) d.pinned->force_sum[c] = mail->force[c];
+  host_body_update(d.pinned, d.bp, par);
+  if (d.graph[par]) {
+    // behind the whole step in `main` (the next step needs all of it anyway): two driver calls per step in total
+    if ((e = cudaMemcpyAsync(mdf->body, d.pinned, sizeof(VsbBodyState), cudaMemcpyHostToDevice, d.main)) != cudaSuccess)
+      return cuda_fail(e, "vsb_run_host_ode (host -> device)");
+  } else {
+    if ((e = cudaMemcpyAsync(mdf->body, d.pinned, sizeof(VsbBodyState), cudaMemcpyHostToDevice, d.ib)) != cudaSuccess)
+      return cuda_fail(e, "vsb_run_host_ode (host -> device)");
+    if ((e = cudaEventRecord(d.ib_done, d.ib)) != cudaSuccess) return cuda_fail(e, "vsb_run_host_ode (ib join)");
+    if ((e = cudaStreamWaitEvent(d.main, d.ib_done, 0)) != cudaSuccess) return cuda_fail(e, "vsb_run_host_ode (join)");
+    if (d.has_edges && (e = cudaStreamWaitEvent(d.main, d.edge_done, 0)) != cudaSuccess) return cuda_fail(e, "vsb_run_host_ode (join)");
+  }
+  host_ode_flip(d);
+  d.in_flight = 0;
+  d.steps_done += 1;
+  return VSB_OK;
+}
+
+// Record the step of both parities as CUDA graphs (the arguments alternate with the parity and with nothing else).
+// Called between steps, after the kernels have run at least once outside capture.
+int host_ode_capture(HostOdeDomain& d) {
+  cudaError_t e;
+  const int saved_seq = d.mdf->mail_seq;
+  d.mdf->mail_seq = -1;
+  int rc = VSB_OK;
+  for (int k = 0; k < 2 && rc == VSB_OK; ++k) {
+    const int par = d.mdf->parity & 1;
+    cudaGraph_t g = nullptr;
+    if ((e = cudaStreamBeginCapture(d.main, cudaStreamCaptureModeThreadLocal)) != cudaSuccess) {
+      rc = cuda_fail(e, "vsb_run_host_ode (begin capture)");
+      break;
     }
-    // wait for the force of this step (posted by the last CTA of the MDF chain)
-    const int want = mdf->mail_seq;
-    unsigned long long spins = 0;
-    std::chrono::steady_clock::time_point t0;
-    while (*seq != want) {
-      __builtin_ia32_pause();
-      if ((++spins & 0xffff) == 0) {             // every 64 K polls: is the device still alive, are we out of time?
-        if (spins == 0x10000) t0 = std::chrono::steady_clock::now();
-        e = cudaStreamQuery(ib);
+    rc = host_ode_kernels(d, true);
+    e = cudaStreamEndCapture(d.main, &g);
+    if (rc == VSB_OK && e != cudaSuccess) rc = cuda_fail(e, "vsb_run_host_ode (end capture)");
+    if (rc == VSB_OK && (e = cudaGraphInstantiate(&d.graph[par], g, 0)) != cudaSuccess) {
+      d.graph[par] = nullptr;
+      rc = cuda_fail(e, "vsb_run_host_ode (graph instantiate)");
+    }
+    if (g) cudaGraphDestroy(g);
+    host_ode_flip(d);
+  }
+  d.mdf->mail_seq = saved_seq;
+  if (rc != VSB_OK)
+    for (int k = 0; k < 2; ++k)
+      if (d.graph[k]) { cudaGraphExecDestroy(d.graph[k]); d.graph[k] = nullptr; }
+  return rc;
+}
+
+// Serve the domains i = first, first + stride, ... until each has taken n_steps steps.
+int host_ode_serve(HostOdeDomain* dom, int n_domains, int stride, int first, int n_steps, int graph_after) {
+  int rc;
+  long long remaining = 0;
+  for (int i = first; i < n_domains; i += stride) {
+    if ((rc = host_ode_enqueue(dom[i]))) return rc;
+    remaining += n_steps;
+  }
+  unsigned long long idle = 0;
+  std::chrono::steady_clock::time_point t0;
+  while (remaining > 0) {
+    bool progress = false;
+    for (int i = first; i < n_domains; i += stride) {
+      HostOdeDomain& d = dom[i];
+      if (!d.in_flight) continue;
+      if (*reinterpret_cast<volatile int*>(&d.mdf->host_mail->seq) != d.want) continue;
+      if ((rc = host_ode_complete(d))) return rc;
+      --remaining;
+      progress = true;
+      // long runs: after both parities have run once kernel by kernel, replay them as graphs
+      if (graph_after > 0 && d.steps_done == graph_after && n_steps - d.steps_done >= 2 && (rc = host_ode_capture(d))) return rc;
+      if (d.steps_done < n_steps && (rc = host_ode_enqueue(d))) return rc;
+    }
+    if (progress) { idle = 0; continue; }
+    __builtin_ia32_pause();
+    if ((++idle & 0xffff) == 0) {             // every 64 K empty rounds: is the device still alive, are we out of time?
+      if (idle == 0x10000) t0 = std::chrono::steady_clock::now();
+      for (int i = first; i < n_domains; i += stride) {
+        HostOdeDomain& d = dom[i];
+        if (!d.in_flight) continue;
+        cudaError_t e = cudaStreamQuery(d.ib);
         if (e != cudaSuccess && e != cudaErrorNotReady) return cuda_fail(e, "vsb_run_host_ode (waiting for the IB force)");
-        if (e == cudaSuccess && *seq != want) {
+        if (e == cudaSuccess && *reinterpret_cast<volatile int*>(&d.mdf->host_mail->seq) != d.want) {
           set_error("vsb_run_host_ode: the IB chain finished without posting the force");
           return VSB_ERR_CUDA;
         }
-        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(10)) {
-          set_error("vsb_run_host_ode: timed out waiting for the IB force");
-          return VSB_ERR_CUDA;
-        }
+      }
+      if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(10)) {
+        set_error("vsb_run_host_ode: timed out waiting for the IB force");
+        return VSB_ERR_CUDA;
       }
     }
-    mail->next = want + 1;
-    for (int c = 0; c < 3; ++c) pinned->force_sum[c] = mail->force[c];
-    host_body_update(pinned, bp, par);
-    if ((e = cudaMemcpyAsync(mdf->body, pinned, sizeof(VsbBodyState), cudaMemcpyHostToDevice, ib)) != cudaSuccess)
-      return cuda_fail(e, "vsb_run_host_ode (host -> device)");
-    a->band = 2;
-    if ((rc = vsb_step(a, ib))) return rc;
-    a->band = 0;
-    if ((e = cudaEventRecord(ib_done, ib)) != cudaSuccess) return cuda_fail(e, "vsb_run_host_ode (ib join)");
-    if ((e = cudaStreamWaitEvent(main, ib_done, 0)) != cudaSuccess) return cuda_fail(e, "vsb_run_host_ode (join)");
-    if (has_edges && (e = cudaStreamWaitEvent(main, edge_done, 0)) != cudaSuccess) return cuda_fail(e, "vsb_run_host_ode (join)");
-    // next step: swap the population buffers and the parity-double-buffered IB fields
-    const float* fi = a->f_in; a->f_in = a->f_out; a->f_out = const_cast<float*>(fi);
-    float* t = mdf->g_win; mdf->g_win = mdf->g_win_next; mdf->g_win_next = t;
-    t = mdf->scratch; mdf->scratch = mdf->scratch_next; mdf->scratch_next = t;
-    mdf->parity = par ^ 1;
   }
-  a->parity = mdf->parity;
-  a->g_win = mdf->g_win;
   return VSB_OK;
+}
+}  // namespace
+
+int vsb_run_host_ode_multi(int n_domains, VsbStepArgs* const* args, VsbMdfArgs* const* mdfs,
+                           const VsbBodyParams* const* params, VsbBodyState* const* pinned,
+                           const VsbHostPlan* const* plans, int n_steps) {
+  VSB_REQUIRE(n_domains >= 1 && n_domains <= 64, "vsb_run_host_ode_multi: n_domains must be 1..64, got %d", n_domains);
+  VSB_REQUIRE(args && mdfs && params && pinned && plans, "vsb_run_host_ode: null argument");
+  HostOdeDomain dom[64];
+  for (int i = 0; i < n_domains; ++i) {
+    HostOdeDomain& d = dom[i];
+    d.a = args[i]; d.mdf = mdfs[i]; d.bp = params[i]; d.pinned = pinned[i];
+    const VsbHostPlan* plan = plans[i];
+    VSB_REQUIRE(d.a && d.mdf && d.bp && d.pinned && plan, "vsb_run_host_ode: null argument");
+    VSB_REQUIRE(d.mdf->body != nullptr && d.mdf->host_mail != nullptr, "vsb_run_host_ode: needs a body state and a host mailbox");
+    VSB_REQUIRE(d.bp->n_dof >= 1 && d.bp->n_dof <= 3, "n_dof must be 1..3, got %d", d.bp->n_dof);
+    VSB_REQUIRE(d.a->do_stream && d.a->do_collide, "vsb_run_host_ode: full steps only");
+    d.main = (cudaStream_t)plan->main; d.ib = (cudaStream_t)plan->ib; d.edge = (cudaStream_t)plan->edge;
+    d.fork = (cudaEvent_t)plan->ev_fork; d.ib_done = (cudaEvent_t)plan->ev_ib; d.edge_done = (cudaEvent_t)plan->ev_edge;
+    VSB_REQUIRE(d.ib && d.fork && d.ib_done, "vsb_run_host_ode: plan needs the ib stream and the fork / ib events");
+    d.has_edges = d.a->edges == 1 && d.a->n_post > 0;
+    if (d.has_edges) VSB_REQUIRE(d.edge && d.edge_done, "vsb_run_host_ode: plan needs the edge stream / event");
+    for (int j = 0; j < i; ++j)
+      VSB_REQUIRE(dom[j].ib != d.ib && (n_domains == 1 || dom[j].main != d.main) && dom[j].mdf->host_mail != d.mdf->host_mail,
+                  "vsb_run_host_ode_multi: domains %d and %d share a stream or a mailbox", j, i);
+    d.want = 0; d.steps_done = 0; d.in_flight = 0;
+    d.graph[0] = d.graph[1] = nullptr;
+  }
+  if (n_steps <= 0) return VSB_OK;
+  // Host threads: one thread serves all domains by default.  VSB_HOST_ODE_THREADS = T gives each of T threads a fixed
+  // subset of the domains (launching kernel by kernel; measured on B200: no gain for eight 1024^2 domains, the
+  // driver serialises the launches).
+  int n_thr = 1;
+  if (const char* e = getenv("VSB_HOST_ODE_THREADS")) n_thr = atoi(e);
+  if (n_thr < 1) n_thr = 1;
+  if (n_thr > n_domains) n_thr = n_domains;
+  // Runs of >= 32 steps replay each domain's step as a CUDA graph (one per parity): two driver calls per step (graph
+  // launch, state copy) instead of about ten.  VSB_HOST_ODE_GRAPH=0 keeps launching kernel by kernel.
+  const char* ge = getenv("VSB_HOST_ODE_GRAPH");
+  const int graph_after = ((ge ? atoi(ge) != 0 : true) && n_steps >= 32 && n_thr == 1) ? 2 : 0;
+  auto cleanup = [&] {
+    for (int i = 0; i < n_domains; ++i)
+      for (int k = 0; k < 2; ++k)
+        if (dom[i].graph[k]) { cudaGraphExecDestroy(dom[i].graph[k]); dom[i].graph[k] = nullptr; }
+  };
+  if (n_thr == 1) {
+    const int rc1 = host_ode_serve(dom, n_domains, 1, 0, n_steps, graph_after);
+    cleanup();
+    return rc1;
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int rcs[64];
+  std::string msgs[64];
+  std::vector<std::thread> workers;
+  for (int t = 1; t < n_thr; ++t)
+    workers.emplace_back([&, t] {
+      cudaSetDevice(dev);
+      rcs[t] = host_ode_serve(dom, n_domains, n_thr, t, n_steps, graph_after);
+      if (rcs[t]) msgs[t] = vsb_last_error();      // the error string is thread-local: hand it to the caller's thread
+    });
+  rcs[0] = host_ode_serve(dom, n_domains, n_thr, 0, n_steps, graph_after);
+  for (auto& w : workers) w.join();
+  cleanup();
+  for (int t = 1; t < n_thr; ++t)
+    if (rcs[t]) { set_error("%s", msgs[t].c_str()); return rcs[t]; }
+  return rcs[0];
+}
+
+int vsb_run_host_ode(VsbStepArgs* a, VsbMdfArgs* mdf, const VsbBodyParams* bp, VsbBodyState* pinned,
+                     const VsbHostPlan* plan, int n_steps) {
+  VSB_REQUIRE(a && mdf && bp && pinned && plan, "vsb_run_host_ode: null argument");
+  return vsb_run_host_ode_multi(1, &a, &mdf, &bp, &pinned, &plan, n_steps);
 }
 
 int vsb_step_host_ode(VsbStepArgs* a, const VsbMdfArgs* mdf, const VsbBodyParams* bp, VsbBodyState* pinned,

@@ -588,11 +588,9 @@ class Stepper:
         return (self.overlap and self.ib is not None and self.body is not None and self.dyn_mode == "host"
                 and self.halo is None and not self.ib_fused and (a.n_post == 0 or self.edge_fused))
 
-    def _run_host_ode(self, n):
-        """n whole steps with the rigid-body ODE on the host in one C call (vsb_run_host_ode): the host loop, the
-        mailbox polling and the Newmark update all happen in C; Python only flips its buffer / parity bookkeeping."""
+    def _host_ode_prepare(self, main):
+        """Argument blocks of the first step of a vsb_run_host_ode[_multi] call whose bulk runs on stream `main`."""
         a, m = self._args, self._mdf
-        main = torch.cuda.current_stream()
         src, dst = self._bufs[self._cur], self._bufs[1 - self._cur]
         a.f_in, a.f_out = src.data_ptr(), dst.data_ptr()
         a.do_stream, a.do_collide = 1, 1
@@ -615,11 +613,20 @@ class Stepper:
             m.scratch, m.scratch_next = buf[par, 1].data_ptr(), buf[par ^ 1, 1].data_ptr()
         m.u_win = None
         a.g_win = m.g_win
-        L.check(L.lib().vsb_run_host_ode(C.byref(a), C.byref(m), C.byref(self._hparams),
-                                         C.c_void_p(self._body_pin.data_ptr()), C.byref(self._plan), int(n)))
+
+    def _host_ode_finish(self, n):
+        """Python-side bookkeeping after n steps taken inside vsb_run_host_ode[_multi]."""
         self._cur = (self._cur + n) % 2
-        self._parity = (par + n) % 2
+        self._parity = (self._parity + n) % 2
         self._g_win = self._ib_buf[self._parity, 0]
+
+    def _run_host_ode(self, n):
+        """n whole steps with the rigid-body ODE on the host in one C call (vsb_run_host_ode): the host loop, the
+        mailbox polling and the Newmark update all happen in C; Python only flips its buffer / parity bookkeeping."""
+        self._host_ode_prepare(torch.cuda.current_stream())
+        L.check(L.lib().vsb_run_host_ode(C.byref(self._args), C.byref(self._mdf), C.byref(self._hparams),
+                                         C.c_void_p(self._body_pin.data_ptr()), C.byref(self._plan), int(n)))
+        self._host_ode_finish(n)
 
     def _ib_part(self, st):
         """Immersed-boundary force of this pass on stream `st`, then the body update."""
@@ -716,3 +723,64 @@ class Stepper:
             if self._body_dev is not None:
                 self._body_dev.copy_(ib_keep[2])
         self._graph = g
+
+
+class Ensemble:
+    """Independent simulations advanced together on one GPU, each with its rigid-body ODE on the host
+    (vsb_run_host_ode_multi) -- e.g. the reduced-velocity sweep of a VIV study, every case being one run of the
+    reference's examples/2d/vortex_induced_vibration.py.  One host thread serves all bodies: whichever domain's IB
+    force has arrived gets its Newmark update (dyn.py:5-51) and its next step, so the device always has other
+    domains' kernels to run while one waits for the host.
+
+        ens = Ensemble([Stepper(spec_k, body=body_k, dyn_mode="host").set_f(f0_k) for k in range(8)])
+        ens.step(1000)
+        d, h = ens.steppers[3].body_state()
+    """
+
+    def __init__(self, steppers):
+        self.steppers = list(steppers)
+        if not 1 <= len(self.steppers) <= 64:
+            raise ValueError("an Ensemble holds 1..64 steppers")
+        dev = self.steppers[0].device
+        for st in self.steppers:
+            if not isinstance(st, Stepper) or st.device != dev:
+                raise ValueError("all members must be Steppers on the same device")
+            if not st._host_ode_eligible():
+                raise ValueError("every member needs an immersed body with dyn_mode='host', overlap on, no halo and "
+                                 "face operations the fused wall blocks support")
+        self._mains = [torch.cuda.Stream(device=dev) for _ in self.steppers]
+
+    def step(self, n=1):
+        """Advance every member n reference time steps."""
+        n = int(n)
+        if n <= 0:
+            return self
+        kinds = {st._kind for st in self.steppers}
+        if None in kinds:
+            raise L.VsbError("no state loaded: call set_f(f) on every member first")
+        if len(kinds) != 1:
+            raise L.VsbError("members are in different states: step them to the same point first")
+        if kinds == {"F"}:              # prologue S_0 = collide(F_0), counted as the first step like Stepper.step
+            for st in self.steppers:
+                st.step(1)
+            n -= 1
+            if n == 0:
+                return self
+        cur = torch.cuda.current_stream()
+        k = len(self.steppers)
+        for st, main in zip(self.steppers, self._mains):
+            main.wait_stream(cur)
+            st._host_ode_prepare(main)
+        args = (C.POINTER(L.VsbStepArgs) * k)(*[C.pointer(st._args) for st in self.steppers])
+        mdfs = (C.POINTER(L.VsbMdfArgs) * k)(*[C.pointer(st._mdf) for st in self.steppers])
+        params = (C.POINTER(L.VsbBodyParams) * k)(*[C.pointer(st._hparams) for st in self.steppers])
+        pinned = (C.c_void_p * k)(*[st._body_pin.data_ptr() for st in self.steppers])
+        plans = (C.POINTER(L.VsbHostPlan) * k)(*[C.pointer(st._plan) for st in self.steppers])
+        rc = L.lib().vsb_run_host_ode_multi(k, args, mdfs, params, pinned, plans, n)
+        for st, main in zip(self.steppers, self._mains):
+            cur.wait_stream(main)
+        L.check(rc)
+        for st in self.steppers:
+            st._host_ode_finish(n)
+            st.n_steps += n
+        return self
