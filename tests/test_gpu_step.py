@@ -359,6 +359,19 @@ def test_host_ode_ensemble_matches_solo_runs(golden):
                 assert_close(x, y, rtol=1e-4, what=f"graph replay member {k} {nm} history")
     finally:
         del os.environ["VSB_HOST_ODE_GRAPH"]
+    # a solo run replays graphs too when it is driven from a capturable stream; on the legacy default stream it keeps
+    # launching kernel by kernel -- same result either way
+    import torch
+    for side in (torch.cuda.Stream(), None):
+        solo = Stepper(spec, body=dict(bodies[0]), dyn_mode="host", follow=1, fuse_ib=False).set_f(f0)
+        if side is not None:
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                solo.step(long_n)
+            torch.cuda.current_stream().wait_stream(side)
+        else:
+            solo.step(long_n)
+        assert_close(N(solo.get_f()), N(ens2.steppers[0].get_f()), what="solo graph replay f")
     # members must be in the same state, eligible, and on distinct streams
     with pytest.raises(ValueError):
         Ensemble([Stepper(spec, body=dict(bodies[0]), dyn_mode="device", follow=1).set_f(f0)])

@@ -838,10 +838,12 @@ int host_ode_complete(HostOdeDomain& d) {
 // Record the step of both parities as CUDA graphs (the arguments alternate with the parity and with nothing else).
 // Called between steps, after the kernels have run at least once outside capture.
 int host_ode_capture(HostOdeDomain& d) {
+  // the legacy default stream cannot be captured: such a domain keeps launching kernel by kernel
+  if (d.main == nullptr || d.main == cudaStreamLegacy || d.main == cudaStreamPerThread) return VSB_OK;
   cudaError_t e;
   const int saved_seq = d.mdf->mail_seq;
   d.mdf->mail_seq = -1;
-  int rc = VSB_OK;
+  int rc = VSB_OK, flips = 0;
   for (int k = 0; k < 2 && rc == VSB_OK; ++k) {
     const int par = d.mdf->parity & 1;
     cudaGraph_t g = nullptr;
@@ -858,11 +860,17 @@ int host_ode_capture(HostOdeDomain& d) {
     }
     if (g) cudaGraphDestroy(g);
     host_ode_flip(d);
+    ++flips;
   }
+  if (flips & 1) host_ode_flip(d);          // leave the arguments at the parity they came with
   d.mdf->mail_seq = saved_seq;
-  if (rc != VSB_OK)
+  if (rc != VSB_OK) {
+    // not capturable here (e.g. a stream that is already part of another capture): carry on kernel by kernel
     for (int k = 0; k < 2; ++k)
       if (d.graph[k]) { cudaGraphExecDestroy(d.graph[k]); d.graph[k] = nullptr; }
+    cudaGetLastError();
+    rc = VSB_OK;
+  }
   return rc;
 }
 
