@@ -53,6 +53,25 @@ def test_validation_errors_without_gpu(lib):
     assert rc == -1 and b"MRT needs op_host" in lib.vsb_last_error()
 
 
+def test_host_ode_runner_validates_before_touching_the_device(lib):
+    """vsb_run_host_ode / _multi: argument checks come first and fail with a message (no GPU needed to see them)."""
+    assert lib.vsb_run_host_ode(None, None, None, None, None, 4) == -1
+    assert b"null argument" in lib.vsb_last_error()
+    assert lib.vsb_run_host_ode_multi(0, None, None, None, None, None, 4) == -1
+    assert b"n_domains must be 1..64" in lib.vsb_last_error()
+    assert lib.vsb_run_host_ode_multi(65, None, None, None, None, None, 4) == -1
+    assert lib.vsb_run_host_ode_multi(2, None, None, None, None, None, 4) == -1
+    assert b"null argument" in lib.vsb_last_error()
+    # a domain without a body state / mailbox is refused
+    from vivsim_b200 import _lib
+    a, m, bp, plan = _lib.VsbStepArgs(), _lib.VsbMdfArgs(), _lib.VsbBodyParams(), _lib.VsbHostPlan()
+    pinned = (ctypes.c_float * 23)()
+    arr = lambda t, x: (ctypes.POINTER(t) * 1)(ctypes.pointer(x))
+    rc = lib.vsb_run_host_ode_multi(1, arr(_lib.VsbStepArgs, a), arr(_lib.VsbMdfArgs, m), arr(_lib.VsbBodyParams, bp),
+                                    (ctypes.c_void_p * 1)(ctypes.addressof(pinned)), arr(_lib.VsbHostPlan, plan), 4)
+    assert rc == -1 and b"needs a body state and a host mailbox" in lib.vsb_last_error()
+
+
 def test_python_api_rejects_cpu_tensors(lib):
     from vivsim_b200 import VsbError, lbm
     with pytest.raises(VsbError):
