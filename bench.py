@@ -299,9 +299,11 @@ def run_ours(args):
     if world > 1 and dt < 0.5:
         # short timed region on N GPUs: every rank runs the same untimed follow-up loop (~1.5 s; dt is the max over ranks,
         # so the step count is identical everywhere) while rank 0 samples the clocks
+        per_replay = len(steppers) * steps_each
         n_follow = int(min(1.5 / max(dt / K, 1e-7), 2e6))
+        n_follow = max(n_follow - n_follow % per_replay, per_replay)        # whole graph replays only
         t_a = time.time()
-        loop(max(n_follow, len(steppers)))
+        loop(n_follow)
         sync()
         if sampler:
             clocks = sampler.summary(t_a, time.time())
