@@ -114,3 +114,27 @@ def test_host_dyn_and_geometry(golden):
     assert_close(ib3d.get_ds(gi["verts"], gi["faces"]), gi["ds3"])
     assert_close(ib3d.get_volume(gi["verts"], gi["faces"]), gi["volume"])
     assert_close(ib3d.get_surface_area(gi["verts"], gi["faces"]), gi["surf_area"])
+
+
+def test_reference_submodule_import_paths():
+    """`from vivsim.ib.kernels import kernel_peskin_4pt`-style imports (used by the reference's own ib3d package and by
+    its examples) resolve to the same objects as the package-level names."""
+    import importlib
+    import vivsim_b200
+    paths = {"lbm": ["basic", "collision.kbc", "collision.mrt", "collision.reg", "forcing.guo", "forcing.edm",
+                     "boundary.bb", "boundary.cbc", "boundary.eq", "boundary.nebb", "boundary.nee"],
+             "ib": ["kernels", "stencil", "mdf", "geometry"], "ib3d": ["stencil", "geometry"]}
+    paths["lbm3d"] = paths["lbm"]
+    n = 0
+    for pkg, subs in paths.items():
+        top = getattr(vivsim_b200, pkg)
+        for sub in subs:
+            mod = importlib.import_module(f"vivsim_b200.{pkg}.{sub}")
+            names = [k for k in vars(mod) if not k.startswith("_")]
+            assert names, f"{mod.__name__} exports nothing"
+            for k in names:
+                assert getattr(mod, k) is getattr(top, k)
+                n += 1
+    assert n >= 60
+    from vivsim_b200.lbm.boundary.nebb import boundary_velocity_nebb, boundary_force_corrected_nebb  # noqa: F401
+    from vivsim_b200.ib.mdf import multi_direct_forcing  # noqa: F401

@@ -1,0 +1,7 @@
+"""Import path of the reference's vivsim/ib/geometry.py: the same public names, implemented in vivsim_b200.ib
+(C ABI underneath, include/vivsim_b200.h)."""
+
+from vivsim_b200.ib import (  # noqa: F401
+    get_area,
+    get_ds,
+)

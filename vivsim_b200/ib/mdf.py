@@ -1,0 +1,6 @@
+"""Import path of the reference's vivsim/ib/mdf.py: the same public names, implemented in vivsim_b200.ib
+(C ABI underneath, include/vivsim_b200.h)."""
+
+from vivsim_b200.ib import (  # noqa: F401
+    multi_direct_forcing,
+)

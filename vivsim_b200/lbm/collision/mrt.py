@@ -1,0 +1,7 @@
+"""Import path of the reference's vivsim/lbm/collision/mrt.py: the same public names, implemented in vivsim_b200.lbm
+(C ABI underneath, include/vivsim_b200.h)."""
+
+from vivsim_b200.lbm import (  # noqa: F401
+    get_mrt_collision_operator,
+    collision_mrt,
+)

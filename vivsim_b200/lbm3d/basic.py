@@ -1,0 +1,11 @@
+"""Import path of the reference's vivsim/lbm3d/basic.py: the same public names, implemented in vivsim_b200.lbm3d
+(C ABI underneath, include/vivsim_b200.h)."""
+
+from vivsim_b200.lbm3d import (  # noqa: F401
+    streaming,
+    get_macroscopic,
+    get_equilibrium,
+    collision_bgk,
+    get_omega,
+    get_velocity_correction,
+)

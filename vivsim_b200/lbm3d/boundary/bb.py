@@ -1,0 +1,8 @@
+"""Import path of the reference's vivsim/lbm3d/boundary/bb.py: the same public names, implemented in vivsim_b200.lbm3d
+(C ABI underneath, include/vivsim_b200.h)."""
+
+from vivsim_b200.lbm3d import (  # noqa: F401
+    boundary_bounce_back,
+    boundary_specular_reflection,
+    obstacle_bounce_back,
+)

@@ -1,0 +1,7 @@
+"""Import path of the reference's vivsim/lbm3d/collision/mrt.py: the same public names, implemented in vivsim_b200.lbm3d
+(C ABI underneath, include/vivsim_b200.h)."""
+
+from vivsim_b200.lbm3d import (  # noqa: F401
+    get_mrt_collision_operator,
+    collision_mrt,
+)

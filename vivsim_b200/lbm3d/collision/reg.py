@@ -1,0 +1,6 @@
+"""Import path of the reference's vivsim/lbm3d/collision/reg.py: the same public names, implemented in vivsim_b200.lbm3d
+(C ABI underneath, include/vivsim_b200.h)."""
+
+from vivsim_b200.lbm3d import (  # noqa: F401
+    collision_reg,
+)
