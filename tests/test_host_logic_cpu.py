@@ -1,0 +1,67 @@
+"""CPU: host-side logic of the hot path that needs no device -- the marker ordering / chunk cutting that feeds the tiled
+MDF kernel, and the BASELINE workload generators."""
+
+import numpy as np
+
+from vivsim_b200 import configs
+from vivsim_b200.stepper import TILE_CELLS, TILE_CHUNK, TILE_COLUMN, cut_marker_chunks
+
+
+def check_chunks(markers, perm, offsets):
+    m = markers.shape[0]
+    assert sorted(perm.tolist()) == list(range(m)), "perm is not a permutation"
+    assert offsets.dtype == np.int32 and offsets[0] == 0 and offsets[-1] == m
+    sizes = np.diff(offsets)
+    assert sizes.min() >= 1 and sizes.max() <= TILE_CHUNK
+    srt = markers[perm]
+    worst = 0
+    for a, b in zip(offsets[:-1], offsets[1:]):
+        c = srt[a:b]
+        col = np.floor(c[:, :2] / TILE_COLUMN)
+        assert (col == col[0]).all(), "a chunk spans more than one column"
+        assert (np.diff(c[:, 2]) >= 0).all(), "markers of a chunk are not z-sorted"
+        # bounding box of the 4-point stencils (floor(x) - 1 .. floor(x) + 2), + 1 cell per axis for a moving body
+        lo = np.floor(c).min(axis=0) - 1
+        hi = np.floor(c).max(axis=0) + 2
+        ext = (hi - lo + 1) + 1
+        worst = max(worst, int(np.prod(ext)))
+    assert worst <= TILE_CELLS, f"a chunk's box needs {worst} cells"
+
+
+def test_chunks_of_the_c5_cylinder_fit_the_tile():
+    spec, _ = configs.oscillating_cylinder_3d()                       # BASELINE config 4: 695 570 markers
+    markers = np.asarray(spec["ib"]["markers"], dtype=np.float32)
+    assert markers.shape == (695570, 3)
+    perm, offsets = cut_marker_chunks(markers)
+    check_chunks(markers, perm, offsets)
+    assert len(offsets) - 1 == 3496                                   # the grid size in profiles/r01_ncu_full_k_mdf_stage_tiled_c5_final.txt
+
+
+def test_chunks_of_ragged_marker_sets():
+    rng = np.random.default_rng(0)
+    for n, box in ((1, 30.0), (7, 3.0), (481, 20.0), (5000, 40.0), (3000, 2.0)):
+        markers = (rng.random((n, 3)) * box + 8.0).astype(np.float32)
+        markers[:, 2] *= 4.0                                          # long in z: forces z cuts as well as 256-marker cuts
+        perm, offsets = cut_marker_chunks(markers)
+        check_chunks(markers, perm, offsets)
+    # one column, one z: the 256-marker limit alone cuts it
+    markers = np.tile(np.array([[9.5, 9.5, 20.25]], dtype=np.float32), (1000, 1))
+    perm, offsets = cut_marker_chunks(markers)
+    check_chunks(markers, perm, offsets)
+    assert np.diff(offsets).tolist() == [256, 256, 256, 232]
+
+
+def test_baseline_workload_generators():
+    spec, body = configs.viv_cylinder_2d()                            # C2
+    assert spec["shape"] == (1024, 1024) and spec["ib"]["markers"].shape == (512, 2) and spec["ib"]["n_iter"] == 5
+    assert spec["collision"] == "bgk" and spec["forcing"] == "guo" and body is not None
+    spec, _ = configs.sphere_3d()                                     # C3
+    assert spec["shape"] == (256, 256, 256) and spec["ib"]["markers"].shape == (2562, 3) and spec["collision"] == "kbc"
+    spec, _ = configs.viv_cylinder_2d_large()                         # C4
+    assert spec["shape"] == (16384, 16384) and spec["collision"] == "kbc"
+    for sp in (spec,):
+        (ox, oy), (sx, sy) = sp["ib"]["window"]
+        mk = np.asarray(sp["ib"]["markers"])
+        # every 4-point stencil lies inside the window (the reference leaves out-of-range indices undefined)
+        assert np.floor(mk[:, 0]).min() - 1 >= ox and np.floor(mk[:, 0]).max() + 2 < ox + sx
+        assert np.floor(mk[:, 1]).min() - 1 >= oy and np.floor(mk[:, 1]).max() + 2 < oy + sy

@@ -40,6 +40,41 @@ def _parse_bc(name):
     return name, ""
 
 
+TILE_CHUNK = 256          # markers per CTA of the tiled MDF kernel (kTiledChunk in csrc/vsb_ib.cu)
+TILE_CELLS = 2304         # cells of its shared-memory box (kTileCells)
+TILE_COLUMN = 4           # markers of one chunk share a TILE_COLUMN x TILE_COLUMN column of cells in (x, y)
+
+
+def cut_marker_chunks(markers):
+    """Storage order and chunk boundaries of a dense 3-D marker set for the tiled MDF kernel (host logic, NumPy only).
+
+    Markers are sorted by (x column of 4 cells, y column of 4 cells, z); the sorted list is cut into chunks of at most
+    TILE_CHUNK markers of ONE column whose z range keeps the chunk's bounding box -- column 4 + stencil 3 + 1 for a
+    moving body = 8 cells in x and in y, z extent = span + 4 stencil cells + 1 margin -- within TILE_CELLS cells.
+    Returns (perm, offsets): `markers[perm]` is the storage order, chunk c holds sorted markers
+    [offsets[c], offsets[c + 1]) (int32, offsets[0] = 0, offsets[-1] = M)."""
+    markers = np.asarray(markers, dtype=np.float32)
+    col = np.floor(markers[:, :2] / float(TILE_COLUMN)).astype(np.int64)
+    perm = np.lexsort((markers[:, 2], col[:, 1], col[:, 0]))
+    srt = markers[perm]
+    col = col[perm]
+    key = col[:, 0] * (1 << 32) + col[:, 1]
+    starts = np.flatnonzero(np.r_[True, key[1:] != key[:-1]])
+    ends = np.r_[starts[1:], key.size]
+    box_xy = TILE_COLUMN + 4
+    z_span = TILE_CELLS // (box_xy * box_xy) - 5
+    offsets = [0]
+    for s_, e_ in zip(starts, ends):
+        z = srt[s_:e_, 2]
+        pos = 0
+        while pos < e_ - s_:
+            stop = min(pos + TILE_CHUNK, int(np.searchsorted(z, z[pos] + z_span, side="left")))
+            stop = max(stop, pos + 1)
+            offsets.append(s_ + stop)
+            pos = stop
+    return perm, np.asarray(offsets, dtype=np.int32)
+
+
 class Stepper:
     def __init__(self, spec, device="cuda", rows=None, vec=0, body=None, dyn_mode="host", follow=1, use_graph=False,
                  fuse_ib=True, fuse_edges=True, overlap=True, buffers=None):
@@ -201,30 +236,13 @@ class Stepper:
         # (x column of 4 cells, y column of 4 cells, z).  Outputs are handed back in the caller's order.
         self._perm = self._inv_perm = None
         if dim == 3 and self._use_uwin and self.n_markers > 480 and ib.get("sort_markers", True):
-            col = np.floor(markers[:, :2] / 4.0).astype(np.int64)
-            perm = np.lexsort((markers[:, 2], col[:, 1], col[:, 0]))
+            perm, offsets = cut_marker_chunks(markers)
             inv = np.empty_like(perm)
             inv[perm] = np.arange(perm.size)
             markers = np.ascontiguousarray(markers[perm])
             self._perm = torch.as_tensor(perm, device=dev)
             self._inv_perm = torch.as_tensor(inv, device=dev)
-            # cut the sorted list into chunks of <= 256 markers of ONE column whose z range keeps the chunk's bounding
-            # box (column 4 + stencil 3 + 1 for a moving body = 8 cells in x and y) within the 2304-cell tile
-            col = col[perm]
-            key = col[:, 0] * (1 << 32) + col[:, 1]
-            starts = np.flatnonzero(np.r_[True, key[1:] != key[:-1]])
-            ends = np.r_[starts[1:], key.size]
-            z_span = 2304 // 64 - 5                   # box z extent = span + 4 stencil cells + 1 margin
-            offsets = [0]
-            for s_, e_ in zip(starts, ends):
-                z = markers[s_:e_, 2]
-                pos = 0
-                while pos < e_ - s_:
-                    stop = min(pos + 256, int(np.searchsorted(z, z[pos] + z_span, side="left")))
-                    stop = max(stop, pos + 1)
-                    offsets.append(s_ + stop)
-                    pos = stop
-            self._chunk_offsets = torch.as_tensor(np.asarray(offsets, dtype=np.int32), device=dev)
+            self._chunk_offsets = torch.as_tensor(offsets, device=dev)
         self._markers = torch.as_tensor(markers, device=dev)
         # force field [0] and per-iteration work fields [1:], double-buffered by step parity: each step clears the
         # set the next step will accumulate into (see vsb_ib_mdf), so there is no memset on the step path
