@@ -1,88 +1,33 @@
 """CPU: the oracle reproduces the analytic answers the reference's examples compare against (SURVEY.md section 4:
 Taylor-Green decay, Couette profile, the four Poiseuille recipes, ABC flow).  The reference ships no tests; these
-known-answer cases pin the physics of the restated algorithm next to the fixtures that pin its arithmetic."""
+known-answer cases pin the physics of the restated algorithm next to the fixtures that pin its arithmetic.
+tests/test_gpu_z_analytic.py runs the same cases through the CUDA stepper."""
 
-import numpy as np
 import pytest
 
-from oracle import lbm, lbm3d, recipes
-
-F32 = np.float32
-
-
-def rel_l2(a, b):
-    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+import analytic_cases as ac
+from oracle import recipes
 
 
-def test_taylor_green_vortex_decay():
-    """examples/2d/taylor_green_vortex.py:28-56: u(t) = u(0) exp(-nu k^2 t), energy ~ exp(-2 nu k^2 t)."""
-    n, u0, nu, steps = 64, 0.02, 0.02, 600
-    k = 2 * np.pi / n
-    x = np.arange(n, dtype=F32)[:, None]
-    y = np.arange(n, dtype=F32)[None, :]
+def run(case):
+    spec, f0, steps, check = case
+    f, _ = recipes.run(spec, f0, steps)
+    check(f)
 
-    def exact(t):
-        d = np.exp(-nu * 2 * k * k * t)
-        return np.stack([u0 * np.sin(k * x) * np.cos(k * y) * d, -u0 * np.cos(k * x) * np.sin(k * y) * d]).astype(F32)
 
-    spec = dict(dim=2, shape=(n, n), collision="bgk", omega=lbm.get_omega(nu), forcing=None, post=[])
-    # (a) initialised as the example does (rho = 1: the missing pressure field rings acoustically, ~1 % of |u|),
-    # (b) with the exact solution's pressure field rho = 1 + 3 p
-    p0 = (-u0 * u0 / 4.0 * (np.cos(2 * k * x) + np.cos(2 * k * y))).astype(F32)
-    for rho0, tol in ((np.ones((n, n), F32), 1.5e-2), ((1.0 - 3.0 * p0).astype(F32), 3e-3)):
-        f, _ = recipes.run(spec, lbm.get_equilibrium(rho0, exact(0)), steps)
-        rho, u = lbm.get_macroscopic(f)
-        assert rel_l2(u, exact(steps)) < tol
-        e0, e1 = np.mean(exact(0) ** 2), np.mean(u ** 2)
-        assert abs(e1 / e0 / np.exp(-2 * nu * 2 * k * k * steps) - 1) < 6e-3
-        assert abs(float(rho.mean()) - float(rho0.mean())) < 2e-5          # mass is conserved (to fp32 accumulation over 600 steps)
+@pytest.mark.parametrize("prepared", [False, True])
+def test_taylor_green_vortex_decay(prepared):
+    run(ac.taylor_green(prepared))
 
 
 def test_couette_profile():
-    """examples/2d/couette_flow.py:51-91: BGK + NEE walls, linear profile U0 y / (NY - 1)."""
-    n, u0, nu, steps = 16, 0.08, 0.1, 6000
-    spec = dict(dim=2, shape=(n, n), collision="bgk", omega=lbm.get_omega(nu), forcing=None,
-                post=[("nee", "bottom", {}), ("nee", "top", {"ux_wall": u0})])
-    f = lbm.get_equilibrium(np.ones((n, n), F32), np.zeros((2, n, n), F32))
-    f, _ = recipes.run(spec, f, steps)
-    _, u = lbm.get_macroscopic(f)
-    exact = np.broadcast_to(u0 * np.arange(n, dtype=F32) / (n - 1), (n, n))
-    assert rel_l2(u[0], exact) < 1e-3
-    assert np.abs(u[1]).max() < 1e-6
+    run(ac.couette())
 
 
-@pytest.mark.parametrize("kind", ["bgk_edm", "bgk_guo", "mrt_guo", "kbc_edm"])
+@pytest.mark.parametrize("kind", ac.POISEUILLE_KINDS)
 def test_poiseuille_profile(kind):
-    """examples/2d/poiseuille_channel.py:80-148,176-181: the four collision / forcing recipes against
-    g / (2 nu) y (H - y), H = NY - 1, with the half-force velocity correction applied to the output."""
-    nx = ny = 10
-    nu, gx, steps = 0.2, 1e-3, 3000                      # 3000 steps = 7 viscous times H^2 / nu
-    coll, forcing = kind.split("_")
-    spec = dict(dim=2, shape=(nx, ny), collision=coll, omega=lbm.get_omega(nu), forcing=forcing, g=(gx, 0.0),
-                post=[("force_corrected_nebb", "top", {"gx_wall": gx}), ("force_corrected_nebb", "bottom", {"gx_wall": gx})])
-    u_init = np.zeros((2, nx, ny), F32)
-    u_init[0] = -gx / 2
-    f = lbm.get_equilibrium(np.ones((nx, ny), F32), u_init)
-    f, _ = recipes.run(spec, f, steps)
-    rho, u = lbm.get_macroscopic(f)
-    ux = u[0] + gx / (2 * rho)
-    yy = np.arange(ny, dtype=F32)
-    h = ny - 1
-    exact = gx / (2 * nu) * yy * (h - yy)
-    assert np.abs(ux[nx // 2] - exact).max() < 2e-3 * exact.max()
-    assert np.abs(ux - ux[0]).max() < 1e-6               # uniform along the periodic direction
+    run(ac.poiseuille(kind))
 
 
 def test_abc_flow_decay():
-    """examples/3d/abc_flow.py:59-68,128-130: regularised collision, velocity decays as exp(-nu k^2 t)."""
-    n, u0, nu, steps = 32, 0.02, 0.005, 200
-    k = 2 * np.pi / n
-    x, y, z = np.meshgrid(*(np.arange(n, dtype=F32),) * 3, indexing="ij")
-    a = b = c = u0
-    u_init = np.stack([a * np.sin(k * z) + c * np.cos(k * y), b * np.sin(k * x) + a * np.cos(k * z),
-                       c * np.sin(k * y) + b * np.cos(k * x)]).astype(F32)
-    f = lbm3d.get_equilibrium(np.ones((n, n, n), F32), u_init)
-    spec = dict(dim=3, shape=(n, n, n), collision="reg", omega=lbm3d.get_omega(nu), forcing=None, post=[])
-    f, _ = recipes.run(spec, f, steps)
-    _, u = lbm3d.get_macroscopic(f)
-    assert rel_l2(u, u_init * np.exp(-nu * k * k * steps)) < 2e-2
+    run(ac.abc_flow())
