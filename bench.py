@@ -35,8 +35,9 @@ METRIC = "MLUPS (IB-LBM step, D2Q9 1024x1024 VIV cylinder, 512 markers, MDF + Gu
 L2_BYTES = 126e6
 # ensemble members: overlap the IB chain with the bulk inside each domain (the domains overlap each other either way)
 ENSEMBLE_OVERLAP = os.environ.get("VSB_BENCH_OVERLAP", "1") != "0"
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_step<2,BGK,vec4> launch at 1024^2 (ncu --set full, profiles/)
-TRAFFIC_NCU = 39.4e6   # 37.88 MB read + 1.5 MB written to DRAM during the launch (the rest of the writes leave L2 later)
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_step<2,BGK,vec4> launch at 1024^2 (ncu --set full,
+# profiles/r01_ncu_full_k_step_c2_final.txt: the 1181-block launch of the bench command)
+TRAFFIC_NCU = 39.0e6   # 37.71 MB read + 1.28 MB written to DRAM during the launch (the rest of the writes leave L2 later)
 
 
 def peaks():
