@@ -298,6 +298,10 @@ class Stepper:
                 raise ValueError("dyn_mode must be 'host' or 'device'")
             self.follow = int(follow)
             self.n_dof = int(body.get("n_dof", 2))
+            if not 1 <= self.n_dof <= dim:
+                # the fused path moves the markers by translation only; rotation (the third degree of freedom of
+                # dyn.newmark_3dof in 2-D, dyn.py:84-120) is available through the vivsim_b200.dyn functions
+                raise ValueError(f"body['n_dof'] must be 1..{dim} translational degrees of freedom in {dim}-D, got {self.n_dof}")
             bp = L.VsbBodyParams()
             bp.n_dof, bp.follow = (self.n_dof if dyn_mode == "device" else 0), self.follow
             bp.m, bp.k, bp.c, bp.added_mass = (float(body[k]) for k in ("m", "k", "c", "added_mass"))
