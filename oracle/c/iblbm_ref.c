@@ -10,8 +10,10 @@
  *   -> get_equilibrium + collision_{bgk,kbc,reg} -> forcing_{edm,guo_bgk} -> streaming
  *   -> inlet NEBB (left) -> outlet equilibrium (right)
  *
- * fp32 arithmetic throughout.  Checked against the NumPy oracle by tests/test_oracle_cport.py.
- * Never linked into or called by the product. */
+ * fp32 arithmetic throughout (REF_REAL = float, the build every parity test and the CPU baseline use).  Compiled a
+ * second time with -DREF_REAL=double (libiblbm_ref64.so) it is the fp64 yardstick that tells how far two correct fp32
+ * evaluations of the same recipe may drift apart (tests: force tolerance over long horizons).
+ * Checked against the NumPy oracle by tests/test_oracle_cport.py.  Never linked into or called by the product. */
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -19,23 +21,36 @@
 #include <omp.h>
 #endif
 
+#ifndef REF_REAL
+#define REF_REAL float
+#endif
+typedef REF_REAL real;
+#define R(x) ((real)(x))
+#define FABS(x) ((real)fabs((double)(x)))
+#define SQRT(x) (sizeof(real) == 4 ? (real)sqrtf((float)(x)) : (real)sqrt((double)(x)))
+#define FLOOR(x) ((real)floor((double)(x)))
+
 typedef struct {
   int dim, nx, ny, nz;          /* nz = 1 for dim 2 */
-  int collision;                /* 0 bgk, 2 kbc, 3 reg */
+  int collision;                /* 0 bgk, 1 mrt (operators below), 2 kbc, 3 reg */
   int forcing;                  /* 0 none, 1 edm, 2 guo */
   double omega;
-  float g0[3];                  /* uniform body force */
+  real g0[3];                  /* uniform body force */
   int n_markers, n_iter;
-  const float* markers0;        /* (M, dim) */
-  const float* ds;              /* (M) */
-  float worg0[3];               /* window origin (float), size */
+  const real* markers0;        /* (M, dim) */
+  const real* ds;              /* (M) */
+  real worg0[3];               /* window origin (real), size */
   int wsz[3];
   int moving;                   /* 1: 2-DOF Newmark body, window follows trunc(origin0 + d) */
   double body_m, body_k, body_c, body_added;
-  float d[3], v[3], a[3], h[3]; /* body state (in/out) */
+  real d[3], v[3], a[3], h[3]; /* body state (in/out) */
   int inlet_outlet;             /* 1: left NEBB(ux=u0) + right equilibrium(ux=u0) */
-  float u0;
-  float* marker_force;          /* (M, dim) out: +F */
+  real u0;
+  real* marker_force;          /* (M, dim) out: +F */
+  const real* mrt_op;          /* Q x Q collision operator A = M^-1 S M (collision 1) */
+  const real* mrt_fop;         /* Q x Q source operator B = M^-1 (I - S/2) M (collision 1 + forcing 2) */
+  int follow;                   /* window rule of a moving body: 1 trunc(origin0 + d) (2-D VIV example :104-105),
+                                   2 clip(floor(origin0 + d), 0, N - size) (examples/3d/oscillating_cylinder.py:241-243) */
 } RefSpec;
 
 static const int C2[9][3] = {{0,0,0},{1,0,0},{0,1,0},{-1,0,0},{0,-1,0},{1,1,0},{-1,1,0},{-1,-1,0},{1,-1,0}};
@@ -45,139 +60,150 @@ static const int OPP3[19] = {0,2,1,4,3,6,5,10,9,8,7,14,13,12,11,18,17,16,15};
 
 static inline int Q(int dim) { return dim == 2 ? 9 : 19; }
 static inline const int* CV(int dim, int q) { return dim == 2 ? C2[q] : C3[q]; }
-static inline float W(int dim, int q) {
-  if (dim == 2) return q == 0 ? 4.0f / 9.0f : (q < 5 ? 1.0f / 9.0f : 1.0f / 36.0f);
-  return q == 0 ? 1.0f / 3.0f : (q < 7 ? 1.0f / 18.0f : 1.0f / 36.0f);
+static inline real W(int dim, int q) {
+  if (dim == 2) return q == 0 ? R(4.0) / R(9.0) : (q < 5 ? R(1.0) / R(9.0) : R(1.0) / R(36.0));
+  return q == 0 ? R(1.0) / R(3.0) : (q < 7 ? R(1.0) / R(18.0) : R(1.0) / R(36.0));
 }
 
 /* lbm/basic.py:107-110, lbm3d/basic.py:102-105 */
-static void cell_moments(int dim, const float* f, float* rho, float* u) {
+static void cell_moments(int dim, const real* f, real* rho, real* u) {
   const int q_n = Q(dim);
-  float r = 0.f, m[3] = {0.f, 0.f, 0.f};
+  real r = R(0.), m[3] = {R(0.), R(0.), R(0.)};
   for (int q = 0; q < q_n; ++q) {
     r += f[q];
     const int* c = CV(dim, q);
-    for (int d = 0; d < dim; ++d) m[d] += (float)c[d] * f[q];
+    for (int d = 0; d < dim; ++d) m[d] += (real)c[d] * f[q];
   }
   *rho = r;
   for (int d = 0; d < dim; ++d) u[d] = m[d] / r;
 }
 
 /* lbm/basic.py:132-135 */
-static void cell_feq(int dim, float rho, const float* u, float* feq) {
-  float usq = 0.f;
+static void cell_feq(int dim, real rho, const real* u, real* feq) {
+  real usq = R(0.);
   for (int d = 0; d < dim; ++d) usq += u[d] * u[d];
   for (int q = 0; q < Q(dim); ++q) {
     const int* c = CV(dim, q);
-    float cu = 0.f;
-    for (int d = 0; d < dim; ++d) cu += (float)c[d] * u[d];
-    feq[q] = rho * W(dim, q) * (1.0f + 3.0f * cu + 4.5f * cu * cu - 1.5f * usq);
+    real cu = R(0.);
+    for (int d = 0; d < dim; ++d) cu += (real)c[d] * u[d];
+    feq[q] = rho * W(dim, q) * (R(1.0) + R(3.0) * cu + R(4.5) * cu * cu - R(1.5) * usq);
   }
 }
 
 /* lbm/collision/reg.py:23-47, lbm3d/collision/reg.py:10-41 */
-static void cell_proj(int dim, const float* fneq, float* out) {
-  float pi[3][3] = {{0}};
+static void cell_proj(int dim, const real* fneq, real* out) {
+  real pi[3][3] = {{0}};
   const int q_n = Q(dim);
   for (int q = 0; q < q_n; ++q) {
     const int* c = CV(dim, q);
     for (int a = 0; a < dim; ++a)
-      for (int b = 0; b < dim; ++b) pi[a][b] += (float)(c[a] * c[b]) * fneq[q];
+      for (int b = 0; b < dim; ++b) pi[a][b] += (real)(c[a] * c[b]) * fneq[q];
   }
-  float tr = 0.f;
+  real tr = R(0.);
   for (int a = 0; a < dim; ++a) tr += pi[a][a];
   for (int q = 0; q < q_n; ++q) {
     const int* c = CV(dim, q);
-    float s = 0.f;
+    real s = R(0.);
     for (int a = 0; a < dim; ++a)
-      for (int b = 0; b < dim; ++b) s += (float)(c[a] * c[b]) * pi[a][b];
-    out[q] = W(dim, q) * 4.5f * (s - tr * (1.0f / 3.0f));
+      for (int b = 0; b < dim; ++b) s += (real)(c[a] * c[b]) * pi[a][b];
+    out[q] = W(dim, q) * R(4.5) * (s - tr * (R(1.0) / R(3.0)));
   }
 }
 
-static void cell_collide(const RefSpec* s, float* f, const float* feq) {
+static void cell_collide(const RefSpec* s, real* f, const real* feq) {
   const int dim = s->dim, q_n = Q(dim);
-  const float om = (float)s->omega;
+  const real om = (real)s->omega;
+  if (s->collision == 1) { /* f + A (feq - f): lbm/collision/mrt.py:88, lbm3d/collision/mrt.py:96-98 */
+    real dq[19], out[19];
+    for (int q = 0; q < q_n; ++q) dq[q] = feq[q] - f[q];
+    for (int q = 0; q < q_n; ++q) {
+      real acc = R(0.);
+      for (int k = 0; k < q_n; ++k) acc += s->mrt_op[q * q_n + k] * dq[k];
+      out[q] = f[q] + acc;
+    }
+    for (int q = 0; q < q_n; ++q) f[q] = out[q];
+    return;
+  }
   if (s->collision == 0) { /* lbm/basic.py:156 */
-    const float a = (float)(1.0 - s->omega);
+    const real a = (real)(1.0 - s->omega);
     for (int q = 0; q < q_n; ++q) f[q] = a * f[q] + om * feq[q];
     return;
   }
-  float fneq[19], sh[19];
+  real fneq[19], sh[19];
   for (int q = 0; q < q_n; ++q) fneq[q] = f[q] - feq[q];
   if (s->collision == 3) { /* lbm/collision/reg.py:49 */
     cell_proj(dim, fneq, sh);
-    const float a = (float)(1.0 - s->omega);
+    const real a = (real)(1.0 - s->omega);
     for (int q = 0; q < q_n; ++q) f[q] = feq[q] + a * sh[q];
     return;
   }
   /* KBC: lbm/collision/kbc.py:29-59, lbm3d/collision/kbc.py:29-42 */
   if (dim == 2) {
-    const float n4 = (fneq[1] - fneq[2] + fneq[3] - fneq[4]) / 4.0f;
-    const float p4 = (fneq[5] - fneq[6] + fneq[7] - fneq[8]) / 4.0f;
-    sh[0] = 0.f; sh[1] = n4; sh[2] = -n4; sh[3] = n4; sh[4] = -n4; sh[5] = p4; sh[6] = -p4; sh[7] = p4; sh[8] = -p4;
+    const real n4 = (fneq[1] - fneq[2] + fneq[3] - fneq[4]) / R(4.0);
+    const real p4 = (fneq[5] - fneq[6] + fneq[7] - fneq[8]) / R(4.0);
+    sh[0] = R(0.); sh[1] = n4; sh[2] = -n4; sh[3] = n4; sh[4] = -n4; sh[5] = p4; sh[6] = -p4; sh[7] = p4; sh[8] = -p4;
   } else {
     cell_proj(dim, fneq, sh);
   }
-  float ssh = 0.f, shh = 0.f;
+  real ssh = R(0.), shh = R(0.);
   for (int q = 0; q < q_n; ++q) {
-    const float hi = fneq[q] - sh[q], inv = 1.0f / (feq[q] + 1e-20f);
+    const real hi = fneq[q] - sh[q], inv = R(1.0) / (feq[q] + R(1e-20));
     ssh += hi * sh[q] * inv;
     shh += hi * hi * inv;
   }
-  const float iw = (float)(1.0 / s->omega), omi = (float)(1.0 - 1.0 / s->omega);
-  const float hg = iw - omi * ssh / (shh + 1e-20f);
+  const real iw = (real)(1.0 / s->omega), omi = (real)(1.0 - 1.0 / s->omega);
+  const real hg = iw - omi * ssh / (shh + R(1e-20));
   for (int q = 0; q < q_n; ++q) f[q] -= om * (sh[q] + hg * (fneq[q] - sh[q]));
 }
 
 /* lbm/forcing/guo.py:21-33 */
-static void cell_guo(int dim, const float* g, const float* u, float* G) {
-  float ug = 0.f;
+static void cell_guo(int dim, const real* g, const real* u, real* G) {
+  real ug = R(0.);
   for (int d = 0; d < dim; ++d) ug += u[d] * g[d];
   for (int q = 0; q < Q(dim); ++q) {
     const int* c = CV(dim, q);
-    float cu = 0.f, cg = 0.f;
-    for (int d = 0; d < dim; ++d) { cu += (float)c[d] * u[d]; cg += (float)c[d] * g[d]; }
-    G[q] = W(dim, q) * (3.0f * (cg - ug) + 9.0f * cu * cg);
+    real cu = R(0.), cg = R(0.);
+    for (int d = 0; d < dim; ++d) { cu += (real)c[d] * u[d]; cg += (real)c[d] * g[d]; }
+    G[q] = W(dim, q) * (R(3.0) * (cg - ug) + R(9.0) * cu * cg);
   }
 }
 
 /* ib/kernels.py:25-43 */
-static float peskin4(float r) {
-  const float a = fabsf(r);
-  if (a > 2.0f) return 0.f;
-  if (a < 1.0f) return (3.0f - 2.0f * a + sqrtf(1.0f + 4.0f * a - 4.0f * a * a)) * 0.125f;
-  return (5.0f - 2.0f * a - sqrtf(-7.0f + 12.0f * a - 4.0f * a * a)) * 0.125f;
+static real peskin4(real r) {
+  const real a = FABS(r);
+  if (a > R(2.0)) return R(0.);
+  if (a < R(1.0)) return (R(3.0) - R(2.0) * a + SQRT(R(1.0) + R(4.0) * a - R(4.0) * a * a)) * R(0.125);
+  return (R(5.0) - R(2.0) * a - SQRT(-R(7.0) + R(12.0) * a - R(4.0) * a * a)) * R(0.125);
 }
 
-typedef struct { float w[64]; int idx[64]; } Stencil;
+typedef struct { real w[64]; int idx[64]; } Stencil;
 
 /* ib/stencil.py:27-51, ib3d/stencil.py:36-59 (window-local coordinates) */
-static void make_stencil(const RefSpec* s, const int* worg, const float* shift, int m, Stencil* st) {
+static void make_stencil(const RefSpec* s, const int* worg, const real* shift, int m, Stencil* st) {
   const int dim = s->dim, ns = dim == 2 ? 16 : 64;
-  float x[3]; int base[3];
+  real x[3]; int base[3];
   for (int d = 0; d < dim; ++d) {
-    x[d] = (s->markers0[m * dim + d] + shift[d]) - (float)worg[d];
-    base[d] = (int)floorf(x[d]);
+    x[d] = (s->markers0[m * dim + d] + shift[d]) - (real)worg[d];
+    base[d] = (int)FLOOR(x[d]);
   }
   for (int k = 0; k < ns; ++k) {
-    int kk = k, node[3]; float w = 1.f;
-    for (int d = dim - 1; d >= 0; --d) { node[d] = base[d] + (kk & 3) - 1; kk >>= 2; w *= peskin4((float)node[d] - x[d]); }
+    int kk = k, node[3]; real w = R(1.);
+    for (int d = dim - 1; d >= 0; --d) { node[d] = base[d] + (kk & 3) - 1; kk >>= 2; w *= peskin4((real)node[d] - x[d]); }
     st->w[k] = w;
     st->idx[k] = dim == 2 ? node[0] * s->wsz[1] + node[1] : (node[0] * s->wsz[1] + node[1]) * s->wsz[2] + node[2];
   }
 }
 
-static void interp(int dim, int wcells, const float* grid, const Stencil* st, float scale, float* out) {
+static void interp(int dim, int wcells, const real* grid, const Stencil* st, real scale, real* out) {
   const int ns = dim == 2 ? 16 : 64;
   for (int c = 0; c < dim; ++c) {
-    float acc = 0.f;
+    real acc = R(0.);
     for (int k = 0; k < ns; ++k) acc += st->w[k] * (grid[c * wcells + st->idx[k]] * scale);
     out[c] = acc;
   }
 }
 
-static void spread(int dim, int wcells, float* grid, const Stencil* st, const float* val) {
+static void spread(int dim, int wcells, real* grid, const Stencil* st, const real* val) {
   const int ns = dim == 2 ? 16 : 64;
   for (int c = 0; c < dim; ++c)
     for (int k = 0; k < ns; ++k) grid[c * wcells + st->idx[k]] += val[c] * st->w[k];
@@ -193,7 +219,7 @@ int ref_num_threads(void) {
 
 /* Advance n_steps reference time steps in place (f holds F_n, the reference's carried state).
  * work: f_tmp (Q*ncell), rho (ncell), u (dim*ncell). */
-int ref_run(RefSpec* s, float* f, float* f_tmp, float* rho, float* u, int n_steps, int n_threads) {
+int ref_run(RefSpec* s, real* f, real* f_tmp, real* rho, real* u, int n_steps, int n_threads) {
   const int dim = s->dim, q_n = Q(dim);
   const int nx = s->nx, ny = s->ny, nz = dim == 3 ? s->nz : 1;
   const long ncell = (long)nx * ny * nz;
@@ -203,17 +229,17 @@ int ref_run(RefSpec* s, float* f, float* f_tmp, float* rho, float* u, int n_step
   int wcells = 1;
   for (int d = 0; d < dim; ++d) wcells *= s->wsz[d];
   const int M = s->n_markers;
-  float* uw = NULL; float* gw = NULL; float* tmpw = NULL; float* um = NULL; float* Ft = NULL; Stencil* sten = NULL;
+  real* uw = NULL; real* gw = NULL; real* tmpw = NULL; real* um = NULL; real* Ft = NULL; Stencil* sten = NULL;
   if (M > 0) {
-    uw = malloc(sizeof(float) * dim * wcells); gw = malloc(sizeof(float) * dim * wcells);
-    tmpw = malloc(sizeof(float) * dim * wcells); um = malloc(sizeof(float) * M * dim);
-    Ft = malloc(sizeof(float) * M * dim); sten = malloc(sizeof(Stencil) * M);
+    uw = malloc(sizeof(real) * dim * wcells); gw = malloc(sizeof(real) * dim * wcells);
+    tmpw = malloc(sizeof(real) * dim * wcells); um = malloc(sizeof(real) * M * dim);
+    Ft = malloc(sizeof(real) * M * dim); sten = malloc(sizeof(Stencil) * M);
   }
   for (int step = 0; step < n_steps; ++step) {
     /* ---- get_macroscopic on the whole grid */
 #pragma omp parallel for schedule(static)
     for (long i = 0; i < ncell; ++i) {
-      float fl[19], uu[3];
+      real fl[19], uu[3];
       for (int q = 0; q < q_n; ++q) fl[q] = f[q * ncell + i];
       cell_moments(dim, fl, &rho[i], uu);
       for (int d = 0; d < dim; ++d) u[d * ncell + i] = uu[d];
@@ -221,11 +247,18 @@ int ref_run(RefSpec* s, float* f, float* f_tmp, float* rho, float* u, int n_step
     /* ---- immersed boundary on the window (ib/mdf.py:31-64) */
     int worg[3] = {0, 0, 0};
     if (M > 0) {
-      float shift[3] = {0.f, 0.f, 0.f};
+      real shift[3] = {R(0.), R(0.), R(0.)};
       for (int d = 0; d < dim; ++d) {
-        float o = s->worg0[d];
+        real o = s->worg0[d];
         if (s->moving && d < 2) { o = o + s->d[d]; shift[d] = s->d[d]; }
-        worg[d] = (int)o;   /* astype(int32): truncation (vortex_induced_vibration.py:104-105) */
+        if (s->follow == 2) {   /* clip(floor(.)): oscillating_cylinder.py:241-243 */
+          const int nd = d == 0 ? nx : (d == 1 ? ny : nz);
+          int oi = (int)FLOOR(o);
+          oi = oi < 0 ? 0 : oi;
+          worg[d] = oi > nd - s->wsz[d] ? nd - s->wsz[d] : oi;
+        } else {
+          worg[d] = (int)o;   /* astype(int32): truncation (vortex_induced_vibration.py:104-105) */
+        }
       }
       for (int c = 0; c < dim; ++c)
         for (int ix = 0; ix < s->wsz[0]; ++ix)
@@ -239,48 +272,48 @@ int ref_run(RefSpec* s, float* f, float* f_tmp, float* rho, float* u, int n_step
 #pragma omp parallel for schedule(static)
       for (int m = 0; m < M; ++m) {
         make_stencil(s, worg, shift, m, &sten[m]);
-        interp(dim, wcells, uw, &sten[m], 1.0f, &um[m * dim]);
-        for (int c = 0; c < dim; ++c) Ft[m * dim + c] = 0.f;
+        interp(dim, wcells, uw, &sten[m], R(1.0), &um[m * dim]);
+        for (int c = 0; c < dim; ++c) Ft[m * dim + c] = R(0.);
       }
       for (int it = 0; it < s->n_iter; ++it) {
-        memset(tmpw, 0, sizeof(float) * dim * wcells);
+        memset(tmpw, 0, sizeof(real) * dim * wcells);
         for (int m = 0; m < M; ++m) {   /* scatter-add: serial, deterministic */
-          float dF[3];
+          real dF[3];
           for (int c = 0; c < dim; ++c) {
-            const float tgt = (s->moving && c < 2) ? s->v[c] : 0.f;
-            dF[c] = (tgt - um[m * dim + c]) * (s->ds[m] * 2.0f);
+            const real tgt = (s->moving && c < 2) ? s->v[c] : R(0.);
+            dF[c] = (tgt - um[m * dim + c]) * (s->ds[m] * R(2.0));
             Ft[m * dim + c] += dF[c];
           }
           spread(dim, wcells, tmpw, &sten[m], dF);
         }
 #pragma omp parallel for schedule(static)
         for (int m = 0; m < M; ++m) {
-          float du[3];
-          interp(dim, wcells, tmpw, &sten[m], 0.5f, du);
+          real du[3];
+          interp(dim, wcells, tmpw, &sten[m], R(0.5), du);
           for (int c = 0; c < dim; ++c) um[m * dim + c] += du[c];
         }
       }
-      memset(gw, 0, sizeof(float) * dim * wcells);
-      float hsum[3] = {0.f, 0.f, 0.f};
+      memset(gw, 0, sizeof(real) * dim * wcells);
+      real hsum[3] = {R(0.), R(0.), R(0.)};
       for (int m = 0; m < M; ++m) {
         spread(dim, wcells, gw, &sten[m], &Ft[m * dim]);
         for (int c = 0; c < dim; ++c) { hsum[c] += -Ft[m * dim + c]; if (s->marker_force) s->marker_force[m * dim + c] = Ft[m * dim + c]; }
       }
       if (s->moving) {   /* dyn.py:27-51 with gamma = 1/2, beta = 1/4, dt = 1 */
-        const float denom = (float)(s->body_m + 0.5 * s->body_c + 0.25 * s->body_k);
+        const real denom = (real)(s->body_m + 0.5 * s->body_c + 0.25 * s->body_k);
         for (int c = 0; c < 2; ++c) {
-          const float h = hsum[c] + s->a[c] * (float)s->body_added;
-          const float v1 = s->v[c] + 0.5f * s->a[c];
-          const float d1 = s->d[c] + s->v[c] + 0.25f * s->a[c];
-          const float an = (h - (float)s->body_c * v1 - (float)s->body_k * d1) / denom;
-          s->h[c] = h; s->a[c] = an; s->v[c] = 0.5f * an + v1; s->d[c] = 0.25f * an + d1;
+          const real h = hsum[c] + s->a[c] * (real)s->body_added;
+          const real v1 = s->v[c] + R(0.5) * s->a[c];
+          const real d1 = s->d[c] + s->v[c] + R(0.25) * s->a[c];
+          const real an = (h - (real)s->body_c * v1 - (real)s->body_k * d1) / denom;
+          s->h[c] = h; s->a[c] = an; s->v[c] = R(0.5) * an + v1; s->d[c] = R(0.25) * an + d1;
         }
       }
     }
     /* ---- equilibrium + collision + forcing, in place */
 #pragma omp parallel for schedule(static)
     for (long i = 0; i < ncell; ++i) {
-      float fl[19], feq[19], G[19], uu[3], g[3];
+      real fl[19], feq[19], G[19], uu[3], g[3];
       for (int q = 0; q < q_n; ++q) fl[q] = f[q * ncell + i];
       for (int d = 0; d < dim; ++d) { uu[d] = u[d * ncell + i]; g[d] = s->g0[d]; }
       if (M > 0) {
@@ -296,13 +329,21 @@ int ref_run(RefSpec* s, float* f, float* f_tmp, float* rho, float* u, int n_step
         }
       }
       if (s->forcing == 2)
-        for (int d = 0; d < dim; ++d) uu[d] += g[d] * 0.5f / rho[i];
+        for (int d = 0; d < dim; ++d) uu[d] += g[d] * R(0.5) / rho[i];
       cell_feq(dim, rho[i], uu, feq);
       cell_collide(s, fl, feq);
       if (s->forcing) {
         cell_guo(dim, g, uu, G);
-        const float sc = s->forcing == 2 ? (float)(1.0 - 0.5 * s->omega) : 1.0f;
-        for (int q = 0; q < q_n; ++q) fl[q] += G[q] * sc;
+        if (s->forcing == 2 && s->collision == 1) {   /* f + B G: lbm/forcing/guo.py:106-107, lbm3d/forcing/guo.py:84-87 */
+          for (int q = 0; q < q_n; ++q) {
+            real acc = R(0.);
+            for (int k = 0; k < q_n; ++k) acc += s->mrt_fop[q * q_n + k] * G[k];
+            fl[q] += acc;
+          }
+        } else {
+          const real sc = s->forcing == 2 ? (real)(1.0 - 0.5 * s->omega) : R(1.0);
+          for (int q = 0; q < q_n; ++q) fl[q] += G[q] * sc;
+        }
       }
       for (int q = 0; q < q_n; ++q) f[q * ncell + i] = fl[q];
     }
@@ -314,8 +355,8 @@ int ref_run(RefSpec* s, float* f, float* f_tmp, float* rho, float* u, int n_step
         const int sx = (x - c[0] + nx) % nx;
         for (int y = 0; y < ny; ++y) {
           const int sy = (y - c[1] + ny) % ny;
-          float* dst = f_tmp + q * ncell + ((long)x * ny + y) * nz;
-          const float* src = f + q * ncell + ((long)sx * ny + sy) * nz;
+          real* dst = f_tmp + q * ncell + ((long)x * ny + y) * nz;
+          const real* src = f + q * ncell + ((long)sx * ny + sy) * nz;
           if (dim == 2 || c[2] == 0) { for (int z = 0; z < nz; ++z) dst[z] = src[z]; }
           else { for (int z = 0; z < nz; ++z) dst[z] = src[(z - c[2] + nz) % nz]; }
         }
@@ -325,28 +366,28 @@ int ref_run(RefSpec* s, float* f, float* f_tmp, float* rho, float* u, int n_step
       const long nface = (long)ny * nz;
 #pragma omp parallel for schedule(static)
       for (long k = 0; k < nface; ++k) {
-        const float u0 = s->u0;
+        const real u0 = s->u0;
         if (dim == 2) {   /* boundary_force_corrected_nebb(left, ux=u0) with g_wall = 0, rho_wall = 1: lbm/boundary/nebb.py:41-58 */
           const long cw = k;   /* x = 0 */
-          const float f2 = f_tmp[2 * ncell + cw], f4 = f_tmp[4 * ncell + cw];
-          const float shear = 0.5f * (f2 - f4);
-          f_tmp[1 * ncell + cw] = f_tmp[3 * ncell + cw] + (2.0f / 3.0f) * u0;
-          f_tmp[5 * ncell + cw] = f_tmp[7 * ncell + cw] - shear + (1.0f / 6.0f) * u0;
-          f_tmp[8 * ncell + cw] = f_tmp[6 * ncell + cw] + shear + (1.0f / 6.0f) * u0;
+          const real f2 = f_tmp[2 * ncell + cw], f4 = f_tmp[4 * ncell + cw];
+          const real shear = R(0.5) * (f2 - f4);
+          f_tmp[1 * ncell + cw] = f_tmp[3 * ncell + cw] + (R(2.0) / R(3.0)) * u0;
+          f_tmp[5 * ncell + cw] = f_tmp[7 * ncell + cw] - shear + (R(1.0) / R(6.0)) * u0;
+          f_tmp[8 * ncell + cw] = f_tmp[6 * ncell + cw] + shear + (R(1.0) / R(6.0)) * u0;
         } else {          /* lbm3d/boundary/nebb.py:16-32 */
-          float uw3[3] = {u0, 0.f, 0.f}, fe[19];
-          cell_feq(3, 1.0f, uw3, fe);
+          real uw3[3] = {u0, R(0.), R(0.)}, fe[19];
+          cell_feq(3, R(1.0), uw3, fe);
           for (int q = 0; q < 19; ++q)
             if (C3[q][0] > 0) f_tmp[q * ncell + k] = f_tmp[OPP3[q] * ncell + k] + fe[q] - fe[OPP3[q]];
         }
         /* boundary_equilibrium(right, ux=u0): lbm/boundary/eq.py:45-56 */
-        float uwr[3] = {u0, 0.f, 0.f}, fe[19];
-        cell_feq(dim, 1.0f, uwr, fe);
+        real uwr[3] = {u0, R(0.), R(0.)}, fe[19];
+        cell_feq(dim, R(1.0), uwr, fe);
         const long cr = (long)(nx - 1) * nface + k;
         for (int q = 0; q < q_n; ++q) f_tmp[q * ncell + cr] = fe[q];
       }
     }
-    memcpy(f, f_tmp, sizeof(float) * q_n * ncell);
+    memcpy(f, f_tmp, sizeof(real) * q_n * ncell);
   }
   free(uw); free(gw); free(tmpw); free(um); free(Ft); free(sten);
   return 0;

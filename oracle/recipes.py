@@ -141,8 +141,11 @@ def run(spec, f, n_steps):
     return f, h
 
 
-def viv_step(spec, body, f, d, v, a):
+def viv_step(spec, body, f, d, v, a, follow=1):
     """Moving rigid body coupled through Newmark-beta (2-DOF translation).
+
+    follow = 1: window origin trunc(origin0 + d) (vortex_induced_vibration.py:104-105); follow = 2:
+    clip(floor(origin0 + d), 0, N - size) (examples/3d/oscillating_cylinder.py:241-243).
 
     ``body`` = dict(m, k, c, added_mass) ; markers in ``spec['ib']['markers']`` are the
     initial coordinates, shifted by ``d`` every step; the IB window origin follows
@@ -153,7 +156,11 @@ def viv_step(spec, body, f, d, v, a):
     origin0, size = ibs["window"]
     origin = list(origin0)
     for k in range(len(d)):
-        origin[k] = int(np.trunc(F32(origin0[k]) + d[k]))
+        shifted = F32(origin0[k]) + d[k]
+        if follow == 2:
+            origin[k] = int(min(max(int(np.floor(shifted)), 0), spec["shape"][k] - size[k]))
+        else:
+            origin[k] = int(np.trunc(shifted))
     ibs["window"] = (tuple(origin), size)
     shift = np.zeros(dim, dtype=F32); shift[:len(d)] = d
     markers = (f32(spec["ib"]["markers"]) + shift).astype(F32)

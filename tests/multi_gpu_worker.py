@@ -1,7 +1,7 @@
-"""Multi-GPU parity check (run under torchrun on N GPUs of one node):
+"""Multi-GPU parity worker (run under torchrun on N GPUs of one node; tests/test_gpu_multi.py launches it):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        scripts/multi_gpu_check.py
+        tests/multi_gpu_worker.py
 
 Every rank runs its slab of (a) a periodic D2Q9 KBC + EDM body-force case, (b) the C2 recipe with walls and one
 immersed cylinder per slab, (c) a D3Q19 BGK case, (d) a D3Q19 MRT case with walls and a densely meshed immersed cylinder; rank 0 also runs the whole domain on one GPU and compares:

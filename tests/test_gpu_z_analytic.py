@@ -5,11 +5,7 @@ import pytest
 
 import analytic_cases as ac
 
-# Written after the round's GPU budget was spent: the checks themselves run on the oracle in the CPU suite, but these
-# stepper runs have not been on hardware yet.  Until they have (scripts/gpu_round2_first.sh), an unexpected failure is
-# reported as xfail and a pass as XPASS instead of turning the parity suite red; drop the mark after the first pass.
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first hardware run pending (added after the last GPU visit)")]
+pytestmark = pytest.mark.gpu
 
 
 def run(case, **kw):

@@ -400,6 +400,11 @@ class Stepper:
         self.n_steps = 0
         return self
 
+    def _drop_graph(self):
+        """A captured graph replays from the (buffer, parity) pair it was recorded with.  After restore() the live pair
+        may be the other one; rather than rely on one realigning step, re-capture from the restored state."""
+        self._graph = None
+
     def get_f(self):
         """Return F_n, the state the reference carries after n steps (a new tensor)."""
         self._require_state()
@@ -473,6 +478,7 @@ class Stepper:
             raise ValueError(f"checkpoint is for a {tuple(ck['shape'])} grid, this stepper is {self.shape}")
         if (self._body_dev is not None) != ("body" in ck) or (self.ib is not None) != ("marker_force" in ck):
             raise ValueError("checkpoint and stepper disagree about the immersed body")
+        self._drop_graph()
         self._bufs[self._cur].copy_(torch.as_tensor(np.ascontiguousarray(ck["populations"])))
         self._kind = str(ck["kind"])
         self.n_steps = int(ck["n_steps"])
@@ -708,9 +714,11 @@ class Stepper:
         if graphable and n >= 2:
             if self._graph is None:
                 self._capture()
-            if self._graph_cur != self._cur or self._graph_parity != self._parity:   # recorded from the other buffer / parity
+            if (self._graph_cur, self._graph_parity) != (self._cur, self._parity):   # recorded from the other buffer / parity
                 self._advance()
                 n -= 1
+                if (self._graph_cur, self._graph_parity) != (self._cur, self._parity):
+                    self._capture()          # buffer and parity out of phase with the recording: record again
             while n >= 2:
                 self._graph.replay()
                 n -= 2
