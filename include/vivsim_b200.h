@@ -152,10 +152,12 @@ typedef struct {
   int step;               /* number of body updates performed so far (index of the next history row)     */
 } VsbBodyState;
 
-/* Structural parameters and window rule of a translating rigid body (reference dyn.py:5-51 with gamma = 1/2,
- * beta = 1/4, dt = 1; coupling of examples/2d/vortex_induced_vibration.py:104-105,135-137). */
+/* Structural parameters and window rule of a rigid body (reference dyn.py:5-51 with gamma = 1/2, beta = 1/4,
+ * dt = 1; coupling of examples/2d/vortex_induced_vibration.py:104-105,135-137).  Translation in 1..dim components;
+ * in 2-D a third degree of freedom is the rotation about `center` (dyn.py:54-57 newmark_3dof, :84-120 marker
+ * kinematics, :139-154 torque): d[2] = angle, v[2] = angular velocity, force_sum[2] = torque of +F. */
 typedef struct {
-  int n_dof;              /* 1..3 translation components; 0 = fixed body (no update)                       */
+  int n_dof;              /* 1..3 degrees of freedom; 0 = fixed body (no update)                           */
   int follow;             /* window rule: 0 fixed, 1 trunc(origin0 + d) (2-D VIV example :104-105),
                              2 clip(floor(origin0 + d)) (examples/3d/oscillating_cylinder.py:241-243)       */
   float origin0[3];       /* window origin for d = 0                                                       */
@@ -166,6 +168,13 @@ typedef struct {
                              update_chunk returns (examples/2d/vortex_induced_vibration.py:150-157).  DEVICE memory for
                              the device update, HOST memory for vsb_body_newmark_host / vsb_step_host_ode             */
   int history_capacity;
+  int rotation;           /* 1 (2-D, n_dof = 3): degree of freedom 2 is the rotation about `center`         */
+  float center[2];        /* x_center_init, y_center_init of dyn.py:84-154                                  */
+  int matrix_form;        /* 0: the scalars m, k, c, added_mass act on every degree of freedom (dyn.py:44-46);
+                             1: multi-DOF form of dyn.py:36-42 with the row-major 3 x 3 matrices below (their
+                             leading n_dof x n_dof block) and one added mass per degree of freedom            */
+  double mat_m[9], mat_k[9], mat_c[9];
+  double added_mass_v[3];
 } VsbBodyParams;
 
 /* Mailbox in page-locked host memory (reachable from the device under unified addressing). */
@@ -221,6 +230,13 @@ typedef struct {
                       body) holds at most 2304 cells; a chunk that does not fit falls back to global reductions.
                       NULL: fixed chunks of 256 consecutive markers */
   int n_chunks;
+  int rotation;                    /* 2-D rigid rotation (see VsbBodyParams): marker position
+                      center + d[0:2] + R(d[2]) (markers0 - center), target velocity v[0:2] + v[2] x lever arm,
+                      torque of +F accumulated into body->force_sum[2]                                        */
+  float center[2];
+  int chain_mode;                  /* how a small body's iterations are chained inside one launch:
+                      0 auto; 1 grid barriers through `barrier` (cooperative launch); 2 one thread-block cluster with
+                      the work fields in distributed shared memory (2-D, <= 512 markers); 3 one launch per iteration */
 } VsbMdfArgs;
 
 /* ---- fused time step ------------------------------------------------------------------- *

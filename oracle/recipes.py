@@ -172,6 +172,35 @@ def viv_step(spec, body, f, d, v, a, follow=1):
     return stream_and_post(sp, f_post), d2, v2, a2, h
 
 
+def viv_step_3dof(spec, body, f, d, v, a, follow=1):
+    """Moving rigid body with three degrees of freedom in 2-D (x, y, rotation about body['center']).
+
+    Marker coordinates and target velocities from dyn.py:84-120, total force and torque from dyn.py:123-154, matrix-form
+    Newmark (dyn.py:36-42); the rest as viv_step.  ``body`` = dict(m, k, c (3 x 3), added_mass (3,), center)."""
+    ibs = dict(spec["ib"])
+    d = f32(d); v = f32(v); a = f32(a)
+    origin0, size = ibs["window"]
+    origin = list(origin0)
+    for k in range(2):
+        shifted = F32(origin0[k]) + d[k]
+        if follow == 2:
+            origin[k] = int(min(max(int(np.floor(shifted)), 0), spec["shape"][k] - size[k]))
+        else:
+            origin[k] = int(np.trunc(shifted))
+    ibs["window"] = (tuple(origin), size)
+    xc, yc = body["center"]
+    m0 = f32(spec["ib"]["markers"])
+    mx, my = dyn.get_markers_coords_3dof(m0[:, 0], m0[:, 1], xc, yc, d)
+    markers = np.stack([mx, my], axis=1).astype(F32)
+    tgt = dyn.get_markers_velocity_3dof(mx, my, xc, yc, d, v)
+    sp = dict(spec); sp["ib"] = ibs
+    f_post, _, _, hm = collide(sp, f, markers, tgt)
+    h = np.concatenate([dyn.get_force_to_obj(hm), [dyn.get_torque_to_obj(mx, my, xc, yc, d, hm)]]).astype(F32)
+    h = (h + a * f32(body["added_mass"])).astype(F32)
+    a2, v2, d2 = dyn.newmark_3dof(a, v, d, h, f32(body["m"]), f32(body["k"]), f32(body["c"]))
+    return stream_and_post(sp, f_post), d2, v2, a2, h
+
+
 # ------------------------------------------------------------------ named configurations
 def cavity_spec(n=100, u0=0.5, nu=0.1):
     """BASELINE config 0 (README.md:89-122): BGK, NEE on four walls, lid last."""

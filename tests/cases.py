@@ -70,6 +70,21 @@ def viv(g):
     return spec, body, _eq2(nx, ny, ux=float(u0)), state, 20
 
 
+def viv_rotation(g):
+    """Elastically mounted ellipse with three degrees of freedom (tests/golden/make_golden.py rotation_fixture)."""
+    (nx, ny, u0, nu, xc, yc, X0, Y0, size, th0, vy0, om0) = g["rot_params"]
+    nx, ny, X0, Y0, size = int(nx), int(ny), int(X0), int(Y0), int(size)
+    markers = np.stack([g["rot_MX"], g["rot_MY"]], axis=1)
+    spec = dict(dim=2, shape=(nx, ny), collision="bgk", omega=lbm.get_omega(nu), forcing="edm",
+                ib=dict(markers=markers, ds=g["rot_ds"], kernel="peskin4", n_iter=3, window=((X0, Y0), (size, size))),
+                post=[("force_corrected_nebb", "left", {"ux_wall": float(u0)}),
+                      ("equilibrium", "right", {"ux_wall": float(u0)})])
+    body = dict(m=g["rot_M"], k=g["rot_K"], c=g["rot_C"], added_mass=g["rot_added"], center=(float(xc), float(yc)),
+                rotation=True, n_dof=3)
+    state = (np.array([0, 0, th0], F32), np.array([0, vy0, om0], F32), np.zeros(3, F32))
+    return spec, body, _eq2(nx, ny, ux=float(u0)), state, 30
+
+
 def text_mask(g):
     nx, ny, u0, nu = g["text_params"]; nx, ny = int(nx), int(ny)
     spec = dict(dim=2, shape=(nx, ny), collision="kbc", omega=lbm.get_omega(nu), forcing=None,

@@ -65,4 +65,4 @@ def assert_bitexact(actual, expected, what=""):
 
 @pytest.fixture(scope="session")
 def golden():
-    return {n: load_golden(n) for n in ("lattice", "ops2d", "ops3d", "ib", "dyn", "recipes")}
+    return {n: load_golden(n) for n in ("lattice", "ops2d", "ops3d", "ib", "dyn", "recipes", "rotation")}

@@ -426,6 +426,58 @@ def recipes_fixture():
     save("recipes", out)
 
 
+# ---------------------------------------------------------------- 3-DOF rigid body (translation + rotation)
+def rotation_fixture():
+    """An elastically mounted ELLIPSE with three degrees of freedom (x, y, rotation), composed from the reference's
+    own functions the way examples/2d/vortex_induced_vibration.py:96-148 composes the 2-DOF case: marker coordinates
+    and velocities from dyn.get_markers_coords_3dof / get_markers_velocity_3dof (dyn.py:84-120), torque from
+    dyn.get_torque_to_obj (dyn.py:139-154), matrix-form dyn.newmark_3dof (dyn.py:36-42).  72 x 48, 30 steps."""
+    out = {}
+    nx, ny, u0 = 72, 48, 0.06
+    A_, B_ = 6.0, 3.5
+    nu = u0 * 2 * A_ / 100
+    omega = lbm.get_omega(nu)
+    m = 40
+    th = np.linspace(0, 2 * np.pi, m, endpoint=False)
+    XC, YC = 24.3, 23.6
+    MX = (XC + A_ * np.cos(th)).astype(F32); MY = (YC + B_ * np.sin(th)).astype(F32)
+    area = np.pi * A_ * B_
+    inertia = 0.25 * area * 10 * (A_ ** 2 + B_ ** 2)
+    M = np.diag([10 * area, 10 * area, inertia]).astype(F32)
+    K = np.array([[0.02, 0.0, 0.0], [0.0, 0.05, 0.01], [0.0, 0.01, 0.9]], dtype=F32)
+    C = np.array([[0.01, 0.0, 0.0], [0.0, 0.02, 0.0], [0.0, 0.0, 0.3]], dtype=F32)
+    added = np.array([area, area, 0.0], dtype=F32)
+    pad = 5
+    X0 = int(XC - A_ - pad); Y0 = int(YC - A_ - pad); size = int(2 * A_ + 2 * pad)
+    mds = A(ib.get_ds(J(np.stack([MX, MY], axis=1))))
+    f = lbm.get_equilibrium(jnp.ones((nx, ny)), jnp.zeros((2, nx, ny)).at[0].set(u0))
+    d = jnp.zeros(3).at[2].set(0.35); v = jnp.zeros(3).at[1].set(0.3 * u0).at[2].set(0.004); a = jnp.zeros(3)
+    rec = []
+    for _ in range(30):
+        rho, u = lbm.get_macroscopic(f)
+        f = lbm.collision_bgk(f, lbm.get_equilibrium(rho, u), omega)
+        ibx = (X0 + d[0]).astype(jnp.int32); iby = (Y0 + d[1]).astype(jnp.int32)
+        ib_u = jax.lax.dynamic_slice(u, (0, ibx, iby), (2, size, size))
+        ib_f = jax.lax.dynamic_slice(f, (0, ibx, iby), (9, size, size))
+        mxx, myy = dyn.get_markers_coords_3dof(J(MX), J(MY), XC, YC, d)
+        mv = dyn.get_markers_velocity_3dof(mxx, myy, XC, YC, d, v)
+        w, idx = ib.get_ib_stencil(mxx - ibx, myy - iby, size, kernel=ib.kernel_peskin_4pt, stencil_radius=2)
+        ib_g, hm = ib.multi_direct_forcing(ib_u, w, idx, mv, J(mds), n_iter=3)
+        h = jnp.concatenate([dyn.get_force_to_obj(hm), dyn.get_torque_to_obj(mxx, myy, XC, YC, d, hm)[None]])
+        h = h + a * J(added)
+        a, v, d = dyn.newmark_3dof(a, v, d, h, J(M), J(K), J(C))
+        f = jax.lax.dynamic_update_slice(f, lbm.forcing_edm(ib_f, ib_g, ib_u), (0, ibx, iby))
+        f = lbm.streaming(f)
+        f = lbm.boundary_force_corrected_nebb(f, loc="left", ux_wall=u0)
+        f = lbm.boundary_equilibrium(f, loc="right", ux_wall=u0)
+        rec.append(np.concatenate([A(d), A(v), A(a), A(h)]))
+    out["rot_f30"], out["rot_dvah"] = f, np.array(rec)
+    out["rot_MX"], out["rot_MY"], out["rot_ds"] = MX, MY, mds
+    out["rot_M"], out["rot_K"], out["rot_C"], out["rot_added"] = M, K, C, added
+    out["rot_params"] = np.array([nx, ny, u0, nu, XC, YC, X0, Y0, size, 0.35, 0.3 * u0, 0.004])
+    save("rotation", out)
+
+
 # ---------------------------------------------------------------- post.py diagnostics (SURVEY 8f row 3)
 def post_fixture():
     from vivsim import post
@@ -494,6 +546,8 @@ if __name__ == "__main__":
         dyn_fixture()
     if want("recipes"):
         recipes_fixture()
+    if want("rotation"):
+        rotation_fixture()
     if want("post"):
         post_fixture()
     if want("multigrid"):

@@ -33,7 +33,7 @@ def test_header_symbols_exported(lib):
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
     from vivsim_b200 import _lib
     assert sorted(_lib.EXPORTS) == names, "ctypes binding and header disagree"
-    assert lib.vsb_abi_version() == 1
+    assert lib.vsb_abi_version() == 2
 
 
 def test_struct_layouts_match_header(lib):

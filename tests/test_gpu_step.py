@@ -76,6 +76,28 @@ def test_viv_moving_body_host_and_device(golden):
             assert_close(hist[:, 2 * k:2 * k + 2], ref[:, 2 * k:2 * k + 2], rtol=1e-4, what=f"viv {nm} ({mode})")
 
 
+@pytest.mark.parametrize("chain", ["auto", "barrier", "launches"])
+def test_viv_rotating_body_host_and_device(golden, chain):
+    """Rotational degree of freedom in the fused path (dyn.py:84-154): marker kinematics, per-marker
+    target velocity, torque sum and the matrix-form Newmark update, ODE on the host and on the device, against the
+    reference's own 3-DOF functions (tests/golden/rotation.npz)."""
+    g = golden["rotation"]
+    spec, body, f0, (d, v, a), n = cases.viv_rotation(g)
+    from vivsim_b200 import Stepper
+    ref = g["rot_dvah"]
+    for mode in ("host", "device"):
+        bd = dict(body, d0=d, v0=v, a0=a)
+        st = Stepper(spec, body=bd, dyn_mode=mode, follow=1, ib_chain=chain).set_f(f0)
+        hist = []
+        for _ in range(n):
+            st.step(1)
+            hist.append(np.concatenate(st.body_state()))
+        hist = np.array(hist)
+        assert_close(N(st.get_f()), g["rot_f30"], what=f"rotation f ({mode}, {chain})")
+        for k, nm in enumerate(("d", "v", "a", "h")):
+            assert_close(hist[:, 3 * k:3 * k + 3], ref[:, 3 * k:3 * k + 3], rtol=1e-4, what=f"rotation {nm} ({mode}, {chain})")
+
+
 def _horizon(spec, f0, n):
     """CUDA vs the fp32 oracle and the fp64 yardstick (oracle.cport, same C source in float and double) after n steps."""
     from oracle import cport

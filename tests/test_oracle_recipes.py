@@ -49,6 +49,20 @@ def test_viv_moving_body(golden):
         assert_close(hist[:, 2 * k:2 * k + 2], ref[:, 2 * k:2 * k + 2], rtol=1e-4, what=f"viv {nm}")
 
 
+def test_viv_rotating_body(golden):
+    """3-DOF body (x, y, rotation; dyn.py:84-154 with the matrix-form Newmark) against the reference's own functions."""
+    g = golden["rotation"]
+    spec, body, f, (d, v, a), n = cases.viv_rotation(g)
+    hist = []
+    for _ in range(n):
+        f, d, v, a, h = recipes.viv_step_3dof(spec, body, f, d, v, a)
+        hist.append(np.concatenate([d, v, a, h]))
+    assert_close(f, g["rot_f30"], what="rotation f")
+    hist = np.array(hist); ref = g["rot_dvah"]
+    for k, nm in enumerate(("d", "v", "a", "h")):
+        assert_close(hist[:, 3 * k:3 * k + 3], ref[:, 3 * k:3 * k + 3], rtol=1e-4, what=f"rotation {nm}")
+
+
 @pytest.mark.parametrize("mod,shape", [(lbm, (9, 7)), (lbm3d, (5, 4, 6))])
 def test_invariants(mod, shape):
     rng = np.random.default_rng(0)

@@ -20,6 +20,7 @@ BC = {"nee": 0, "nebb": 1, "equilibrium": 2, "bounce_back": 3, "specular_reflect
 WRAP = {"": 0, "velocity": 1, "pressure": 2, "force_corrected": 3}
 LOC = {"left": 0, "right": 1, "bottom": 2, "top": 3, "back": 4, "front": 5}
 DELTA = {"peskin3": 0, "peskin4": 1, "cosine4": 2, "hat2": 3}
+CHAIN = {"auto": 0, "barrier": 1, "cluster": 2, "launches": 3}
 DIAG = {"velocity_magnitude": 0, "velocity_gradient": 1, "vorticity": 2, "vorticity_magnitude": 3, "divergence": 4,
         "strain_rate": 5, "strain_rate_magnitude": 6, "kinetic_energy": 7, "pressure": 8, "enstrophy": 9,
         "q_criterion": 10}
@@ -65,7 +66,10 @@ BODY_BYTES = C.sizeof(VsbBodyState)   # 15 fp32 + 8 int32 = 92 bytes
 class VsbBodyParams(C.Structure):
     _fields_ = [("n_dof", C.c_int), ("follow", C.c_int), ("origin0", C.c_float * 3), ("grid_size", C.c_int * 3),
                 ("win_size", C.c_int * 3), ("m", C.c_double), ("k", C.c_double), ("c", C.c_double),
-                ("added_mass", C.c_double), ("history", C.c_void_p), ("history_capacity", C.c_int)]
+                ("added_mass", C.c_double), ("history", C.c_void_p), ("history_capacity", C.c_int),
+                ("rotation", C.c_int), ("center", C.c_float * 2), ("matrix_form", C.c_int),
+                ("mat_m", C.c_double * 9), ("mat_k", C.c_double * 9), ("mat_c", C.c_double * 9),
+                ("added_mass_v", C.c_double * 3)]
 
 
 class VsbMdfArgs(C.Structure):
@@ -76,7 +80,8 @@ class VsbMdfArgs(C.Structure):
                 ("g_win_next", C.c_void_p),
                 ("scratch", C.c_void_p), ("scratch_next", C.c_void_p), ("marker_u", C.c_void_p),
                 ("marker_force", C.c_void_p), ("body", C.c_void_p), ("barrier", C.c_void_p),
-                ("host_mail", C.c_void_p), ("mail_seq", C.c_int), ("chunk_offsets", C.c_void_p), ("n_chunks", C.c_int)]
+                ("host_mail", C.c_void_p), ("mail_seq", C.c_int), ("chunk_offsets", C.c_void_p), ("n_chunks", C.c_int),
+                ("rotation", C.c_int), ("center", C.c_float * 2), ("chain_mode", C.c_int)]
 
 
 class VsbStepArgs(C.Structure):

@@ -11,7 +11,7 @@
 #include <thread>
 #include <vector>
 
-#include "vsb_step.cuh"
+#include "vsb_mdf.cuh"
 
 namespace vsb {
 
@@ -55,7 +55,14 @@ __global__ void k_interpolate(int ncomp, long long ncell, const float* __restric
   if (m >= n_markers) return;
   for (int c = 0; c < ncomp; ++c) {
     float acc = 0.f;
-    for (int s = lane; s < ns; s += 32) acc += w[m * ns + s] * grid[c * ncell + idx[m * ns + s]];
+    for (int s = lane; s < ns; s += 32) {
+      // out-of-range stencil indices (a marker within 2 cells of the grid edge): jnp indexing wraps a negative index
+      // once and clamps a gather index into range; nothing is read outside the grid
+      long long i = idx[m * ns + s];
+      i += (i < 0) ? ncell : 0;
+      i = i < 0 ? 0 : (i >= ncell ? ncell - 1 : i);
+      acc += w[m * ns + s] * grid[c * ncell + i];
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) out[m * ncomp + c] = acc;
@@ -69,34 +76,13 @@ __global__ void k_spread(int ncomp, long long ncell, float* __restrict__ grid, l
   if (t >= n_markers * ns) return;
   const long long m = t / ns;
   const float wt = w[t];
-  const int i = idx[t];
+  long long i = idx[t];
+  i += (i < 0) ? ncell : 0;                 // jnp: a negative index wraps once ...
+  if (i < 0 || i >= ncell) return;          // ... and an out-of-range scatter update is dropped
   for (int c = 0; c < ncomp; ++c) atomicAdd(&grid[c * ncell + i], vals[m * ncomp + c] * wt);
 }
 
 // ----------------------------------------------------------------------------- MDF stage chain
-struct MdfParams {
-  int delta_kind, n_iter, stage, stage_end, parity;
-  unsigned long long* barrier;
-  long long n_markers;
-  int origin0[3], wsize[3];
-  const float* markers0;
-  const float* u_target;
-  const float* ds_ptr;
-  float ds_value;
-  const float* u_win;   // optional: precomputed window velocity (stage 0 interpolates it instead of pulling populations)
-  float* g_win;         // this step's force field (zero on entry of the last stage)
-  float* g_win_next;    // next step's force field: cleared by stage 0
-  float* scratch;       // this step's per-iteration fields, (n_iter - 1) x dim x window
-  float* scratch_next;  // next step's: buffer k is cleared by stage k
-  float* marker_u;
-  float* marker_force;
-  VsbBodyState* body;
-  int update_body;
-  VsbHostMail* host_mail;   // host-ODE mode: post the total force to page-locked host memory
-  int mail_seq;
-  const int* chunk_offsets; // tiled kernel: marker range of every CTA (NULL: 256 consecutive markers each)
-};
-
 // Stage k of multi_direct_forcing (ib/mdf.py:31-64), one launch per iteration, markers spread over many CTAs:
 //   k = 0     : u at the stencil points = moments of the pulled (streamed, masked) populations, u_m = interp(u)
 //   k > 0     : u_m += interp(0.5 * spread(dF_{k-1}))        (buffer scratch[k-1], filled by stage k-1)
@@ -108,6 +94,7 @@ struct MdfParams {
 // Buffers are double-buffered by step parity: while this step accumulates into its own set, every stage clears the
 // matching buffer of the other set, so no memset is needed and nothing is cleared while it may still be read.
 // Barrier across the (small, co-resident) grid of the fused MDF launch.  Monotonic 64-bit ticket counter: never reset.
+// The launch is cooperative (cudaLaunchCooperativeKernel), so the CTAs are guaranteed to be co-resident.
 __device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned nblocks) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -157,17 +144,16 @@ __global__ void __launch_bounds__(kBlock, DIM == 3 ? 5 : 8) k_mdf_stage(const St
   long long idx[PPL];
   int node[PPL][DIM];
   bool ok[PPL];
-  float ds2 = 0.f, tgt[DIM], u_m[DIM], F[DIM];
+  float ds2 = 0.f, tgt[DIM], u_m[DIM], F[DIM], pos[DIM], arm[2];
 #pragma unroll
-  for (int c = 0; c < DIM; ++c) { tgt[c] = 0.f; u_m[c] = 0.f; F[c] = 0.f; }
+  for (int c = 0; c < DIM; ++c) { tgt[c] = 0.f; u_m[c] = 0.f; F[c] = 0.f; pos[c] = 0.f; }
   if (active) {
     float x[DIM];
     int base[DIM];
+    marker_kinematics<DIM>(p, m, pos, tgt, arm);
 #pragma unroll
     for (int d = 0; d < DIM; ++d) {
-      float pos = p.markers0[m * DIM + d];
-      if (p.body) pos += p.body->d[d];
-      x[d] = pos - (float)org[d];   // window-local coordinate, as in the reference's marker_x - ib_x0
+      x[d] = pos[d] - (float)org[d];   // window-local coordinate, as in the reference's marker_x - ib_x0
       base[d] = (int)floorf(x[d]);
     }
 #pragma unroll
@@ -189,10 +175,8 @@ __global__ void __launch_bounds__(kBlock, DIM == 3 ? 5 : 8) k_mdf_stage(const St
     }
     ds2 = (p.ds_ptr ? p.ds_ptr[m] : p.ds_value) * 2.0f;
 #pragma unroll
-    for (int c = 0; c < DIM; ++c) {
-      tgt[c] = p.u_target ? p.u_target[m * DIM + c] : (p.body ? p.body->v[c] : 0.f);
+    for (int c = 0; c < DIM; ++c)
       if (p.stage > 0) { u_m[c] = p.marker_u[m * DIM + c]; F[c] = p.marker_force[m * DIM + c]; }   // from the previous launch
-    }
   } else {
 #pragma unroll
     for (int j = 0; j < PPL; ++j) { w[j] = 0.f; ok[j] = false; idx[j] = 0; }
@@ -268,6 +252,9 @@ __global__ void __launch_bounds__(kBlock, DIM == 3 ? 5 : 8) k_mdf_stage(const St
       if (last && p.body && gl == 0) {
 #pragma unroll
         for (int c = 0; c < DIM; ++c) atomicAdd(&s_force[c], spread_val[c]);
+        if constexpr (DIM == 2) {
+          if (p.rotation) atomicAdd(&s_force[2], marker_torque(p, pos, spread_val));
+        }
       }
     }
     if (stage + 1 < p.stage_end) grid_barrier(p.barrier, gridDim.x);
@@ -276,7 +263,7 @@ __global__ void __launch_bounds__(kBlock, DIM == 3 ? 5 : 8) k_mdf_stage(const St
 
   if (p.stage_end == p.n_iter && p.body) {
     __syncthreads();
-    if (threadIdx.x < DIM) atomicAdd(&p.body->force_sum[threadIdx.x], s_force[threadIdx.x]);
+    if (threadIdx.x < (p.rotation ? 3 : DIM)) atomicAdd(&p.body->force_sum[threadIdx.x], s_force[threadIdx.x]);
     if (p.update_body || p.host_mail) {   // the last CTA to arrive sees every contribution
       __shared__ int s_last;
       __syncthreads();
@@ -288,14 +275,7 @@ __global__ void __launch_bounds__(kBlock, DIM == 3 ? 5 : 8) k_mdf_stage(const St
       if (s_last && threadIdx.x == 0) {
         __threadfence();
         p.body->ticket = 0;
-        if (p.update_body) {
-          body_update(p.body, bu, p.parity);          // ODE on the device
-        } else {                                      // ODE on the host: post the force, the host polls for seq
-          volatile VsbHostMail* mail = p.host_mail;
-          for (int c = 0; c < 3; ++c) mail->force[c] = __ldcg(&p.body->force_sum[c]);
-          __threadfence_system();
-          mail->seq = p.mail_seq >= 0 ? p.mail_seq : p.body->step + 1;   // < 0: the step being taken (graph replays)
-        }
+        finish_body(p, bu);
       }
     }
   }
@@ -543,14 +523,7 @@ __global__ void __launch_bounds__(kTiledChunk, 3) k_mdf_stage_tiled(const MdfPar
       if (s_last && tid == 0) {
         __threadfence();
         p.body->ticket = 0;
-        if (p.update_body) {
-          body_update(p.body, bu, p.parity);
-        } else {
-          volatile VsbHostMail* mail = p.host_mail;
-          for (int c = 0; c < 3; ++c) mail->force[c] = __ldcg(&p.body->force_sum[c]);
-          __threadfence_system();
-          mail->seq = p.mail_seq >= 0 ? p.mail_seq : p.body->step + 1;   // < 0: the step being taken (graph replays)
-        }
+        finish_body(p, bu);
       }
     }
   }
@@ -578,16 +551,37 @@ static int mdf_impl(const VsbStepArgs& sa, const VsbMdfArgs& a, const VsbBodyPar
   p.host_mail = (a.body && !p.update_body) ? a.host_mail : nullptr;
   p.mail_seq = a.mail_seq;
   p.chunk_offsets = nullptr;
+  p.rotation = (DIM == 2 && a.rotation) ? 1 : 0;
+  p.center[0] = a.center[0]; p.center[1] = a.center[1];
   BodyUpdate bu{};
   if (p.update_body) bu = make_body_update(*bp, DIM);
   const int lanes = (DIM == 2) ? 16 : 32;
   const unsigned nb = blocks_for(a.n_markers * lanes, kBlock);
   p.barrier = reinterpret_cast<unsigned long long*>(a.barrier);
-  // Small bodies: every iteration in ONE launch, separated by grid barriers (all CTAs are co-resident: at most 120 of
-  // 128 threads).  Large bodies: one launch per iteration.
-  if (a.barrier && nb <= 120) {   // (one marker per lane group: the kernel keeps u_m and F in registers across stages)
-    p.stage = 0; p.stage_end = a.n_iter;
-    k_mdf_stage<DIM><<<nb, kBlock, 0, stream>>>(sp, p, bu);
+  p.stage = 0; p.stage_end = a.n_iter;
+  const int mode = a.chain_mode;
+  bool use_cluster = false;
+  if constexpr (DIM == 2) {
+    // Small 2-D bodies: the whole chain in one thread-block cluster, work fields in distributed shared memory,
+    // hardware cluster barriers between the iterations (vsb_mdf_cluster.cu)
+    use_cluster = (mode == 0 || mode == 2) && a.u_win == nullptr && mdf_cluster2d_supported(p);
+    if (mode == 2 && !use_cluster) {
+      set_error("vsb_ib_mdf: chain_mode 2 (cluster) needs a 2-D body of at most 512 markers, no u_win, and a window "
+                "whose three work slabs fit the cluster's shared memory");
+      return VSB_ERR_INVALID;
+    }
+    if (use_cluster) return launch_mdf_cluster2d(sp, p, bu, stream);
+  } else if (mode == 2) {
+    set_error("vsb_ib_mdf: chain_mode 2 (cluster) is for 2-D bodies");
+    return VSB_ERR_INVALID;
+  }
+  // Small bodies: every iteration in ONE launch, separated by grid barriers.  The launch is cooperative, so all of its
+  // CTAs (at most 120 of 128 threads) are co-resident whatever else runs on the device.  Large bodies: one launch
+  // per iteration.
+  if (a.barrier && nb <= 120 && mode != 3) {   // (one marker per lane group: the kernel keeps u_m and F in registers across stages)
+    void* kargs[] = {(void*)&sp, (void*)&p, (void*)&bu};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_mdf_stage<DIM>, dim3(nb), dim3(kBlock), kargs, 0, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "vsb_ib_mdf (cooperative launch)");
   } else if (DIM == 3 && a.u_win != nullptr && !getenv("VSB_MDF_UNTILED")) {
     // dense body with a precomputed window velocity: every stage reads a window field -> shared-memory tiles
     if constexpr (DIM == 3) {
@@ -712,28 +706,9 @@ int vsb_body_newmark_host(VsbBodyState* body, VsbBodyState* pinned, const VsbBod
 
 static void host_body_update(VsbBodyState* pinned, const VsbBodyParams* bp, int parity) {
   // dyn.py:27-51 with gamma = 1/2, beta = 1/4, dt = 1, in fp32 like the reference's jnp arithmetic;
-  // h = sum(-F) + a * added_mass (examples/2d/vortex_induced_vibration.py:135-136)
-  const float denom = (float)(bp->m + 0.5 * bp->c + 0.25 * bp->k);
-  const float k = (float)bp->k, c = (float)bp->c, am = (float)bp->added_mass;
-  for (int i = 0; i < bp->n_dof; ++i) {
-    const float h = -pinned->force_sum[i] + pinned->a[i] * am;
-    const float v1 = pinned->v[i] + 0.5f * pinned->a[i];
-    const float d1 = pinned->d[i] + pinned->v[i] + 0.25f * pinned->a[i];
-    const float a_next = (h - c * v1 - k * d1) / denom;
-    pinned->h[i] = h;
-    pinned->a[i] = a_next;
-    pinned->v[i] = 0.5f * a_next + v1;
-    pinned->d[i] = 0.25f * a_next + d1;
-  }
-  for (int i = 0; i < 3; ++i) pinned->force_sum[i] = 0.f;
+  // h = sum(-F) + a * added_mass (examples/2d/vortex_induced_vibration.py:135-136).  bp->history is a HOST ring here.
   const int dim = bp->grid_size[2] <= 1 ? 2 : 3;
-  for (int d = 0; d < dim; ++d)
-    pinned->origin2[(parity & 1) ^ 1][d] = origin_rule(bp->follow, bp->origin0[d], pinned->d[d], bp->grid_size[d], bp->win_size[d]);
-  if (bp->history && bp->history_capacity > 0) {   // HOST ring in this mode
-    float* row = bp->history + 6 * (pinned->step % bp->history_capacity);
-    for (int i = 0; i < 3; ++i) { row[i] = pinned->d[i]; row[3 + i] = pinned->h[i]; }
-  }
-  pinned->step += 1;
+  body_update(pinned, make_body_update(*bp, dim), parity & 1);
 }
 
 // One domain of vsb_run_host_ode_multi: what is enqueued for a step, and what happens when its force has arrived.
@@ -904,7 +879,9 @@ int host_ode_serve(HostOdeDomain* dom, int n_domains, int stride, int first, int
       for (int i = first; i < n_domains; i += stride) {
         HostOdeDomain& d = dom[i];
         if (!d.in_flight) continue;
-        cudaError_t e = cudaStreamQuery(d.ib);
+        // the stream the chain of the step in flight was enqueued on: `main` for a graph replay (the side streams
+        // are idle then, so querying `ib` would report a finished chain while the graph is still running)
+        cudaError_t e = cudaStreamQuery(d.graph[d.mdf->parity & 1] ? d.main : d.ib);
         if (e != cudaSuccess && e != cudaErrorNotReady) return cuda_fail(e, "vsb_run_host_ode (waiting for the IB force)");
         if (e == cudaSuccess && *reinterpret_cast<volatile int*>(&d.mdf->host_mail->seq) != d.want) {
           set_error("vsb_run_host_ode: the IB chain finished without posting the force");

@@ -257,6 +257,7 @@ extern "C" {
 
 int vsb_ib_fused_supported(const VsbMdfArgs* a) {
   if (!a || (a->dim != 2 && a->dim != 3) || a->n_markers <= 0 || a->n_markers > (1 << 24)) return 0;
+  if (a->rotation) return 0;   // marker kinematics with rotation live in the multi-CTA chain (vsb_ib_mdf)
   // Shared-memory fp32 atomics retire at ~2 cycles per lane on the one SM this kernel occupies (measured: 512 markers
   // x 16 points x 2 components x 5 iterations = 97 us), so the single-CTA form only pays for small bodies; larger ones
   // use the multi-CTA chain (vsb_ib_mdf), whose global reductions are spread over the whole chip.

@@ -1,41 +1,37 @@
-// EXPERIMENTAL -- NOT PART OF libvivsim_b200.so (vivsim_b200/_build.py compiles csrc/*.cu only; this file is only
-// compile-checked: nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 --expt-relaxed-constexpr -c).
-// It has never run on a GPU.  DESIGN.md section 7, item 3 ("single-domain latency").
-//
 // Whole multi-direct-forcing chain of a small 2-D body (<= 512 markers: the C2 cylinder) in ONE thread-block cluster
-// of 8 CTAs x 1024 threads.  The production kernel (k_mdf_stage<2>, all iterations in one launch) separates the
-// iterations by grid barriers through a global counter and keeps the per-iteration work fields in global memory:
-// ~3.5 us per iteration, 18-20 us for the five iterations of C2, which is the critical path of a single domain
-// (bulk kernel: 11.5 us).  Here
+// of 8 CTAs x 1024 threads.  The grid-barrier variant (k_mdf_stage<2>, all iterations in one cooperative launch)
+// separates the iterations by barriers through a global counter and keeps the per-iteration work fields in global
+// memory: ~3.5 us per iteration, 18-20 us for the five iterations of C2 -- the critical path of a single domain (the
+// bulk kernel takes 11.5 us).  Here
 //   * the work fields live in DISTRIBUTED SHARED MEMORY: CTA r owns a slab of window rows; spreading is a
 //     red.shared::cluster.add.f32 into the owner's slab, interpolation a ld.shared::cluster from it;
-//   * iterations are separated by the hardware cluster barrier (barrier.cluster.arrive / wait);
+//   * iterations are separated by the hardware cluster barrier (barrier.cluster.arrive / wait, ~0.2 us);
 //   * three slabs per CTA rotate (spread into k % 3, gather from (k - 1) % 3, clear (k + 1) % 3), so one barrier per
 //     iteration suffices: the slab being cleared was last read one barrier ago and is next written one barrier ahead.
 // Arithmetic and operation order per marker are those of k_mdf_stage<2> (ib/mdf.py:31-64); the last iteration
-// spreads F into the global force window with vector reductions exactly like the production kernel, so vsb_step
-// needs no change.
+// spreads F into the global force window with vector reductions exactly like that kernel, so vsb_step needs no change.
 #include <cooperative_groups.h>
 
-#include "../vsb_ib.cu"   // MdfParams, BodyUpdate, delta(), pull_cell(), moments() of the production kernels
+#include "vsb_mdf.cuh"
 
 namespace vsb {
 namespace cg = cooperative_groups;
 
 constexpr int kClusterCtas = 8;        // portable cluster size
 constexpr int kClusterThreads = 1024;  // 64 marker groups of 16 lanes per CTA -> 512 markers per cluster
+constexpr size_t kClusterSmemMax = 200 * 1024;
 
 __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterThreads, 1)
 k_mdf_cluster2d(const StepParams<2> sp, const MdfParams p, const BodyUpdate bu, int rows_per_cta) {
   using L = Lat<2>;
-  constexpr int NS = 16, G = 16;   // 4 x 4 stencil points, one per lane of the marker's group
+  constexpr int G = 16;   // 4 x 4 stencil points, one per lane of the marker's group
   extern __shared__ float2 s_field[];            // 3 slabs of rows_per_cta x wsize[1] cells
-  __shared__ float s_force[2];
+  __shared__ float s_force[3];
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned rank = cluster.block_rank();
   const int w1 = p.wsize[1];
   const int slab_cells = rows_per_cta * w1;
-  if (threadIdx.x < 2) s_force[threadIdx.x] = 0.f;
+  if (threadIdx.x < 3) s_force[threadIdx.x] = 0.f;
   for (int i = threadIdx.x; i < 3 * slab_cells; i += blockDim.x) s_field[i] = make_float2(0.f, 0.f);
 
   const int gthread = (int)(rank * blockDim.x + threadIdx.x);
@@ -45,21 +41,20 @@ k_mdf_cluster2d(const StepParams<2> sp, const MdfParams p, const BodyUpdate bu, 
   const bool active = m < p.n_markers;
   const long long wcells = (long long)p.wsize[0] * w1;
 
-  int org[2] = {p.origin0[0], p.origin0[1]};
+  int org[3] = {p.origin0[0], p.origin0[1], 0};
   if (p.body) { org[0] = p.body->origin2[p.parity][0]; org[1] = p.body->origin2[p.parity][1]; }
 
   // this lane's stencil point: the same for every iteration
-  float w = 0.f, ds2 = 0.f, tgt[2] = {0.f, 0.f}, u_m[2] = {0.f, 0.f}, F[2] = {0.f, 0.f};
+  float w = 0.f, ds2 = 0.f, tgt[2] = {0.f, 0.f}, u_m[2] = {0.f, 0.f}, F[2] = {0.f, 0.f}, pos[2] = {0.f, 0.f}, arm[2];
   int node[2] = {0, 0};
   bool ok = false;
   if (active) {
     float x[2];
     int base[2];
+    marker_kinematics<2>(p, m, pos, tgt, arm);
 #pragma unroll
     for (int d = 0; d < 2; ++d) {
-      float pos = p.markers0[m * 2 + d];
-      if (p.body) pos += p.body->d[d];
-      x[d] = pos - (float)org[d];
+      x[d] = pos[d] - (float)org[d];
       base[d] = (int)floorf(x[d]);
     }
     int s = gl;
@@ -73,8 +68,6 @@ k_mdf_cluster2d(const StepParams<2> sp, const MdfParams p, const BodyUpdate bu, 
       ok = ok && node[d] >= 0 && node[d] < p.wsize[d];
     }
     ds2 = (p.ds_ptr ? p.ds_ptr[m] : p.ds_value) * 2.0f;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) tgt[c] = p.u_target ? p.u_target[m * 2 + c] : (p.body ? p.body->v[c] : 0.f);
   }
   // owner CTA and slab-local index of this lane's stencil cell
   const unsigned owner = ok ? (unsigned)(node[0] / rows_per_cta) : 0u;
@@ -82,25 +75,29 @@ k_mdf_cluster2d(const StepParams<2> sp, const MdfParams p, const BodyUpdate bu, 
   float2* remote = cluster.map_shared_rank(s_field, owner);
   const long long gidx = (long long)node[0] * w1 + node[1];
 
-  // next step's global force window is cleared here, as in the production kernel (no memset on the step path)
+  // stage 0: velocity at the stencil point from the streamed (pulled, masked) populations -- issued before the first
+  // cluster barrier so that the loads are in flight while the slabs are being cleared
+  float um[2] = {0.f, 0.f};
+  if (ok) {
+    float f[L::Q], rho, u[2];
+    pull_cell<2>(sp, 0, org[0] + node[0], org[1] + node[1], f, true);
+    moments<2>(f, rho, u);
+    um[0] = w * u[0];
+    um[1] = w * u[1];
+  }
+  // next step's global force window is cleared here, as in k_mdf_stage (no memset on the step path)
   for (long long i = gthread; i < 2 * wcells; i += nthreads) p.g_win_next[i] = 0.f;
   cluster.sync();                                 // every CTA's slabs are zero before anybody spreads into them
 
   for (int stage = 0; stage < p.n_iter; ++stage) {
     const bool last = stage == p.n_iter - 1;
-    float um[2] = {0.f, 0.f};
-    if (stage == 0) {
-      if (ok) {            // velocity at the stencil point from the streamed (pulled, masked) populations
-        float f[L::Q], rho, u[2];
-        pull_cell<2>(sp, 0, org[0] + node[0], org[1] + node[1], f, true);
-        moments<2>(f, rho, u);
-        um[0] = w * u[0];
-        um[1] = w * u[1];
+    if (stage > 0) {       // 0.5 * spread(dF_{k-1}) at the stencil point, from the owner's slab
+      um[0] = um[1] = 0.f;
+      if (ok) {
+        const float2 v = remote[((stage - 1) % 3) * slab_cells + local];
+        um[0] = w * v.x;
+        um[1] = w * v.y;
       }
-    } else if (ok) {       // 0.5 * spread(dF_{k-1}) at the stencil point, from the owner's slab
-      const float2 v = remote[((stage - 1) % 3) * slab_cells + local];
-      um[0] = w * v.x;
-      um[1] = w * v.y;
     }
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
@@ -108,7 +105,7 @@ k_mdf_cluster2d(const StepParams<2> sp, const MdfParams p, const BodyUpdate bu, 
       for (int o = G / 2; o > 0; o >>= 1) um[c] += __shfl_xor_sync(0xffffffffu, um[c], o);
     }
     // the slab that the NEXT iteration spreads into: last read one barrier ago
-    if (!last) {
+    if (!last && stage + 1 >= 3) {
       float2* z = s_field + ((stage + 1) % 3) * slab_cells;
       for (int i = threadIdx.x; i < slab_cells; i += blockDim.x) z[i] = make_float2(0.f, 0.f);
     }
@@ -137,6 +134,7 @@ k_mdf_cluster2d(const StepParams<2> sp, const MdfParams p, const BodyUpdate bu, 
           p.marker_force[m * 2 + c] = F[c];
           if (p.body) atomicAdd(&s_force[c], val[c]);
         }
+        if (p.body && p.rotation) atomicAdd(&s_force[2], marker_torque(p, pos, val));
       }
     }
     if (!last) cluster.sync();
@@ -144,36 +142,35 @@ k_mdf_cluster2d(const StepParams<2> sp, const MdfParams p, const BodyUpdate bu, 
 
   if (p.body) {
     __syncthreads();
-    if (threadIdx.x < 2) atomicAdd(&p.body->force_sum[threadIdx.x], s_force[threadIdx.x]);
+    if (threadIdx.x < (p.rotation ? 3 : 2)) atomicAdd(&p.body->force_sum[threadIdx.x], s_force[threadIdx.x]);
     __threadfence();
     cluster.sync();                                // all eight partial sums are in before the update
-    if (rank == 0 && threadIdx.x == 0) {
-      if (p.update_body) {
-        body_update(p.body, bu, p.parity);
-      } else if (p.host_mail) {
-        volatile VsbHostMail* mail = p.host_mail;
-        for (int c = 0; c < 3; ++c) mail->force[c] = __ldcg(&p.body->force_sum[c]);
-        __threadfence_system();
-        mail->seq = p.mail_seq >= 0 ? p.mail_seq : p.body->step + 1;
-      }
+    if (rank == 0 && threadIdx.x == 0 && (p.update_body || p.host_mail)) {
+      __threadfence();
+      finish_body(p, bu);
     }
   } else {
     cluster.sync();                                // nobody leaves while its shared memory may still be addressed
   }
 }
 
-// Launch recipe (what mdf_impl<2> would do for n_markers <= 512 and a window of at most ~68 k cells):
-//   rows_per_cta = ceil(wsize[0] / 8); smem = 3 * rows_per_cta * wsize[1] * sizeof(float2)  (C2: 3 x 14 x 108 x 8 B = 36 KB)
-//   cudaFuncSetAttribute(k_mdf_cluster2d, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)   if smem > 48 KB
-//   k_mdf_cluster2d<<<kClusterCtas, kClusterThreads, smem, stream>>>(sp, p, bu, rows_per_cta);
-inline int launch_mdf_cluster2d(const StepParams<2>& sp, const MdfParams& p, const BodyUpdate& bu, cudaStream_t stream) {
-  if (p.n_markers > (long long)kClusterCtas * kClusterThreads / 16) return VSB_ERR_INVALID;
-  const int rows_per_cta = (p.wsize[0] + kClusterCtas - 1) / kClusterCtas;
-  const size_t smem = (size_t)3 * rows_per_cta * p.wsize[1] * sizeof(float2);
-  if (smem > 200 * 1024) return VSB_ERR_INVALID;
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(k_mdf_cluster2d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+static inline int cluster_rows(const MdfParams& p) { return (p.wsize[0] + kClusterCtas - 1) / kClusterCtas; }
+static inline size_t cluster_smem(const MdfParams& p) { return (size_t)3 * cluster_rows(p) * p.wsize[1] * sizeof(float2); }
+
+bool mdf_cluster2d_supported(const MdfParams& p) {
+  return p.n_markers > 0 && p.n_markers <= (long long)kClusterCtas * kClusterThreads / 16 && p.u_win == nullptr &&
+         cluster_smem(p) <= kClusterSmemMax;
+}
+
+// rows_per_cta = ceil(wsize[0] / 8); smem = 3 slabs (C2: 3 x 14 x 108 x 8 B = 36 KB)
+int launch_mdf_cluster2d(const StepParams<2>& sp, const MdfParams& p, const BodyUpdate& bu, cudaStream_t stream) {
+  const int rows_per_cta = cluster_rows(p);
+  const size_t smem = cluster_smem(p);
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_mdf_cluster2d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemMax);
     if (e != cudaSuccess) return cuda_fail(e, "k_mdf_cluster2d (shared-memory opt-in)");
+    configured = kClusterSmemMax;
   }
   k_mdf_cluster2d<<<kClusterCtas, kClusterThreads, smem, stream>>>(sp, p, bu, rows_per_cta);
   VSB_LAUNCH_CHECK("k_mdf_cluster2d");

@@ -162,7 +162,7 @@ using namespace vsb;
 
 extern "C" {
 
-int vsb_abi_version(void) { return 1; }
+int vsb_abi_version(void) { return 2; }
 const char* vsb_last_error(void) { return vsb::g_err; }
 
 int vsb_streaming(const VsbGrid* grid, const float* f, float* out, vsb_stream_t stream) {

@@ -100,48 +100,105 @@ __device__ __forceinline__ void window_origin(const StepParams<DIM>& p, int (&wo
 // Window origin rule for a displaced body (host and device):
 //   follow 1: astype(int32) truncation      (examples/2d/vortex_induced_vibration.py:104-105)
 //   follow 2: clip(floor(.), 0, N - size)   (examples/3d/oscillating_cylinder.py:241-243)
+// Both are kept inside [0, N - size]: lax.dynamic_slice clamps the start of the slice in the same way, so a body that
+// drifts to the edge of the grid never makes the kernels address cells outside it.
 __host__ __device__ inline int origin_rule(int follow, float origin0, float d, int grid_n, int win_n) {
   const float shifted = origin0 + (follow ? d : 0.f);
-  if (follow == 2) {
-    int o = (int)floorf(shifted);
+  int o = (follow == 2) ? (int)floorf(shifted) : (int)shifted;
+  if (follow) {
+    o = o > grid_n - win_n ? grid_n - win_n : o;
     o = o < 0 ? 0 : o;
-    return o > grid_n - win_n ? grid_n - win_n : o;
   }
-  return (int)shifted;
+  return o;
 }
 
 // Body update: h = -force_sum + a*added_mass; Newmark-beta (gamma 1/2, beta 1/4, dt 1); next window origin.
-// (dyn.py:27-51,136; examples/2d/vortex_induced_vibration.py:135-137)      One thread.
+// (dyn.py:27-51,136; examples/2d/vortex_induced_vibration.py:135-137)      One thread, host or device.
+// Scalar form (dyn.py:44-46): every degree of freedom uses the same m, k, c.  Matrix form (dyn.py:36-42):
+// a_next = (M + C/2 + K/4)^-1 (h - C v1 - K d1); the inverse is formed once on the host in double precision.
 struct BodyUpdate {
-  int n_dof, follow, dim;
+  int n_dof, follow, dim, matrix;
   float origin0[3];
   int grid_size[3], win_size[3];
-  float denom, k, c, added_mass;   // denom = m + c/2 + k/4 evaluated in double on the host
+  float denom, k, c, added_mass;   // scalar form; denom = m + c/2 + k/4 evaluated in double on the host
+  float minv[9], kmat[9], cmat[9], added_v[3];   // matrix form (row-major 3 x 3, leading n_dof x n_dof block)
   float* history;                  // optional (capacity, 6) ring of (d, h) per step
   int history_capacity;
 };
 
 inline BodyUpdate make_body_update(const VsbBodyParams& bp, int dim) {
-  BodyUpdate u;
-  u.n_dof = bp.n_dof; u.follow = bp.follow; u.dim = dim;
+  BodyUpdate u{};
+  u.n_dof = bp.n_dof; u.follow = bp.follow; u.dim = dim; u.matrix = bp.matrix_form ? 1 : 0;
   for (int d = 0; d < 3; ++d) { u.origin0[d] = bp.origin0[d]; u.grid_size[d] = bp.grid_size[d]; u.win_size[d] = bp.win_size[d]; }
   u.denom = (float)(bp.m + 0.5 * bp.c + 0.25 * bp.k);
   u.k = (float)bp.k; u.c = (float)bp.c; u.added_mass = (float)bp.added_mass;
+  if (u.matrix) {
+    // effective mass matrix and its inverse (Gauss-Jordan with partial pivoting, double) on the n_dof x n_dof block
+    const int n = bp.n_dof < 1 ? 1 : (bp.n_dof > 3 ? 3 : bp.n_dof);
+    double a[3][6] = {};
+    for (int i = 0; i < n; ++i) {
+      for (int j = 0; j < n; ++j) a[i][j] = bp.mat_m[3 * i + j] + 0.5 * bp.mat_c[3 * i + j] + 0.25 * bp.mat_k[3 * i + j];
+      a[i][n + i] = 1.0;
+    }
+    for (int col = 0; col < n; ++col) {
+      int piv = col;
+      for (int r = col + 1; r < n; ++r)
+        if ((a[r][col] < 0 ? -a[r][col] : a[r][col]) > (a[piv][col] < 0 ? -a[piv][col] : a[piv][col])) piv = r;
+      for (int j = 0; j < 2 * n; ++j) { const double t = a[col][j]; a[col][j] = a[piv][j]; a[piv][j] = t; }
+      const double d = a[col][col];
+      if (d == 0.0) continue;   // singular: validated by the caller (make_body_update has no error channel)
+      for (int j = 0; j < 2 * n; ++j) a[col][j] /= d;
+      for (int r = 0; r < n; ++r)
+        if (r != col) {
+          const double fct = a[r][col];
+          for (int j = 0; j < 2 * n; ++j) a[r][j] -= fct * a[col][j];
+        }
+    }
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) {
+        u.minv[3 * i + j] = (float)a[i][n + j];
+        u.kmat[3 * i + j] = (float)bp.mat_k[3 * i + j];
+        u.cmat[3 * i + j] = (float)bp.mat_c[3 * i + j];
+      }
+    for (int i = 0; i < 3; ++i) u.added_v[i] = (float)bp.added_mass_v[i];
+  }
   u.history = bp.history_capacity > 0 ? bp.history : nullptr;
   u.history_capacity = bp.history_capacity;
   return u;
 }
 
-__device__ __forceinline__ void body_update(VsbBodyState* b, const BodyUpdate& u, int parity) {
-  for (int i = 0; i < u.n_dof; ++i) {
-    const float h = -b->force_sum[i] + b->a[i] * u.added_mass;
-    const float v1 = b->v[i] + 0.5f * b->a[i];
-    const float d1 = b->d[i] + b->v[i] + 0.25f * b->a[i];
-    const float a_next = (h - u.c * v1 - u.k * d1) / u.denom;
-    b->h[i] = h;
-    b->a[i] = a_next;
-    b->v[i] = 0.5f * a_next + v1;
-    b->d[i] = 0.25f * a_next + d1;
+__host__ __device__ inline void body_update(VsbBodyState* b, const BodyUpdate& u, int parity) {
+  if (!u.matrix) {
+    for (int i = 0; i < u.n_dof; ++i) {
+      const float h = -b->force_sum[i] + b->a[i] * u.added_mass;
+      const float v1 = b->v[i] + 0.5f * b->a[i];
+      const float d1 = b->d[i] + b->v[i] + 0.25f * b->a[i];
+      const float a_next = (h - u.c * v1 - u.k * d1) / u.denom;
+      b->h[i] = h;
+      b->a[i] = a_next;
+      b->v[i] = 0.5f * a_next + v1;
+      b->d[i] = 0.25f * a_next + d1;
+    }
+  } else {
+    float h[3], v1[3], d1[3], rhs[3];
+    for (int i = 0; i < u.n_dof; ++i) {
+      h[i] = -b->force_sum[i] + b->a[i] * u.added_v[i];
+      v1[i] = b->v[i] + 0.5f * b->a[i];
+      d1[i] = b->d[i] + b->v[i] + 0.25f * b->a[i];
+    }
+    for (int i = 0; i < u.n_dof; ++i) {
+      float cv = 0.f, kd = 0.f;
+      for (int j = 0; j < u.n_dof; ++j) { cv += u.cmat[3 * i + j] * v1[j]; kd += u.kmat[3 * i + j] * d1[j]; }
+      rhs[i] = h[i] - cv - kd;
+    }
+    for (int i = 0; i < u.n_dof; ++i) {
+      float a_next = 0.f;
+      for (int j = 0; j < u.n_dof; ++j) a_next += u.minv[3 * i + j] * rhs[j];
+      b->h[i] = h[i];
+      b->a[i] = a_next;
+      b->v[i] = 0.5f * a_next + v1[i];
+      b->d[i] = 0.25f * a_next + d1[i];
+    }
   }
   for (int i = 0; i < 3; ++i) b->force_sum[i] = 0.f;
   for (int d = 0; d < u.dim; ++d)

@@ -77,11 +77,17 @@ def cut_marker_chunks(markers):
 
 class Stepper:
     def __init__(self, spec, device="cuda", rows=None, vec=0, body=None, dyn_mode="host", follow=1, use_graph=False,
-                 fuse_ib=True, fuse_edges=True, overlap=True, buffers=None):
+                 fuse_ib=True, fuse_edges=True, overlap=True, buffers=None, ib_chain="auto"):
         """rows: (begin, end) range of the slowest axis that is physical domain (ghost layers outside; slab
         decomposition).  body: dict(m, k, c, added_mass, n_dof=2, d0, v0, a0) for a moving rigid body coupled by
-        Newmark-beta; dyn_mode "host" (reference-faithful, one tiny D2H/H2D per step) or "device"
+        Newmark-beta; m, k, c scalars (dyn.py:44-46) or (n_dof, n_dof) matrices / length-n_dof diagonals
+        (dyn.py:36-42), added_mass a scalar or one value per degree of freedom; in 2-D, n_dof=3 with
+        rotation=True and center=(cx, cy) adds the rotation about the centre (dyn.py:84-154).
+        dyn_mode "host" (reference-faithful, one tiny D2H/H2D per step) or "device"
         (vsb_body_newmark, graph-capturable).  follow: IB window rule for a moving body (1 trunc, 2 clip(floor)).
+        ib_chain: how a small body's MDF iterations are chained in one launch -- "auto", "barrier" (grid barriers,
+        cooperative launch), "cluster" (one thread-block cluster, work fields in distributed shared memory; 2-D,
+        <= 512 markers) or "launches" (one launch per iteration).
         fuse_ib / fuse_edges / overlap: use the single-kernel IB path, the single-kernel wall path and concurrent
         streams when the configuration allows (all three only change scheduling, not arithmetic per cell)."""
         L.lib()
@@ -114,6 +120,9 @@ class Stepper:
         self._parity = 0
         self.halo = None
         self._want = dict(fuse_ib=bool(fuse_ib), fuse_edges=bool(fuse_edges), overlap=bool(overlap))
+        if ib_chain not in L.CHAIN:
+            raise ValueError(f"ib_chain must be one of {sorted(L.CHAIN)}, got {ib_chain!r}")
+        self._ib_chain = ib_chain
         self._side = None
 
         a = L.VsbStepArgs()
@@ -285,7 +294,8 @@ class Stepper:
         self._mdf_barrier = torch.zeros(2, dtype=torch.int64, device=dev)
         m.barrier = self._mdf_barrier.data_ptr()
         lanes = 16 if dim == 2 else 32
-        self._mdf_one_launch = (self.n_markers * lanes + 127) // 128 <= 120
+        m.chain_mode = L.CHAIN[self._ib_chain]
+        self._mdf_one_launch = (self.n_markers * lanes + 127) // 128 <= 120 and self._ib_chain != "launches"
         m.marker_u = self._marker_u.data_ptr()
         m.marker_force = self._marker_force.data_ptr()
         a.g_win = self._g_win.data_ptr()
@@ -298,13 +308,42 @@ class Stepper:
                 raise ValueError("dyn_mode must be 'host' or 'device'")
             self.follow = int(follow)
             self.n_dof = int(body.get("n_dof", 2))
-            if not 1 <= self.n_dof <= dim:
-                # the fused path moves the markers by translation only; rotation (the third degree of freedom of
-                # dyn.newmark_3dof in 2-D, dyn.py:84-120) is available through the vivsim_b200.dyn functions
-                raise ValueError(f"body['n_dof'] must be 1..{dim} translational degrees of freedom in {dim}-D, got {self.n_dof}")
+            self.rotation = bool(body.get("rotation", False))
+            if self.rotation and (dim != 2 or self.n_dof != 3 or "center" not in body):
+                # the reference's rigid-body kinematics with rotation are 2-D (dyn.py:84-154)
+                raise ValueError("body['rotation'] needs a 2-D body with n_dof=3 and center=(cx, cy)")
+            if not 1 <= self.n_dof <= (3 if self.rotation else dim):
+                raise ValueError(f"body['n_dof'] must be 1..{dim} translational degrees of freedom in {dim}-D (3 with "
+                                 f"rotation=True in 2-D), got {self.n_dof}")
             bp = L.VsbBodyParams()
             bp.n_dof, bp.follow = (self.n_dof if dyn_mode == "device" else 0), self.follow
-            bp.m, bp.k, bp.c, bp.added_mass = (float(body[k]) for k in ("m", "k", "c", "added_mass"))
+            mats = {key: np.asarray(body[key], dtype=np.float64) for key in ("m", "k", "c")}
+            added = np.asarray(body.get("added_mass", 0.0), dtype=np.float64)
+            if any(v.ndim > 0 for v in mats.values()) or added.ndim > 0:
+                bp.matrix_form = 1
+                n = self.n_dof
+                for key, field in (("m", bp.mat_m), ("k", bp.mat_k), ("c", bp.mat_c)):
+                    v = mats[key]
+                    full = v * np.eye(n) if v.ndim == 0 else (np.diag(v) if v.ndim == 1 else v)
+                    if full.shape != (n, n):
+                        raise ValueError(f"body[{key!r}] must be a scalar, {n} diagonal entries or an ({n}, {n}) matrix")
+                    for i in range(n):
+                        for j in range(n):
+                            field[3 * i + j] = float(full[i, j])
+                eff = np.array([[bp.mat_m[3 * i + j] + 0.5 * bp.mat_c[3 * i + j] + 0.25 * bp.mat_k[3 * i + j]
+                                 for j in range(n)] for i in range(n)])
+                if abs(np.linalg.det(eff)) == 0.0:
+                    raise ValueError("m + c/2 + k/4 is singular")
+                av = np.broadcast_to(added, (n,))
+                for i in range(n):
+                    bp.added_mass_v[i] = float(av[i])
+            else:
+                bp.m, bp.k, bp.c, bp.added_mass = (float(mats[k_]) for k_ in ("m", "k", "c")) + (float(added),)
+            if self.rotation:
+                bp.rotation = 1
+                bp.center[0], bp.center[1] = (float(x) for x in body["center"])
+                m.rotation = 1
+                m.center[0], m.center[1] = bp.center[0], bp.center[1]
             for d in range(3):
                 bp.origin0[d] = self.win_origin0[d] if d < dim else 0.0
                 bp.grid_size[d] = self.shape[d] if d < dim else 1
@@ -349,10 +388,10 @@ class Stepper:
         out = np.zeros(3, dtype=np.int32)
         for k in range(self.dim):
             shifted = np.float32(self.win_origin0[k]) + (np.float32(d[k]) if self.follow else np.float32(0))
-            if self.follow == 2:
-                out[k] = min(max(int(np.floor(shifted)), 0), self.shape[k] - self.win_size[k])
-            else:
-                out[k] = int(shifted)   # truncation toward zero, like astype(int32)
+            o = int(np.floor(shifted)) if self.follow == 2 else int(shifted)   # int(): truncation like astype(int32)
+            if self.follow:             # inside the grid, like the start of a lax.dynamic_slice
+                o = max(min(o, self.shape[k] - self.win_size[k]), 0)
+            out[k] = o
         return out
 
     def _check_window_clear_of(self, loc):
