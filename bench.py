@@ -46,6 +46,9 @@ CHUNK = 500          # lattice time steps per domain per bench step (reference C
 GRAPH_STEPS = 10     # lattice time steps per domain per CUDA-graph replay (even: the buffers ping-pong)
 # ensemble members: overlap the IB chain with the bulk inside each domain (the domains overlap each other either way)
 ENSEMBLE_OVERLAP = os.environ.get("VSB_BENCH_OVERLAP", "1") != "0"
+# how the MDF iterations of an ensemble member are chained: with other domains' kernels to fill the gaps, one plain
+# launch per iteration beats the single-launch chains (measured: launches 76.2, cluster 73.6, barrier 68.6 GLUPS)
+ENSEMBLE_CHAIN = os.environ.get("VSB_BENCH_CHAIN", "launches")
 
 
 def peaks():
@@ -290,6 +293,44 @@ def extra_workload(name, hbm_gbs):
             "hbm_frac_of_measured": mlups * 1e6 * bpc / (hbm_gbs * 1e9), "finite": ok}
 
 
+def multi_gpu_config(name, world, rank, hbm_gbs):
+    """BASELINE configs 4 and 5 on all N GPUs (strong scaling of one fixed global grid, collective: every rank calls it).
+    C4: 16384^2 KBC VIV cylinder, slabs along x, the body's chain on the rank that owns it.  C5: 1024 x 512 x 512 MRT
+    with the 695 k-marker cylinder, slabs along x, the IB chain SHARED by all ranks over peer memory (ib='shard')."""
+    import torch
+    import torch.distributed as dist
+    from vivsim_b200 import configs
+    from vivsim_b200.multidevice import SlabStepper
+    if name == "c4":
+        spec, body = configs.viv_cylinder_2d_large()
+        label, bpc, steps, kw = "C4: D2Q9 KBC VIV cylinder 16384^2, 3276 markers, MDF(5) + EDM", 72, 24, dict(ib="owner", follow=1)
+    else:
+        spec, body = configs.oscillating_cylinder_3d()
+        label, bpc, steps, kw = ("C5: D3Q19 MRT oscillating cylinder 1024x512x512, 695570 markers, MDF(3) + Guo-MRT",
+                                 152, 24, dict(ib="shard", follow=2))
+    st = SlabStepper(spec, body=dict(body), dyn_mode="device", halo="peer", **kw)
+    st.set_f_local(configs.uniform_state(dict(spec, shape=st.slab.local_shape), noise=1e-3))
+    st.step(3)
+    loop = GraphLoop([st], 2)
+    loop.run(2)
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    dt, _, _ = timed(lambda: loop.run(steps // 2), lambda: (torch.cuda.synchronize(), dist.barrier(), torch.cuda.synchronize()))
+    t = torch.tensor([dt], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t)
+    ok = torch.tensor([1.0 if bool(torch.isfinite(st.stepper.state).all()) else 0.0], device="cuda")
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    timed_out = bool(st.peer is not None and st.peer.timed_out()) or bool(st.ib_shard is not None and st.ib_shard.timed_out())
+    mlups = cells_of(spec) * steps / dt / 1e6
+    out = {"workload": f"{label} on {world} GPUs (strong scaling, x-slabs, peer-memory halo)", "ib": st.ib_mode,
+           "mlups": mlups, "steps": steps, "ms_per_step": dt / steps * 1e3,
+           "per_gpu_hbm_frac_of_measured": mlups / world * 1e6 * bpc / (hbm_gbs * 1e9), "finite": bool(ok.item()),
+           "timed_out": timed_out, "launches_per_step": st.n_launch_per_step}
+    del loop, st
+    torch.cuda.empty_cache()
+    return out
+
+
 def parity_vs_one_gpu(world, rank):
     """N slabs against one GPU on the same global problem (C2 recipe with walls and an immersed cylinder, KBC periodic
     case): max relative difference of F after 20 steps, gathered on every rank, compared on rank 0."""
@@ -346,7 +387,7 @@ def run_ours(args):
     replays_per_step = CHUNK // GRAPH_STEPS
     if world == 1:
         for i in range(n_rep):
-            st = Stepper(spec, body=dict(body), dyn_mode="device", overlap=ENSEMBLE_OVERLAP)
+            st = Stepper(spec, body=dict(body), dyn_mode="device", overlap=ENSEMBLE_OVERLAP, ib_chain=ENSEMBLE_CHAIN)
             st.set_f(f0)
             st.step(1)     # prologue: internal state is now S_0
             steppers.append(st)
@@ -365,7 +406,7 @@ def run_ours(args):
 
         f_loc = torch.cat([f0[:, -1:], f0, f0[:, :1]], dim=1).contiguous()     # local slab + periodic ghost layers
         for i in range(n_rep):
-            st = SlabStepper(gspec, local_ib=local_ib, body=dict(body), dyn_mode="device", halo="peer")
+            st = SlabStepper(gspec, local_ib=local_ib, body=dict(body), dyn_mode="device", halo="peer", ib_chain=ENSEMBLE_CHAIN)
             st.set_f_local(f_loc)
             st.step(1)
             steppers.append(st)
@@ -420,7 +461,7 @@ def run_ours(args):
         from vivsim_b200 import Ensemble
         del loop
         hist_body = dict(body, history=CHUNK)
-        ens = Ensemble([Stepper(spec, body=dict(hist_body), dyn_mode="host") for _ in range(n_rep)])
+        ens = Ensemble([Stepper(spec, body=dict(hist_body), dyn_mode="host", ib_chain=ENSEMBLE_CHAIN) for _ in range(n_rep)])
         for st in ens.steppers:
             st.set_f(f_host)
         ens.step(40)
@@ -522,8 +563,17 @@ def run_ours(args):
         del one
 
     parity = None
+    also_multi = []
     if world > 1:
         parity = parity_vs_one_gpu(world, rank)
+        if not args.no_extra:
+            del steppers, inner
+            torch.cuda.empty_cache()
+            for name in ("c4", "c5"):
+                try:
+                    also_multi.append(multi_gpu_config(name, world, rank, hbm_gbs))
+                except Exception as exc:  # report, never hide
+                    also_multi.append({"workload": name, "error": f"{type(exc).__name__}: {exc}"})
 
     line = None
     if rank == 0:
@@ -564,7 +614,7 @@ def run_ours(args):
                                 f"{nk} launches rotating over {n_rep} domains (working set {n_rep * bytes_per_domain / 1e6:.0f} MB > L2)"}
             del ks, gk
 
-        also = []
+        also = list(also_multi)
         if not args.no_extra and world == 1:
             del steppers, inner
             torch.cuda.empty_cache()
@@ -587,7 +637,7 @@ def run_ours(args):
                                          + (" on every GPU" if world > 1 else "")
                                          + " (reference update_chunk, vortex_induced_vibration.py:28,150-157)",
                            "lattice_steps_per_bench_step": CHUNK, "cells_per_lattice_step": cells,
-                           "ensemble_domains": n_rep,
+                           "ensemble_domains": n_rep, "ib_chain": ENSEMBLE_CHAIN,
                            "graph_replays": timed_replays, "eager_steps": 0,
                            "lattice_steps_per_graph_replay": GRAPH_STEPS,
                            "us_per_lattice_step": dt / (lattice_steps * n_rep) * 1e6,

@@ -235,8 +235,12 @@ typedef struct {
                       torque of +F accumulated into body->force_sum[2]                                        */
   float center[2];
   int chain_mode;                  /* how a small body's iterations are chained inside one launch:
-                      0 auto; 1 grid barriers through `barrier` (cooperative launch); 2 one thread-block cluster with
-                      the work fields in distributed shared memory (2-D, <= 512 markers); 3 one launch per iteration */
+                      0 auto; 1 grid barriers through `barrier` (cooperative launch); 2 one thread-block cluster that
+                      iterates in marker space (2-D, <= 512 markers, needs nbr_list); 3 one launch per iteration */
+  const uint16_t* nbr_list;        /* chain_mode 0 / 2: (nbr_stride, 512) device array, neighbour-major: column m lists the
+                      markers whose 4 x 4 stencil can overlap that of marker m under any rigid motion of the body (m
+                      itself included), padded with 0xffff; nbr_stride a multiple of 4, <= 48.  NULL: no cluster kernel */
+  int nbr_stride;
 } VsbMdfArgs;
 
 /* ---- fused time step ------------------------------------------------------------------- *
@@ -277,6 +281,9 @@ typedef struct {
   int sub_begin, sub_end;     /* rows of [row_begin, row_end) this launch updates (sub_end = 0: all of them);
                                  lets edge rows, which read ghost layers, run later than the interior */
   int edge_rows_only;         /* 1: update just the first and the last physical row (ignores sub_begin / sub_end) */
+  int win_shift[3];           /* added to body->origin2[parity] by the fluid kernels: the body state of a slab-decomposed
+                                 run carries GLOBAL coordinates (identical on every rank) while `grid` is the local
+                                 slab with its ghost layer: win_shift[0] = 1 - x0 of the slab */
 } VsbStepArgs;
 
 int vsb_step(const VsbStepArgs* args, vsb_stream_t stream);
@@ -380,6 +387,46 @@ int vsb_halo_push(const VsbHaloArgs* args, vsb_stream_t stream);
  * second stream.  vsb_halo_push == send followed by wait. */
 int vsb_halo_send(const VsbHaloArgs* args, vsb_stream_t stream);
 int vsb_halo_wait(const VsbHaloArgs* args, vsb_stream_t stream);
+
+/* ---- multi-GPU: immersed-boundary chain shared by all ranks over peer memory --------------------------------- *
+ * The slab decomposition cuts the fluid along x; an immersed body is compact, so "owner computes" would leave its
+ * whole multi-direct-forcing chain (ib/mdf.py:10-64) to the one or two ranks whose slabs contain it, and a body
+ * crossing a cut could not run at all.  Instead the MARKERS are divided among all ranks and the window fields
+ * (velocity, per-iteration work fields, force) exist once per rank in peer-mapped symmetric memory:
+ *   1. every rank computes the window velocity on the window cells of ITS slab and stores it into the copy of every
+ *      rank whose markers can touch that cell (need box);
+ *   2. every iteration, a rank interpolates at its markers from its own copy and adds what it spreads into the copy of
+ *      every rank whose need box contains the cell (red.global.add over NVLink);
+ *   3. the last iteration adds the force field into the copy of the rank whose SLAB contains the cell (the fluid
+ *      kernel of that rank reads it), and every rank stores its partial force (and torque) sum into a slot of every
+ *      rank; all ranks then add the slots in rank order -- the "small all-reduce of total IB force and torque" of the
+ *      reference's design -- and advance identical replicas of the rigid-body state;
+ *   4. the steps are separated by an all-to-all flag barrier (one word per rank pair, system-scope release/acquire).
+ * Everything is stream-ordered device code: graph-capturable, no NCCL call, no host synchronisation.
+ * Coordinates of markers, window origin and body state are GLOBAL here; args->grid is the local slab and
+ * args->win_shift maps global to local x. */
+enum { VSB_MAX_RANKS = 8 };
+typedef struct {
+  int n_ranks, rank;
+  float* fields[VSB_MAX_RANKS];      /* base of the window-field block of every rank (own entry = local address), laid out
+                                        as [parity 2][slot n_iter + 1][window cells][2 | 4]: slot 0 force field,
+                                        slots 1 .. n_iter-1 work fields, slot n_iter velocity                     */
+  uint32_t* flags[VSB_MAX_RANKS];    /* VSB_MAX_RANKS words per rank: flags[r][src] = last barrier number published by src */
+  float* sums[VSB_MAX_RANKS];        /* VSB_MAX_RANKS x 4 floats per rank: sums[r][src] = partial (Fx, Fy, Fz | torque, -)   */
+  int need_lo[VSB_MAX_RANKS][3], need_hi[VSB_MAX_RANKS][3];   /* window-local box [lo, hi) of cells rank r's markers can touch */
+  int x_lo[VSB_MAX_RANKS], x_hi[VSB_MAX_RANKS];               /* global x range [lo, hi) of the slab of rank r          */
+  int64_t marker_begin, marker_end;  /* this rank's share of the marker arrays                                    */
+  int chunk_begin, chunk_end;        /* ... and of mdf->chunk_offsets (tiled kernel); 0, 0: untiled                 */
+  uint32_t* counter;                 /* 4 local device words: barrier number, spare, time-out indicator, spare      */
+} VsbIbShard;
+
+/* One whole sharded chain of a step: window velocity -> barrier -> n_iter x (iteration -> barrier) -> force / torque
+ * sums and body update (params->n_dof > 0: device ODE on every rank's replica).  mdf->g_win / scratch / u_win are
+ * ignored: the fields live in shard->fields.  mdf->marker_u / marker_force are filled for this rank's share only. */
+int vsb_ibshard_chain(const VsbStepArgs* args, const VsbMdfArgs* mdf, const VsbIbShard* shard,
+                      const VsbBodyParams* params, vsb_stream_t stream);
+/* The flag barrier alone (used between set-up phases and by tests). */
+int vsb_ibshard_barrier(const VsbIbShard* shard, vsb_stream_t stream);
 
 #ifdef __cplusplus
 }

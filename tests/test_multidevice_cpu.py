@@ -97,3 +97,60 @@ def test_slab_geometry_and_spec_localisation():
     bad = dict(spec, ib=dict(markers=markers, ds=1.0, window=((13, 1), (7, 6))))
     with pytest.raises(ValueError):
         localize_spec(bad, slab)
+
+
+# ------------------------------------------------------------------ shared IB chain: host-side plan (no GPU needed)
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("case", ["cylinder3d", "circle2d", "tiny"])
+def test_ib_shard_plan_invariants(world, case):
+    """plan_ib_shards: the ranks' shares partition the markers, chunks stay inside their share and inside the tile, and
+    every stencil cell of a rank's markers (with the sub-cell drift of a window that follows the body) lies in that
+    rank's need box."""
+    from vivsim_b200 import configs
+    from vivsim_b200.multidevice import plan_ib_shards
+    from vivsim_b200.stepper import TILE_CELLS, TILE_CHUNK
+    if case == "cylinder3d":
+        spec, _ = configs.oscillating_cylinder_3d(nx=128, ny=48, nz=64, diameter=12.0, center_x=30.0, moving=False)
+        dense = True
+    elif case == "circle2d":
+        spec, _ = configs.viv_cylinder_2d(nx=256, ny=128, n_marker=96, radius=9.0, center=(128.0, 64.0), moving=False)
+        dense = False
+    else:
+        spec, _ = configs.viv_cylinder_2d(nx=64, ny=64, n_marker=5, radius=3.0, center=(32.0, 32.0), moving=False)
+        dense = False
+    ib = spec["ib"]
+    markers = np.asarray(ib["markers"], dtype=np.float32)
+    origin, size = ib["window"]
+    pl = plan_ib_shards(markers, ib["window"], world, dense)
+    perm = pl["perm"]
+    assert sorted(perm.tolist()) == list(range(len(markers)))
+    mr = pl["marker_ranges"]
+    assert mr[0, 0] == 0 and mr[-1, 1] == len(markers) and (mr[1:, 0] == mr[:-1, 1]).all()
+    assert (mr[:, 1] - mr[:, 0]).max() - (mr[:, 1] - mr[:, 0]).min() <= 1          # balanced
+    stored = markers[perm]
+    for r in range(world):
+        b, e = mr[r]
+        if e == b:
+            continue
+        for drift in (0.0, 0.999):                   # follow = 2: window-local coordinates move by less than one cell
+            base = np.floor(stored[b:e].astype(np.float64) - np.floor(origin) + drift).astype(int)
+            lo = np.maximum(base.min(axis=0) - 1, 0)
+            hi = np.minimum(base.max(axis=0) + 3, size)
+            assert (lo >= pl["need_lo"][r]).all() and (hi <= pl["need_hi"][r]).all(), (r, lo, hi)
+        assert (pl["need_lo"][r] >= 0).all() and (pl["need_hi"][r] <= np.asarray(size)).all()
+    if dense:
+        off = pl["chunk_offsets"]
+        cr = pl["chunk_ranges"]
+        assert off[0] == 0 and off[-1] == len(markers) and (np.diff(off) > 0).all() and (np.diff(off) <= TILE_CHUNK).all()
+        for r in range(world):
+            assert off[cr[r, 0]] == mr[r, 0] and off[cr[r, 1]] == mr[r, 1]
+        for c in range(len(off) - 1):
+            base = np.floor(stored[off[c]:off[c + 1]].astype(np.float64))
+            ext = base.max(axis=0) - base.min(axis=0) + 4 + 1
+            assert np.prod(ext) <= TILE_CELLS
+    else:
+        assert pl["chunk_offsets"] is None
+    whole = plan_ib_shards(markers, ib["window"], world, dense, moving_in_window=True)
+    for r in range(world):
+        if whole["marker_ranges"][r, 1] > whole["marker_ranges"][r, 0]:
+            assert (whole["need_lo"][r] == 0).all() and (whole["need_hi"][r] == np.asarray(size)).all()

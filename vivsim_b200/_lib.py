@@ -33,7 +33,7 @@ EXPORTS = [
     "vsb_body_newmark", "vsb_edge_fused", "vsb_edge_fused_supported", "vsb_ib_fused", "vsb_ib_fused_supported",
     "vsb_halo_push", "vsb_body_newmark_host", "vsb_halo_send", "vsb_halo_wait", "vsb_step_host_ode",
     "vsb_post_field", "vsb_post_mean", "vsb_mg_fine_to_coarse", "vsb_mg_coarse_to_fine", "vsb_run_host_ode",
-    "vsb_run_host_ode_multi",
+    "vsb_run_host_ode_multi", "vsb_ibshard_chain", "vsb_ibshard_barrier",
 ]
 
 
@@ -81,7 +81,8 @@ class VsbMdfArgs(C.Structure):
                 ("scratch", C.c_void_p), ("scratch_next", C.c_void_p), ("marker_u", C.c_void_p),
                 ("marker_force", C.c_void_p), ("body", C.c_void_p), ("barrier", C.c_void_p),
                 ("host_mail", C.c_void_p), ("mail_seq", C.c_int), ("chunk_offsets", C.c_void_p), ("n_chunks", C.c_int),
-                ("rotation", C.c_int), ("center", C.c_float * 2), ("chain_mode", C.c_int)]
+                ("rotation", C.c_int), ("center", C.c_float * 2), ("chain_mode", C.c_int),
+                ("nbr_list", C.c_void_p), ("nbr_stride", C.c_int)]
 
 
 class VsbStepArgs(C.Structure):
@@ -91,7 +92,20 @@ class VsbStepArgs(C.Structure):
                 ("f_out", C.c_void_p), ("g_uniform", C.c_float * 3), ("g_win", C.c_void_p),
                 ("win_origin", C.c_int * 3), ("win_size", C.c_int * 3), ("body", C.c_void_p), ("parity", C.c_int),
                 ("n_post", C.c_int), ("post", C.POINTER(VsbPostOp)), ("vec", C.c_int), ("band", C.c_int),
-                ("edges", C.c_int), ("sub_begin", C.c_int), ("sub_end", C.c_int), ("edge_rows_only", C.c_int)]
+                ("edges", C.c_int), ("sub_begin", C.c_int), ("sub_end", C.c_int), ("edge_rows_only", C.c_int),
+                ("win_shift", C.c_int * 3)]
+
+
+MAX_RANKS = 8
+
+
+class VsbIbShard(C.Structure):
+    _fields_ = [("n_ranks", C.c_int), ("rank", C.c_int), ("fields", C.c_void_p * MAX_RANKS),
+                ("flags", C.c_void_p * MAX_RANKS), ("sums", C.c_void_p * MAX_RANKS),
+                ("need_lo", (C.c_int * 3) * MAX_RANKS), ("need_hi", (C.c_int * 3) * MAX_RANKS),
+                ("x_lo", C.c_int * MAX_RANKS), ("x_hi", C.c_int * MAX_RANKS),
+                ("marker_begin", C.c_int64), ("marker_end", C.c_int64), ("chunk_begin", C.c_int), ("chunk_end", C.c_int),
+                ("counter", C.c_void_p)]
 
 
 class VsbHostPlan(C.Structure):

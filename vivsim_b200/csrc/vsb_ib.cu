@@ -110,8 +110,9 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned n
 // 3-D: five CTAs of 128 threads per SM (<= 102 registers) = 740 resident CTAs, so that a body of up to ~2900 markers
 // (the 2562-marker sphere of the 256^3 case needs 641 CTAs) runs as ONE wave; at 110 registers the last 49 CTAs made
 // up a second wave that cost a whole CTA latency per stage.
-template <int DIM>
-__global__ void __launch_bounds__(kBlock, DIM == 3 ? 5 : 8) k_mdf_stage(const StepParams<DIM> sp, const MdfParams p, const BodyUpdate bu) {
+template <int DIM, bool SHARD>
+__global__ void __launch_bounds__(kBlock, DIM == 3 ? 5 : 8) k_mdf_stage(const StepParams<DIM> sp, const MdfParams p, const BodyUpdate bu,
+                                                                      const ShardArg<SHARD> sh) {
   using L = Lat<DIM>;
   constexpr int NS = (DIM == 2) ? 16 : 64;   // 4^D stencil points
   constexpr int G = (DIM == 2) ? 16 : 32;    // lanes per marker
@@ -134,10 +135,10 @@ __global__ void __launch_bounds__(kBlock, DIM == 3 ? 5 : 8) k_mdf_stage(const St
   // most of every SM to the bulk kernel running beside it): the groups then walk the marker list in batches.  The
   // trip count is the same for every thread, so the warp shuffles below stay converged.
   const long long mstride = nthreads / G;
-  const long long n_batch = (p.n_markers + mstride - 1) / mstride;
+  const long long n_batch = (p.m_end - p.m_begin + mstride - 1) / mstride;
   for (long long batch = 0; batch < n_batch; ++batch) {
-  const long long m = batch * mstride + gthread / G;
-  const bool active = m < p.n_markers;
+  const long long m = p.m_begin + batch * mstride + gthread / G;
+  const bool active = m < p.m_end;
 
   // stencil of this lane's marker: the same for every iteration
   float w[PPL];
@@ -186,11 +187,16 @@ __global__ void __launch_bounds__(kBlock, DIM == 3 ? 5 : 8) k_mdf_stage(const St
   for (int stage = p.stage; stage < p.stage_end; ++stage) {
     const bool last = stage == p.n_iter - 1;
     // clear the other parity's buffers for the next step
-    if (stage == 0 && batch == 0)
-      for (long long i = gthread; i < NC * wcells; i += nthreads) p.g_win_next[i] = 0.f;
+    if (stage == 0 && batch == 0) {
+      long long cb, ce;
+      clear_range(p, org[0], 0, cb, ce);
+      for (long long i = NC * cb + gthread; i < NC * ce; i += nthreads) p.g_win_next[i] = 0.f;
+    }
     if (stage < p.n_iter - 1 && batch == 0) {
       float* z = p.scratch_next + (long long)stage * NC * wcells;
-      for (long long i = gthread; i < NC * wcells; i += nthreads) z[i] = 0.f;
+      long long cb, ce;
+      clear_range(p, org[0], 1, cb, ce);
+      for (long long i = NC * cb + gthread; i < NC * ce; i += nthreads) z[i] = 0.f;
     }
 
     float um[DIM];
@@ -246,8 +252,11 @@ __global__ void __launch_bounds__(kBlock, DIM == 3 ? 5 : 8) k_mdf_stage(const St
 #pragma unroll
       for (int j = 0; j < PPL; ++j)
         if (ok[j]) {   // one vector reduction (red.global.add.v2/v4.f32) per stencil point
-          if constexpr (DIM == 2) atomicAdd(dst + idx[j], make_float2(spread_val[0] * w[j], spread_val[1] * w[j]));
-          else atomicAdd(dst + idx[j], make_float4(spread_val[0] * w[j], spread_val[1] * w[j], spread_val[2] * w[j], 0.f));
+          VecF val;
+          if constexpr (DIM == 2) val = make_float2(spread_val[0] * w[j], spread_val[1] * w[j]);
+          else val = make_float4(spread_val[0] * w[j], spread_val[1] * w[j], spread_val[2] * w[j], 0.f);
+          if constexpr (SHARD) shard_add<VecF>(sh, org[0], node[j][0], node[j][1], DIM == 3 ? node[j][DIM - 1] : 0, idx[j], val);
+          else atomicAdd(dst + idx[j], val);
         }
       if (last && p.body && gl == 0) {
 #pragma unroll
@@ -279,6 +288,7 @@ __global__ void __launch_bounds__(kBlock, DIM == 3 ? 5 : 8) k_mdf_stage(const St
       }
     }
   }
+  if constexpr (SHARD) __threadfence_system();   // this thread's reductions into peer memory are performed before the kernel ends
 }
 
 
@@ -306,8 +316,8 @@ struct TiledShared {
   float val[kTiledChunk][3];          // value spread by the marker (dF, or F at the last stage)
 };
 
-template <int DIM>
-__global__ void __launch_bounds__(kTiledChunk, 3) k_mdf_stage_tiled(const MdfParams p, const BodyUpdate bu) {
+template <int DIM, bool SHARD>
+__global__ void __launch_bounds__(kTiledChunk, 3) k_mdf_stage_tiled(const MdfParams p, const BodyUpdate bu, const ShardArg<SHARD> sh) {
   static_assert(DIM == 3, "the tiled stage is instantiated for D3Q19 bodies only");
   constexpr int NC = 4;
   extern __shared__ float4 s_dyn[];
@@ -331,16 +341,22 @@ __global__ void __launch_bounds__(kTiledChunk, 3) k_mdf_stage_tiled(const MdfPar
     for (int d = 0; d < 3; ++d) { org[d] = p.body->origin2[p.parity][d]; disp[d] = p.body->d[d]; }
   }
   // clear the other parity's buffers for the next step (as k_mdf_stage does)
-  if (stage == 0)
-    for (long long i = gthread; i < NC * wcells; i += nthreads) p.g_win_next[i] = 0.f;
+  if (stage == 0) {
+    long long cb, ce;
+    clear_range(p, org[0], 0, cb, ce);
+    for (long long i = NC * cb + gthread; i < NC * ce; i += nthreads) p.g_win_next[i] = 0.f;
+  }
   if (stage < p.n_iter - 1) {
     float* z = p.scratch_next + (long long)stage * NC * wcells;
-    for (long long i = gthread; i < NC * wcells; i += nthreads) z[i] = 0.f;
+    long long cb, ce;
+    clear_range(p, org[0], 1, cb, ce);
+    for (long long i = NC * cb + gthread; i < NC * ce; i += nthreads) z[i] = 0.f;
   }
 
-  const long long m_begin = p.chunk_offsets ? (long long)p.chunk_offsets[blockIdx.x] : (long long)blockIdx.x * kTiledChunk;
-  const int n_here = p.chunk_offsets ? min(p.chunk_offsets[blockIdx.x + 1] - (int)m_begin, kTiledChunk)
-                                     : (int)min((long long)kTiledChunk, p.n_markers - m_begin);
+  const int chunk = p.chunk_begin + (int)blockIdx.x;
+  const long long m_begin = p.chunk_offsets ? (long long)p.chunk_offsets[chunk] : p.m_begin + (long long)blockIdx.x * kTiledChunk;
+  const int n_here = p.chunk_offsets ? min(p.chunk_offsets[chunk + 1] - (int)m_begin, kTiledChunk)
+                                     : (int)min((long long)kTiledChunk, p.m_end - m_begin);
   // bounding box of the chunk's stencils (window-local cells), clipped to the window
   {
     int bmin[3] = {INT_MAX, INT_MAX, INT_MAX}, bmax[3] = {INT_MIN, INT_MIN, INT_MIN};
@@ -438,9 +454,12 @@ __global__ void __launch_bounds__(kTiledChunk, 3) k_mdf_stage_tiled(const MdfPar
 #pragma unroll
           for (int jz = 0; jz < 4; ++jz) {
             const float w = (wgt[2][jz] * wgt[1][jy]) * sm.w[tid][jx];
-            if (w != 0.f)
-              atomicAdd(dst + ((long long)(b0[0] + jx) * p.wsize[1] + (b0[1] + jy)) * p.wsize[2] + (b0[2] + jz),
-                        make_float4(spread_val[0] * w, spread_val[1] * w, spread_val[2] * w, 0.f));
+            if (w != 0.f) {
+              const long long ci = ((long long)(b0[0] + jx) * p.wsize[1] + (b0[1] + jy)) * p.wsize[2] + (b0[2] + jz);
+              const float4 val = make_float4(spread_val[0] * w, spread_val[1] * w, spread_val[2] * w, 0.f);
+              if constexpr (SHARD) shard_add<float4>(sh, org[0], b0[0] + jx, b0[1] + jy, b0[2] + jz, ci, val);
+              else atomicAdd(dst + ci, val);
+            }
           }
     }
     if (last && p.body) {
@@ -504,9 +523,12 @@ __global__ void __launch_bounds__(kTiledChunk, 3) k_mdf_stage_tiled(const MdfPar
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (cz0 + k < lo[2] + ext[2] && (acc[k][0] != 0.f || acc[k][1] != 0.f || acc[k][2] != 0.f))
-          atomicAdd(dst + ((long long)cx * p.wsize[1] + cy) * p.wsize[2] + (cz0 + k),
-                    make_float4(acc[k][0], acc[k][1], acc[k][2], 0.f));
+        if (cz0 + k < lo[2] + ext[2] && (acc[k][0] != 0.f || acc[k][1] != 0.f || acc[k][2] != 0.f)) {
+          const long long ci = ((long long)cx * p.wsize[1] + cy) * p.wsize[2] + (cz0 + k);
+          const float4 val = make_float4(acc[k][0], acc[k][1], acc[k][2], 0.f);
+          if constexpr (SHARD) shard_add<float4>(sh, org[0], cx, cy, cz0 + k, ci, val);
+          else atomicAdd(dst + ci, val);
+        }
     }
   }
 
@@ -527,6 +549,7 @@ __global__ void __launch_bounds__(kTiledChunk, 3) k_mdf_stage_tiled(const MdfPar
       }
     }
   }
+  if constexpr (SHARD) __threadfence_system();
 }
 
 // body update by one thread (see body_update in vsb_step.cuh)
@@ -551,6 +574,8 @@ static int mdf_impl(const VsbStepArgs& sa, const VsbMdfArgs& a, const VsbBodyPar
   p.host_mail = (a.body && !p.update_body) ? a.host_mail : nullptr;
   p.mail_seq = a.mail_seq;
   p.chunk_offsets = nullptr;
+  p.m_begin = 0; p.m_end = a.n_markers; p.chunk_begin = 0; p.clear_mode = 0;
+  p.nbr_list = a.nbr_list; p.nbr_stride = a.nbr_stride;
   p.rotation = (DIM == 2 && a.rotation) ? 1 : 0;
   p.center[0] = a.center[0]; p.center[1] = a.center[1];
   BodyUpdate bu{};
@@ -566,8 +591,8 @@ static int mdf_impl(const VsbStepArgs& sa, const VsbMdfArgs& a, const VsbBodyPar
     // hardware cluster barriers between the iterations (vsb_mdf_cluster.cu)
     use_cluster = (mode == 0 || mode == 2) && a.u_win == nullptr && mdf_cluster2d_supported(p);
     if (mode == 2 && !use_cluster) {
-      set_error("vsb_ib_mdf: chain_mode 2 (cluster) needs a 2-D body of at most 512 markers, no u_win, and a window "
-                "whose three work slabs fit the cluster's shared memory");
+      set_error("vsb_ib_mdf: chain_mode 2 (cluster) needs a 2-D body of at most 512 markers, no u_win, and the "
+                "neighbour list (nbr_list, nbr_stride <= 48)");
       return VSB_ERR_INVALID;
     }
     if (use_cluster) return launch_mdf_cluster2d(sp, p, bu, stream);
@@ -579,8 +604,9 @@ static int mdf_impl(const VsbStepArgs& sa, const VsbMdfArgs& a, const VsbBodyPar
   // CTAs (at most 120 of 128 threads) are co-resident whatever else runs on the device.  Large bodies: one launch
   // per iteration.
   if (a.barrier && nb <= 120 && mode != 3) {   // (one marker per lane group: the kernel keeps u_m and F in registers across stages)
-    void* kargs[] = {(void*)&sp, (void*)&p, (void*)&bu};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_mdf_stage<DIM>, dim3(nb), dim3(kBlock), kargs, 0, stream);
+    ShardArg<false> none;
+    void* kargs[] = {(void*)&sp, (void*)&p, (void*)&bu, (void*)&none};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_mdf_stage<DIM, false>, dim3(nb), dim3(kBlock), kargs, 0, stream);
     if (e != cudaSuccess) return cuda_fail(e, "vsb_ib_mdf (cooperative launch)");
   } else if (DIM == 3 && a.u_win != nullptr && !getenv("VSB_MDF_UNTILED")) {
     // dense body with a precomputed window velocity: every stage reads a window field -> shared-memory tiles
@@ -588,7 +614,7 @@ static int mdf_impl(const VsbStepArgs& sa, const VsbMdfArgs& a, const VsbBodyPar
       constexpr size_t smem = (size_t)kTileCells * sizeof(float4) + sizeof(TiledShared);
       static bool configured = false;
       if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_mdf_stage_tiled<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_mdf_stage_tiled<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "vsb_ib_mdf (shared-memory opt-in)");
         configured = true;
       }
@@ -597,7 +623,7 @@ static int mdf_impl(const VsbStepArgs& sa, const VsbMdfArgs& a, const VsbBodyPar
       const unsigned nbt = cut ? (unsigned)a.n_chunks : blocks_for(a.n_markers, kTiledChunk);
       for (int k = 0; k < a.n_iter; ++k) {
         p.stage = k; p.stage_end = k + 1;
-        k_mdf_stage_tiled<3><<<nbt, kTiledChunk, smem, stream>>>(p, bu);
+        k_mdf_stage_tiled<3, false><<<nbt, kTiledChunk, smem, stream>>>(p, bu, ShardArg<false>{});
       }
     }
   } else {
@@ -615,10 +641,42 @@ static int mdf_impl(const VsbStepArgs& sa, const VsbMdfArgs& a, const VsbBodyPar
     const unsigned nbc = (cap > 0 && nb > (unsigned)cap) ? (unsigned)cap : nb;
     for (int k = 0; k < a.n_iter; ++k) {
       p.stage = k; p.stage_end = k + 1;
-      k_mdf_stage<DIM><<<nbc, kBlock, 0, stream>>>(sp, p, bu);
+      k_mdf_stage<DIM, false><<<nbc, kBlock, 0, stream>>>(sp, p, bu, ShardArg<false>{});
     }
   }
   VSB_LAUNCH_CHECK("vsb_ib_mdf");
+  return VSB_OK;
+}
+
+// One iteration (p.stage) of this rank's share of a sharded chain: the same kernels with the multicast spread.
+// Stage 0 reads p.u_win (never the populations), so StepParams is a dummy.
+int launch_mdf_stage_sharded(int dim, const MdfParams& p_in, const ShardDev& shd, bool tiled, unsigned n_chunks, cudaStream_t stream) {
+  ShardArg<true> sh;
+  static_cast<ShardDev&>(sh) = shd;
+  BodyUpdate bu{};
+  MdfParams p = p_in;
+  p.update_body = 0;          // the partial sums are combined and the body advanced after the last flag barrier
+  p.host_mail = nullptr;
+  const long long n_mine = p.m_end - p.m_begin;
+  if (n_mine <= 0) return VSB_OK;
+  if (dim == 3 && tiled) {
+    constexpr size_t smem = (size_t)kTileCells * sizeof(float4) + sizeof(TiledShared);
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(k_mdf_stage_tiled<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_fail(e, "vsb_ibshard_chain (shared-memory opt-in)");
+      configured = true;
+    }
+    const unsigned nbt = p.chunk_offsets ? n_chunks : blocks_for(n_mine, kTiledChunk);
+    if (nbt > 0) k_mdf_stage_tiled<3, true><<<nbt, kTiledChunk, smem, stream>>>(p, bu, sh);
+  } else if (dim == 3) {
+    StepParams<3> sp{};
+    k_mdf_stage<3, true><<<blocks_for(n_mine * 32, kBlock), kBlock, 0, stream>>>(sp, p, bu, sh);
+  } else {
+    StepParams<2> sp{};
+    k_mdf_stage<2, true><<<blocks_for(n_mine * 16, kBlock), kBlock, 0, stream>>>(sp, p, bu, sh);
+  }
+  VSB_LAUNCH_CHECK("vsb_ibshard_chain (iteration)");
   return VSB_OK;
 }
 

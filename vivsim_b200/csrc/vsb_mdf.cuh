@@ -31,7 +31,54 @@ struct MdfParams {
   const int* chunk_offsets; // tiled kernel: marker range of every CTA (NULL: 256 consecutive markers each)
   int rotation;             // 2-D: degree of freedom 2 of the body is a rotation about `center`
   float center[2];
+  long long m_begin, m_end; // markers handled by this launch (a rank's share when the chain is sharded over GPUs)
+  int chunk_begin;          // tiled kernel: first chunk of this launch
+  // Which part of the next step's buffers this launch clears: everything (clear_mode 0), or only the window x-planes
+  // this rank's copy can receive contributions in (sharded chain): the slab's x-range +- 2 for the force field, the
+  // need box's x-range for the work fields.
+  const unsigned short* nbr_list;   // cluster kernel: per marker, the markers whose stencils can overlap its own
+  int nbr_stride;
+  int clear_mode;
+  int slab_x[2];            // global x-range of this rank's slab
+  int need_x[2];            // window-local x-range of this rank's need box
 };
+
+// Flat range [begin, end) of window cells to clear in a field: force field (which = 0) or work field (which = 1).
+__device__ __forceinline__ void clear_range(const MdfParams& p, int org_x, int which, long long& begin, long long& end) {
+  const long long plane = (long long)p.wsize[1] * (p.wsize[2] > 0 ? p.wsize[2] : 1);   // 2-D: wsize[2] unused
+  int lo = 0, hi = p.wsize[0];
+  if (p.clear_mode) {
+    lo = which ? p.need_x[0] : p.slab_x[0] - org_x - 2;
+    hi = which ? p.need_x[1] : p.slab_x[1] - org_x + 2;
+    lo = lo < 0 ? 0 : lo;
+    hi = hi > p.wsize[0] ? p.wsize[0] : hi;
+    if (hi < lo) hi = lo;
+  }
+  begin = lo * plane;
+  end = hi * plane;
+}
+
+// Sharded chain (vsb_ibshard.cu): where a value spread onto window cell (nx, ny, nz) has to go.  Work-field stages: the
+// copy of every rank whose need box contains the cell; last stage: the copy of the rank whose slab contains the
+// cell's global x.
+struct ShardDev {
+  int n_ranks, by_slab;
+  float* dst[kMaxRanks];
+  int lo[kMaxRanks][3], hi[kMaxRanks][3];   // need boxes, window-local [lo, hi)
+  int x_lo[kMaxRanks], x_hi[kMaxRanks];     // slabs, global x [lo, hi)
+};
+template <bool SHARD> struct ShardArg {};
+template <> struct ShardArg<true> : ShardDev {};
+
+template <typename VecF>
+__device__ __forceinline__ void shard_add(const ShardDev& sh, int org_x, int nx, int ny, int nz, long long idx, VecF v) {
+  for (int r = 0; r < sh.n_ranks; ++r) {
+    const bool in = sh.by_slab ? (org_x + nx >= sh.x_lo[r] && org_x + nx < sh.x_hi[r])
+                               : (nx >= sh.lo[r][0] && nx < sh.hi[r][0] && ny >= sh.lo[r][1] && ny < sh.hi[r][1] &&
+                                  nz >= sh.lo[r][2] && nz < sh.hi[r][2]);
+    if (in) atomicAdd(reinterpret_cast<VecF*>(sh.dst[r]) + idx, v);
+  }
+}
 
 // Position, target velocity and lever arm of marker m for the body state in p.body (dyn.py:69-120):
 //   translation   pos = markers0 + d                                 (get_markers_coords_2dof, dyn.py:69-81)
@@ -87,6 +134,10 @@ __device__ __forceinline__ void finish_body(const MdfParams& p, const BodyUpdate
     mail->seq = p.mail_seq >= 0 ? p.mail_seq : p.body->step + 1;   // < 0: the step being taken (graph replays)
   }
 }
+
+// One iteration of this rank's share of a sharded chain (defined in vsb_ib.cu next to the kernels it instantiates).
+int launch_mdf_stage_sharded(int dim, const MdfParams& p, const ShardDev& sh, bool tiled, unsigned n_chunks,
+                             cudaStream_t stream);
 
 // Whole chain of a small 2-D body in one thread-block cluster (vsb_mdf_cluster.cu).
 bool mdf_cluster2d_supported(const MdfParams& p);

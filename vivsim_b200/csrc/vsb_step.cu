@@ -434,7 +434,7 @@ int fill_params(const VsbStepArgs& a, StepParams<DIM>& p) {
   p.do_stream = a.do_stream; p.do_collide = a.do_collide; p.forcing = a.forcing;
   VSB_REQUIRE(a.forcing >= VSB_FORCE_NONE && a.forcing <= VSB_FORCE_GUO, "vsb_step: unknown forcing %d", a.forcing);
   p.rx = make_relax(a.omega);
-  for (int d = 0; d < 3; ++d) { p.g0[d] = a.g_uniform[d]; p.worg[d] = a.win_origin[d]; p.wsz[d] = a.win_size[d]; }
+  for (int d = 0; d < 3; ++d) { p.g0[d] = a.g_uniform[d]; p.worg[d] = a.win_origin[d]; p.wsz[d] = a.win_size[d]; p.wshift[d] = a.win_shift[d]; }
   p.gwin = a.g_win; p.body = a.body; p.parity = a.parity & 1; p.mask = nullptr;
   if (a.g_win) for (int d = 0; d < DIM; ++d) VSB_REQUIRE(a.win_size[d] > 0, "vsb_step: empty force window");
   VSB_REQUIRE(a.band >= 0 && a.band <= 2, "vsb_step: band must be 0, 1 or 2");

@@ -54,6 +54,7 @@ template <int DIM> struct StepParams {
   float g0[3];
   const float* gwin;
   int worg[3], wsz[3];
+  int wshift[3];        // added to body->origin2 (global coordinates of a slab-decomposed run -> local)
   const VsbBodyState* body;
   int parity;
   const uint8_t* mask;
@@ -91,7 +92,9 @@ __device__ __forceinline__ int wrap(int i, int n) {
 template <int DIM>
 __device__ __forceinline__ void window_origin(const StepParams<DIM>& p, int (&worg)[3]) {
   if (p.body) {
-    worg[0] = p.body->origin2[p.parity][0]; worg[1] = p.body->origin2[p.parity][1]; worg[2] = p.body->origin2[p.parity][2];
+    worg[0] = p.body->origin2[p.parity][0] + p.wshift[0];
+    worg[1] = p.body->origin2[p.parity][1] + p.wshift[1];
+    worg[2] = p.body->origin2[p.parity][2] + p.wshift[2];
   } else {
     worg[0] = p.worg[0]; worg[1] = p.worg[1]; worg[2] = p.worg[2];
   }

@@ -178,7 +178,112 @@ class LocalHalo:
         return False
 
 
-def localize_spec(spec, slab, local_ib=None):
+def plan_ib_shards(markers, window, world, dense, moving_in_window=False, margin=2):
+    """Divide the markers of one immersed body among `world` ranks (host logic, NumPy only).
+
+    The ranks share the multi-direct-forcing chain (csrc/vsb_ibshard.cu): rank r handles a contiguous range of the
+    stored marker list and needs, in its copy of the window fields, every cell its markers' 4-point stencils can touch
+    -- its NEED BOX.  Markers are split into equal-count groups along the axis of the body's largest extent (for the
+    z-aligned cylinder of BASELINE config 5 that is z: every rank gets a slice of the cylinder), so the boxes are compact
+    and neighbouring boxes overlap by a few cells only.
+
+    dense: the tiled kernel is used -- within each group the markers are ordered and cut into chunks by
+    stepper.cut_marker_chunks.  moving_in_window: the body moves relative to the window (follow = 0, or it rotates),
+    so every rank needs the whole window; otherwise the window follows the body and `margin` cells cover the
+    sub-cell drift.
+    Returns dict(perm, marker_ranges (world, 2), chunk_offsets | None, chunk_ranges (world, 2), need_lo, need_hi
+    (world, dim) window-local [lo, hi), axis)."""
+    from .stepper import cut_marker_chunks
+    markers = np.asarray(markers, dtype=np.float32)
+    n, dim = markers.shape
+    origin, size = window
+    origin = np.floor(np.asarray(origin, dtype=np.float64)).astype(np.int64)
+    size = np.asarray(size, dtype=np.int64)
+    axis = int(np.argmax(markers.max(axis=0) - markers.min(axis=0))) if n else 0
+    order = np.argsort(markers[:, axis], kind="stable")
+    bounds = [(n * r) // world for r in range(world + 1)]
+    perm_parts, marker_ranges, chunk_ranges, offsets = [], [], [], [0]
+    pos = 0
+    for r in range(world):
+        grp = np.sort(order[bounds[r]:bounds[r + 1]])          # the caller's order within a group
+        if dense and grp.size:
+            sub_perm, sub_off = cut_marker_chunks(markers[grp])
+            grp = grp[sub_perm]
+            c0 = len(offsets) - 1
+            offsets.extend((pos + sub_off[1:]).tolist())
+            chunk_ranges.append((c0, len(offsets) - 1))
+        else:
+            chunk_ranges.append((len(offsets) - 1, len(offsets) - 1))
+        perm_parts.append(grp)
+        marker_ranges.append((pos, pos + grp.size))
+        pos += grp.size
+    perm = np.concatenate(perm_parts) if perm_parts else np.zeros(0, dtype=np.int64)
+    need_lo = np.zeros((world, dim), dtype=np.int64)
+    need_hi = np.zeros((world, dim), dtype=np.int64)
+    for r, (b, e) in enumerate(marker_ranges):
+        if e == b:
+            continue                                          # empty share: empty box
+        if moving_in_window:
+            need_hi[r] = size
+            continue
+        base = np.floor(markers[perm[b:e]].astype(np.float64) - origin).astype(np.int64)
+        need_lo[r] = np.clip(base.min(axis=0) - 1 - margin, 0, size)
+        need_hi[r] = np.clip(base.max(axis=0) + 3 + margin, 0, size)
+    return dict(perm=perm, marker_ranges=np.asarray(marker_ranges, dtype=np.int64),
+                chunk_offsets=np.asarray(offsets, dtype=np.int32) if dense else None,
+                chunk_ranges=np.asarray(chunk_ranges, dtype=np.int64), need_lo=need_lo, need_hi=need_hi, axis=axis)
+
+
+class IbShard:
+    """Everything a rank needs to take part in the shared IB chain: the marker plan and the peer-mapped window fields,
+    flag words and sum slots (torch.distributed._symmetric_memory), packed into a VsbIbShard."""
+
+    def __init__(self, slab, ib, n_iter, moving_in_window, group=None):
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib as L
+        group = group if group is not None else dist.group.WORLD
+        dev = torch.device("cuda", torch.cuda.current_device())
+        dim = slab.dim
+        if slab.world > L.MAX_RANKS:
+            raise ValueError(f"the shared IB chain supports at most {L.MAX_RANKS} ranks")
+        origin, size = ib["window"]
+        self.win_size = tuple(int(n) for n in size)
+        markers = np.asarray(ib["markers"], dtype=np.float32)
+        wcells = int(np.prod(self.win_size))
+        dense = dim == 3 and markers.shape[0] * 4 ** dim > 2 * wcells and markers.shape[0] > 480
+        self.plan = plan_ib_shards(markers, ib["window"], slab.world, dense, moving_in_window)
+        nc = 2 if dim == 2 else 4
+        self.fields = symm.empty((2, n_iter + 1) + self.win_size + (nc,), dtype=torch.float32, device=dev)
+        self.fields.zero_()
+        self.flags = symm.empty((16,), dtype=torch.int32, device=dev)
+        self.flags.zero_()
+        self.sums = symm.empty((L.MAX_RANKS * 4,), dtype=torch.float32, device=dev)
+        self.sums.zero_()
+        handles = [symm.rendezvous(t, group) for t in (self.fields, self.flags, self.sums)]
+        torch.cuda.synchronize()
+        dist.barrier(group)
+        self.counter = torch.zeros(4, dtype=torch.int32, device=dev)
+        sh = L.VsbIbShard()
+        sh.n_ranks, sh.rank = slab.world, slab.rank
+        for r in range(slab.world):
+            sh.fields[r], sh.flags[r], sh.sums[r] = (h.buffer_ptrs[r] for h in handles)
+            for d in range(dim):
+                sh.need_lo[r][d] = int(self.plan["need_lo"][r][d])
+                sh.need_hi[r][d] = int(self.plan["need_hi"][r][d])
+            sh.x_lo[r] = r * slab.nx_local
+            sh.x_hi[r] = (r + 1) * slab.nx_local
+        sh.marker_begin, sh.marker_end = (int(x) for x in self.plan["marker_ranges"][slab.rank])
+        sh.chunk_begin, sh.chunk_end = (int(x) for x in self.plan["chunk_ranges"][slab.rank])
+        sh.counter = self.counter.data_ptr()
+        self.args = sh
+        self.slab = slab
+        self._handles = handles
+
+    def timed_out(self):
+        return bool(self.counter[2].item())
+
+
+def localize_spec(spec, slab, local_ib=None, ib_mode="owner"):
     """Per-rank step description: local extent with ghost layers, x-face operations only on the owning rank,
     immersed body (``spec['ib']`` or ``local_ib(slab)``, global coordinates) shifted to local coordinates."""
     out = dict(spec)
@@ -204,15 +309,17 @@ def localize_spec(spec, slab, local_ib=None):
     out["post"] = post
     ib = local_ib(slab) if local_ib is not None else spec.get("ib")
     out["ib"] = None
-    if ib is not None:
+    if ib is not None and ib_mode == "shard":
+        out["ib"] = dict(ib)                  # global coordinates: every rank takes part (IbShard)
+    elif ib is not None:
         (ox, *orest), size = ib["window"]
         lo, hi = int(np.floor(ox)), int(np.floor(ox)) + int(size[0])
         inside = lo >= slab.x0 + 2 and hi <= slab.x0 + slab.nx_local - 2
         overlaps = hi > slab.x0 and lo < slab.x0 + slab.nx_local
         if overlaps and not inside:
             raise ValueError(f"the IB window x-range [{lo}, {hi}) must lie at least 2 layers inside one slab "
-                             f"(rank {slab.rank} owns [{slab.x0}, {slab.x0 + slab.nx_local})); markers near a cut "
-                             "need a wider exchange that is not implemented")
+                             f"(rank {slab.rank} owns [{slab.x0}, {slab.x0 + slab.nx_local})) for ib='owner'; "
+                             "use ib='shard' (or 'auto'), which shares the chain among all ranks")
         if inside:
             loc_ib = dict(ib)
             markers = np.array(ib["markers"], dtype=np.float32, copy=True)
@@ -234,15 +341,40 @@ class SlabStepper:
     NVLink; graph-capturable).  halo = "nccl": torch.distributed send/recv of the edge layers.  "auto": peer when the
     symmetric-memory rendezvous succeeds, else NCCL."""
 
-    def __init__(self, spec, rank=None, world=None, group=None, local_ib=None, body=None, halo="auto", **kw):
+    def __init__(self, spec, rank=None, world=None, group=None, local_ib=None, body=None, halo="auto", ib="auto", **kw):
+        """ib: how an immersed body of the global spec is distributed -- "owner": the rank whose slab contains the IB
+        window (>= 2 layers from a cut) computes the whole chain; "shard": the markers are divided among all ranks and
+        the window fields are shared through peer memory (a body may sit on or move across a cut; the chain of a
+        large body is spread over all GPUs); "auto": "owner" when the window of a fixed body fits one slab, else
+        "shard".  Bodies given per slab through local_ib are always "owner"."""
         from .stepper import Stepper
         self.group = group
         if world is None:
             world = dist.get_world_size(group) if dist.is_initialized() else 1
             rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.slab = Slab(spec["shape"], rank, world)
-        self.local_spec = localize_spec(spec, self.slab, local_ib)
+        if ib not in ("auto", "owner", "shard"):
+            raise ValueError("ib must be 'auto', 'owner' or 'shard'")
+        gib = spec.get("ib") if local_ib is None else None
+        if gib is None or world == 1:
+            ib = "owner"
+        elif ib == "auto":
+            (ox, *_), size = gib["window"]
+            lo, hi = int(np.floor(ox)), int(np.floor(ox)) + int(size[0])
+            k = lo // self.slab.nx_local
+            fits = lo >= k * self.slab.nx_local + 2 and hi <= (k + 1) * self.slab.nx_local - 2
+            ib = "owner" if (fits and body is None) else "shard"
+        self.ib_mode = ib
+        self.local_spec = localize_spec(spec, self.slab, local_ib, ib)
         has_body = self.local_spec["ib"] is not None
+        self.ib_shard = None
+        if ib == "shard":
+            if not torch.cuda.is_available():
+                raise RuntimeError("ib='shard' shares the IB chain through peer-mapped GPU memory")
+            follow = int(kw.get("follow", 1))
+            moving_in_window = body is not None and (follow == 0 or bool(body.get("rotation", False)))
+            self.ib_shard = IbShard(self.slab, gib, int(gib.get("n_iter", 5)), moving_in_window, group)
+            kw = dict(kw, ib_shard=self.ib_shard, dyn_mode=kw.get("dyn_mode", "device"))
         self.peer = None
         self.halo_error = None
         if world > 1 and halo in ("auto", "peer"):
@@ -291,10 +423,27 @@ class SlabStepper:
         """Sum over all bodies / ranks of the hydrodynamic force on the bodies (small all-reduce)."""
         st = self.stepper
         dim = st.dim
+        # sharded chain: every rank holds the forces of its share of the markers (the rest are zero)
         h = (-st.marker_force.sum(dim=0)) if self.owns_body else torch.zeros(dim, device=st.device)
         if self.slab.world > 1:
             dist.all_reduce(h, group=self.group)
         return h
+
+    def marker_force(self):
+        """+F on every marker in the caller's order, on every rank (all-reduce of the ranks' shares when the chain is
+        shared; zeros on ranks that do not own the body otherwise)."""
+        st = self.stepper
+        if not self.owns_body:
+            f = None
+        else:
+            f = st.marker_force.clone()
+        if self.slab.world > 1:
+            n = torch.tensor([0 if f is None else f.shape[0]], device=st.device)
+            dist.all_reduce(n, op=dist.ReduceOp.MAX, group=self.group)
+            if f is None:
+                f = torch.zeros((int(n), st.dim), device=st.device)
+            dist.all_reduce(f, group=self.group)
+        return f
 
     # -- stepping
     def _exchange(self):

@@ -77,7 +77,7 @@ def cut_marker_chunks(markers):
 
 class Stepper:
     def __init__(self, spec, device="cuda", rows=None, vec=0, body=None, dyn_mode="host", follow=1, use_graph=False,
-                 fuse_ib=True, fuse_edges=True, overlap=True, buffers=None, ib_chain="auto"):
+                 fuse_ib=True, fuse_edges=True, overlap=True, buffers=None, ib_chain="auto", ib_shard=None):
         """rows: (begin, end) range of the slowest axis that is physical domain (ghost layers outside; slab
         decomposition).  body: dict(m, k, c, added_mass, n_dof=2, d0, v0, a0) for a moving rigid body coupled by
         Newmark-beta; m, k, c scalars (dyn.py:44-46) or (n_dof, n_dof) matrices / length-n_dof diagonals
@@ -88,6 +88,8 @@ class Stepper:
         ib_chain: how a small body's MDF iterations are chained in one launch -- "auto", "barrier" (grid barriers,
         cooperative launch), "cluster" (one thread-block cluster, work fields in distributed shared memory; 2-D,
         <= 512 markers) or "launches" (one launch per iteration).
+        ib_shard: multidevice.IbShard -- this stepper is one slab of a decomposed run and shares the IB chain with the
+        other ranks (spec['ib'] and the body then carry GLOBAL coordinates).
         fuse_ib / fuse_edges / overlap: use the single-kernel IB path, the single-kernel wall path and concurrent
         streams when the configuration allows (all three only change scheduling, not arithmetic per cell)."""
         L.lib()
@@ -123,6 +125,10 @@ class Stepper:
         if ib_chain not in L.CHAIN:
             raise ValueError(f"ib_chain must be one of {sorted(L.CHAIN)}, got {ib_chain!r}")
         self._ib_chain = ib_chain
+        self._shard = ib_shard
+        # extent the IB window and the body live in: the whole decomposed grid when the chain is shared
+        self._gshape = tuple(ib_shard.slab.global_shape) if ib_shard is not None else self.shape
+        self._xshift = (1 - ib_shard.slab.x0) if ib_shard is not None else 0
         self._side = None
 
         a = L.VsbStepArgs()
@@ -201,7 +207,7 @@ class Stepper:
         a.do_stream, a.do_collide = 1, 1
         a.f_in, a.f_out = self._bufs[0].data_ptr(), self._bufs[1].data_ptr()
         self.edge_fused = bool(n_bc) and self._want["fuse_edges"] and bool(lib.vsb_edge_fused_supported(C.byref(a)))
-        self.ib_fused = (self.ib is not None and self._want["fuse_ib"]
+        self.ib_fused = (self.ib is not None and self._want["fuse_ib"] and self._shard is None
                          and bool(lib.vsb_ib_fused_supported(C.byref(self._mdf))))
         # concurrent branches need every kernel of a step to be independent of launch order
         self.overlap = (self._want["overlap"] and self.ib is not None and (n_bc == 0 or self.edge_fused))
@@ -227,8 +233,8 @@ class Stepper:
         self.win_size = tuple(int(n) for n in size)
         for d in range(dim):
             lo, n = int(np.floor(self.win_origin0[d])), self.win_size[d]
-            if n < 4 or lo < 0 or lo + n > self.shape[d]:
-                raise ValueError(f"IB window axis {d}: [{lo}, {lo + n}) must lie inside the grid [0, {self.shape[d]})")
+            if n < 4 or lo < 0 or lo + n > self._gshape[d]:
+                raise ValueError(f"IB window axis {d}: [{lo}, {lo + n}) must lie inside the grid [0, {self._gshape[d]})")
         if body is None:
             rel = markers - np.floor(np.asarray(self.win_origin0, dtype=np.float32))
             if (np.floor(rel).min(axis=0) < 1).any() or (np.floor(rel).max(axis=0) + 2 >= np.asarray(self.win_size)).any():
@@ -239,12 +245,24 @@ class Stepper:
         # dense marker sets (many stencil points per window cell, e.g. a finely meshed 3-D surface) interpolate a
         # precomputed window velocity; sparse ones take it from the streamed populations at their stencil points
         wcells = int(np.prod(self.win_size))
-        self._use_uwin = self.n_markers * 4 ** dim > 2 * wcells
+        self._use_uwin = self.n_markers * 4 ** dim > 2 * wcells or self._shard is not None
         # The tiled MDF kernel (dense 3-D bodies) gives each CTA 256 consecutive markers and privatises their part of
         # the window in shared memory, so consecutive markers must be close in space: store them sorted by
         # (x column of 4 cells, y column of 4 cells, z).  Outputs are handed back in the caller's order.
         self._perm = self._inv_perm = None
-        if dim == 3 and self._use_uwin and self.n_markers > 480 and ib.get("sort_markers", True):
+        self._chunk_offsets = None
+        if self._shard is not None:
+            # shared chain: the plan fixes the storage order (rank shares are contiguous) and the chunks
+            plan = self._shard.plan
+            perm = plan["perm"]
+            inv = np.empty_like(perm)
+            inv[perm] = np.arange(perm.size)
+            markers = np.ascontiguousarray(markers[perm])
+            self._perm = torch.as_tensor(perm, device=dev)
+            self._inv_perm = torch.as_tensor(inv, device=dev)
+            if plan["chunk_offsets"] is not None:
+                self._chunk_offsets = torch.as_tensor(plan["chunk_offsets"], device=dev)
+        elif dim == 3 and self._use_uwin and self.n_markers > 480 and ib.get("sort_markers", True):
             perm, offsets = cut_marker_chunks(markers)
             inv = np.empty_like(perm)
             inv[perm] = np.arange(perm.size)
@@ -257,9 +275,15 @@ class Stepper:
         # set the next step will accumulate into (see vsb_ib_mdf), so there is no memset on the step path
         # layout: cell-major with the components packed per cell (float2 in 2-D, float4 in 3-D)
         nc = 2 if dim == 2 else 4
-        self._ib_buf = torch.zeros((2, self.n_iter) + self.win_size + (nc,), device=dev)
+        if self._shard is not None:
+            self._ib_buf = self._shard.fields           # (2, n_iter + 1, *window, nc), peer-mapped; slot n_iter = velocity
+            if tuple(self._ib_buf.shape) != (2, self.n_iter + 1) + self.win_size + (nc,):
+                raise ValueError("ib_shard was built for another window / n_iter")
+            self._u_win = None
+        else:
+            self._ib_buf = torch.zeros((2, self.n_iter) + self.win_size + (nc,), device=dev)
+            self._u_win = torch.zeros(self.win_size + (nc,), device=dev) if self._use_uwin else None
         self._g_win = self._ib_buf[0, 0]
-        self._u_win = torch.zeros(self.win_size + (nc,), device=dev) if self._use_uwin else None
         self._marker_u = torch.zeros((self.n_markers, dim), device=dev)
         self._marker_force = torch.zeros((self.n_markers, dim), device=dev)   # +F; reaction on the body is -F
         tgt = ib.get("u_target")
@@ -284,9 +308,10 @@ class Stepper:
         for d in range(dim):
             m.win_origin0[d] = int(np.floor(self.win_origin0[d]))
             m.win_size[d] = self.win_size[d]
-            a.win_origin[d] = m.win_origin0[d]
+            a.win_origin[d] = m.win_origin0[d] + (self._xshift if d == 0 else 0)   # the fluid kernels index the local slab
             a.win_size[d] = self.win_size[d]
-        if self._perm is not None:
+        a.win_shift[0] = self._xshift
+        if self._chunk_offsets is not None:
             m.chunk_offsets = self._chunk_offsets.data_ptr()
             m.n_chunks = self._chunk_offsets.numel() - 1
         m.markers0 = self._markers.data_ptr()
@@ -294,8 +319,28 @@ class Stepper:
         self._mdf_barrier = torch.zeros(2, dtype=torch.int64, device=dev)
         m.barrier = self._mdf_barrier.data_ptr()
         lanes = 16 if dim == 2 else 32
-        m.chain_mode = L.CHAIN[self._ib_chain]
-        self._mdf_one_launch = (self.n_markers * lanes + 127) // 128 <= 120 and self._ib_chain != "launches"
+        chain = self._ib_chain
+        if chain in ("auto", "cluster") and dim == 2 and self.n_markers <= 512:
+            # the cluster kernel keeps, per marker, the markers whose 4 x 4 stencil can overlap its own (within 3 cells
+            # per axis, whatever the rigid motion): at most 96.  The marker set is rigid, so check once.
+            d2 = ((markers[:, None, :].astype(np.float64) - markers[None, :, :]) ** 2).sum(axis=2)
+            near = d2 < (4 * 2 ** 0.5 + 1.5) ** 2            # |base difference| <= 3 per axis => distance < 4 sqrt(2) + 1
+            stride = int(near.sum(axis=1).max())
+            if stride > 48 and chain == "cluster":
+                raise ValueError("ib_chain='cluster': more than 48 markers within reach of one marker's stencil")
+            if stride > 48:
+                chain = "barrier"
+            else:
+                stride = (stride + 3) // 4 * 4
+                nbr = np.full((stride, 512), 0xFFFF, dtype=np.uint16)      # neighbour-major, one column per marker
+                for i in range(self.n_markers):
+                    js = np.flatnonzero(near[i])
+                    nbr[:js.size, i] = js
+                self._nbr = torch.as_tensor(nbr.view(np.int16), device=dev)
+                m.nbr_list, m.nbr_stride = self._nbr.data_ptr(), stride
+        m.chain_mode = L.CHAIN[chain]
+        self._mdf_one_launch = ((self.n_markers * lanes + 127) // 128 <= 120 and self._ib_chain != "launches"
+                                and self._shard is None)
         m.marker_u = self._marker_u.data_ptr()
         m.marker_force = self._marker_force.data_ptr()
         a.g_win = self._g_win.data_ptr()
@@ -338,15 +383,18 @@ class Stepper:
                 for i in range(n):
                     bp.added_mass_v[i] = float(av[i])
             else:
-                bp.m, bp.k, bp.c, bp.added_mass = (float(mats[k_]) for k_ in ("m", "k", "c")) + (float(added),)
+                bp.m, bp.k, bp.c, bp.added_mass = float(mats["m"]), float(mats["k"]), float(mats["c"]), float(added)
             if self.rotation:
                 bp.rotation = 1
                 bp.center[0], bp.center[1] = (float(x) for x in body["center"])
                 m.rotation = 1
                 m.center[0], m.center[1] = bp.center[0], bp.center[1]
+            if self._shard is not None and dyn_mode != "device":
+                raise ValueError("a body whose IB chain is shared among ranks needs dyn_mode='device' (every rank "
+                                 "advances an identical replica of the rigid-body state)")
             for d in range(3):
                 bp.origin0[d] = self.win_origin0[d] if d < dim else 0.0
-                bp.grid_size[d] = self.shape[d] if d < dim else 1
+                bp.grid_size[d] = self._gshape[d] if d < dim else 1
                 bp.win_size[d] = self.win_size[d] if d < dim else 1
             self._bparams = bp
             # optional per-step record of (d, h) (what the reference's update_chunk scan returns): a ring written by
@@ -390,7 +438,7 @@ class Stepper:
             shifted = np.float32(self.win_origin0[k]) + (np.float32(d[k]) if self.follow else np.float32(0))
             o = int(np.floor(shifted)) if self.follow == 2 else int(shifted)   # int(): truncation like astype(int32)
             if self.follow:             # inside the grid, like the start of a lax.dynamic_slice
-                o = max(min(o, self.shape[k] - self.win_size[k]), 0)
+                o = max(min(o, self._gshape[k] - self.win_size[k]), 0)
             out[k] = o
         return out
 
@@ -401,6 +449,8 @@ class Stepper:
         lo = int(np.floor(self.win_origin0[axis]))
         hi = lo + self.win_size[axis]
         rb, re = (self.rows if axis == 0 else (0, self.shape[axis]))
+        if axis == 0 and self._shard is not None:      # global coordinates: only the ends of the whole grid are walls
+            rb, re = 0, self._gshape[0]
         if (low and lo <= rb) or (not low and hi >= re):
             raise ValueError(f"the IB window touches the '{loc}' wall layer, which carries a boundary operation")
 
@@ -413,6 +463,7 @@ class Stepper:
                 n += 1                                    # second launch of the fused kernel (window x-range)
             n += 1 if (self.ib_fused or self._mdf_one_launch) else self.n_iter
             n += 1 if (self._use_uwin and not self.ib_fused) else 0
+            n += (self.n_iter + 1) if self._shard is not None else 0      # flag barriers of the shared chain
         return n
 
     def attach_halo(self, halo):
@@ -426,6 +477,7 @@ class Stepper:
         if self._side is None:
             self._side = self._side_streams()
         self._halo_stream = torch.cuda.Stream(device=self.device)
+        self._chain_done = torch.cuda.Event()
         self.n_launch_per_step += 3 if self.halo_pipelined else 1
 
     # ------------------------------------------------------------------ state access
@@ -585,6 +637,7 @@ class Stepper:
         halo = self.halo if do_collide else None
         dst_index = 1 - self._cur
         pipelined = halo is not None and self.halo_pipelined
+        halo_waited = False
         rb, re = self.rows
         if pipelined:
             s_halo = self._halo_stream
@@ -596,19 +649,29 @@ class Stepper:
             self._host_ode_step(main)                          # the whole pass in one C call
         elif not (self.overlap and with_ib):
             if with_ib:
+                if pipelined and self._shard is not None:      # the shared chain reads the ghost rows: neighbours first
+                    halo.wait(st_halo)
+                    main.wait_stream(s_halo)
+                    halo_waited = True
                 self._ib_part(st_main)
             L.check(lib.vsb_step(ref, st_main))
         else:
             s_ib, s_edge = self._side
             st_ib = C.c_void_p(s_ib.cuda_stream)
             s_ib.wait_stream(main)
+            if pipelined and self._shard is not None:
+                # the shared chain reads this slab's ghost rows (window velocity of the edge rows): neighbours first
+                halo.wait(st_halo)
+                s_ib.wait_stream(s_halo)
             host_body = self.body is not None and self.dyn_mode == "host"
             if host_body:
                 # the host ODE synchronises the IB stream: get the bulk going first so it runs meanwhile
                 a.band = 1
                 L.check(lib.vsb_step(ref, st_main))
             self._ib_part(st_ib)                               # IB chain (its few CTAs should not queue behind
-            a.band = 2                                         # the bulk), then the window's x-range
+            if pipelined and self._shard is not None:          # the bulk), then the window's x-range
+                self._chain_done.record(s_ib)
+            a.band = 2
             L.check(lib.vsb_step(ref, st_ib))
             if not host_body:
                 a.band = 1                                     # everything but the window's x-range
@@ -617,7 +680,12 @@ class Stepper:
             a.band = 0
         if pipelined:
             # second stream: neighbours' ghost layers -> the two edge rows (and the x walls) -> send them on
-            halo.wait(st_halo)
+            if self._shard is not None and with_ib and self.overlap:
+                s_halo.wait_event(self._chain_done)            # a window on a cut: the edge rows read its force field
+            elif halo_waited:
+                s_halo.wait_stream(main)                       # chain and interior rows ran on `main`
+            else:
+                halo.wait(st_halo)
             a.band = 0
             a.sub_begin, a.sub_end, a.edge_rows_only = 0, 0, 1
             L.check(lib.vsb_step(ref, st_halo))
@@ -705,6 +773,9 @@ class Stepper:
         if self.n_iter > 1:
             m.scratch, m.scratch_next = buf[par, 1].data_ptr(), buf[par ^ 1, 1].data_ptr()
         bp = C.byref(self._bparams) if self._bparams is not None else None
+        if self._shard is not None:        # chain shared with the other ranks (window fields in peer memory)
+            L.check(lib.vsb_ibshard_chain(C.byref(a), C.byref(m), C.byref(self._shard.args), bp, st))
+            return
         if self.ib_fused:
             L.check(lib.vsb_ib_fused(C.byref(a), C.byref(m), bp, st))
         else:
