@@ -397,10 +397,14 @@ int vsb_halo_wait(const VsbHaloArgs* args, vsb_stream_t stream);
  *      rank whose markers can touch that cell (need box);
  *   2. every iteration, a rank interpolates at its markers from its own copy and adds what it spreads into the copy of
  *      every rank whose need box contains the cell (red.global.add over NVLink);
- *   3. the last iteration adds the force field into the copy of the rank whose SLAB contains the cell (the fluid
- *      kernel of that rank reads it), and every rank stores its partial force (and torque) sum into a slot of every
- *      rank; all ranks then add the slots in rank order -- the "small all-reduce of total IB force and torque" of the
- *      reference's design -- and advance identical replicas of the rigid-body state;
+ *   3. the last iteration accumulates the force field of a rank's markers in its own copy; the rank then stores the
+ *      cells of its need box into a staging slot [source rank] of the rank whose SLAB contains the cell (plain
+ *      coalesced stores, every cell every step, so nothing has to be cleared), and that rank adds the slots into the
+ *      force field its fluid kernel reads.  Every rank also stores its partial force (and torque) sum into a slot of
+ *      every rank; all ranks then add the slots in rank order -- the "small all-reduce of total IB force and torque"
+ *      of the reference's design -- and advance identical replicas of the rigid-body state;
+ *   Only the window cells some marker's stencil can reach (`cells`, a static list in window-local coordinates: the
+ *   body is rigid and the window follows it) are ever computed, sent or added;
  *   4. the steps are separated by an all-to-all flag barrier (one word per rank pair, system-scope release/acquire).
  * Everything is stream-ordered device code: graph-capturable, no NCCL call, no host synchronisation.
  * Coordinates of markers, window origin and body state are GLOBAL here; args->grid is the local slab and
@@ -418,11 +422,21 @@ typedef struct {
   int64_t marker_begin, marker_end;  /* this rank's share of the marker arrays                                    */
   int chunk_begin, chunk_end;        /* ... and of mdf->chunk_offsets (tiled kernel); 0, 0: untiled                 */
   uint32_t* counter;                 /* 4 local device words: barrier number, spare, time-out indicator, spare      */
+  float* staging[VSB_MAX_RANKS];     /* per rank: n_ranks window-sized fields [source rank][window cells][2 | 4]     */
+  float* force_field;                /* LOCAL window-sized field the fluid kernels of this rank read (args->g_win)  */
+  const int32_t* cells;              /* flat window-local indices of the cells a marker stencil can reach, ascending */
+  int64_t n_cells;
+  void* ev_window_done;              /* optional cudaEvent_t recorded on the chain's stream right after the window-velocity
+                                        kernel: the caller can hold the bulk of the fluid pass back until then, so that the
+                                        first, latency-critical kernel of the chain does not share the memory system   */
+  uint64_t* trace;                   /* optional (NULL: off): 8192 device words; barrier number b stores %globaltimer at
+                                        entry and exit into words 2 (b mod 4096) and 2 (b mod 4096) + 1 (timing aid)   */
 } VsbIbShard;
 
 /* One whole sharded chain of a step: window velocity -> barrier -> n_iter x (iteration -> barrier) -> force / torque
- * sums and body update (params->n_dof > 0: device ODE on every rank's replica).  mdf->g_win / scratch / u_win are
- * ignored: the fields live in shard->fields.  mdf->marker_u / marker_force are filled for this rank's share only. */
+ * sums and body update (params->n_dof > 0: device ODE on every rank's replica) -> shard->force_field.
+ * mdf->g_win / scratch / u_win are ignored: the fields live in shard->fields.  mdf->marker_u / marker_force are
+ * filled for this rank's share only. */
 int vsb_ibshard_chain(const VsbStepArgs* args, const VsbMdfArgs* mdf, const VsbIbShard* shard,
                       const VsbBodyParams* params, vsb_stream_t stream);
 /* The flag barrier alone (used between set-up phases and by tests). */

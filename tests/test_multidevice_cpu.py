@@ -150,7 +150,19 @@ def test_ib_shard_plan_invariants(world, case):
             assert np.prod(ext) <= TILE_CELLS
     else:
         assert pl["chunk_offsets"] is None
+    # the list of reachable cells holds every stencil cell of every marker, for any sub-cell drift of the window
+    reach = np.zeros(int(np.prod(size)), dtype=bool)
+    reach[pl["cells"]] = True
+    assert (np.diff(pl["cells"]) > 0).all()
+    strides = np.cumprod((list(size[1:]) + [1])[::-1])[::-1]
+    for drift in (-0.999, 0.0, 0.999):
+        base = np.floor(stored.astype(np.float64) - np.floor(origin) + drift).astype(int)
+        for off in np.ndindex(*([4] * len(size))):
+            node = base + np.asarray(off) - 1
+            ok = ((node >= 0) & (node < np.asarray(size))).all(axis=1)
+            assert reach[(node[ok] * strides).sum(axis=1)].all()
     whole = plan_ib_shards(markers, ib["window"], world, dense, moving_in_window=True)
+    assert whole["cells"].size == int(np.prod(size))
     for r in range(world):
         if whole["marker_ranges"][r, 1] > whole["marker_ranges"][r, 0]:
             assert (whole["need_lo"][r] == 0).all() and (whole["need_hi"][r] == np.asarray(size)).all()

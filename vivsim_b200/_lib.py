@@ -105,7 +105,8 @@ class VsbIbShard(C.Structure):
                 ("need_lo", (C.c_int * 3) * MAX_RANKS), ("need_hi", (C.c_int * 3) * MAX_RANKS),
                 ("x_lo", C.c_int * MAX_RANKS), ("x_hi", C.c_int * MAX_RANKS),
                 ("marker_begin", C.c_int64), ("marker_end", C.c_int64), ("chunk_begin", C.c_int), ("chunk_end", C.c_int),
-                ("counter", C.c_void_p)]
+                ("counter", C.c_void_p), ("staging", C.c_void_p * MAX_RANKS), ("force_field", C.c_void_p),
+                ("cells", C.c_void_p), ("n_cells", C.c_int64), ("ev_window_done", C.c_void_p), ("trace", C.c_void_p)]
 
 
 class VsbHostPlan(C.Structure):

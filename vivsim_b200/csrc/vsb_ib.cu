@@ -187,17 +187,9 @@ __global__ void __launch_bounds__(kBlock, DIM == 3 ? 5 : 8) k_mdf_stage(const St
   for (int stage = p.stage; stage < p.stage_end; ++stage) {
     const bool last = stage == p.n_iter - 1;
     // clear the other parity's buffers for the next step
-    if (stage == 0 && batch == 0) {
-      long long cb, ce;
-      clear_range(p, org[0], 0, cb, ce);
-      for (long long i = NC * cb + gthread; i < NC * ce; i += nthreads) p.g_win_next[i] = 0.f;
-    }
-    if (stage < p.n_iter - 1 && batch == 0) {
-      float* z = p.scratch_next + (long long)stage * NC * wcells;
-      long long cb, ce;
-      clear_range(p, org[0], 1, cb, ce);
-      for (long long i = NC * cb + gthread; i < NC * ce; i += nthreads) z[i] = 0.f;
-    }
+    if (stage == 0 && batch == 0) clear_field<NC>(p, p.g_win_next, org[0], 0, gthread, nthreads);
+    if (stage < p.n_iter - 1 && batch == 0)
+      clear_field<NC>(p, p.scratch_next + (long long)stage * NC * wcells, org[0], 1, gthread, nthreads);
 
     float um[DIM];
 #pragma unroll
@@ -341,17 +333,8 @@ __global__ void __launch_bounds__(kTiledChunk, 3) k_mdf_stage_tiled(const MdfPar
     for (int d = 0; d < 3; ++d) { org[d] = p.body->origin2[p.parity][d]; disp[d] = p.body->d[d]; }
   }
   // clear the other parity's buffers for the next step (as k_mdf_stage does)
-  if (stage == 0) {
-    long long cb, ce;
-    clear_range(p, org[0], 0, cb, ce);
-    for (long long i = NC * cb + gthread; i < NC * ce; i += nthreads) p.g_win_next[i] = 0.f;
-  }
-  if (stage < p.n_iter - 1) {
-    float* z = p.scratch_next + (long long)stage * NC * wcells;
-    long long cb, ce;
-    clear_range(p, org[0], 1, cb, ce);
-    for (long long i = NC * cb + gthread; i < NC * ce; i += nthreads) z[i] = 0.f;
-  }
+  if (stage == 0) clear_field<NC>(p, p.g_win_next, org[0], 0, gthread, nthreads);
+  if (stage < p.n_iter - 1) clear_field<NC>(p, p.scratch_next + (long long)stage * NC * wcells, org[0], 1, gthread, nthreads);
 
   const int chunk = p.chunk_begin + (int)blockIdx.x;
   const long long m_begin = p.chunk_offsets ? (long long)p.chunk_offsets[chunk] : p.m_begin + (long long)blockIdx.x * kTiledChunk;

@@ -34,22 +34,31 @@ struct MdfParams {
   long long m_begin, m_end; // markers handled by this launch (a rank's share when the chain is sharded over GPUs)
   int chunk_begin;          // tiled kernel: first chunk of this launch
   // Which part of the next step's buffers this launch clears: everything (clear_mode 0), or only the window x-planes
-  // this rank's copy can receive contributions in (sharded chain): the slab's x-range +- 2 for the force field, the
-  // need box's x-range for the work fields.
+  // this rank's copy can receive contributions in (sharded chain): the need box's x-range.
   const unsigned short* nbr_list;   // cluster kernel: per marker, the markers whose stencils can overlap its own
   int nbr_stride;
   int clear_mode;
   int slab_x[2];            // global x-range of this rank's slab
   int need_x[2];            // window-local x-range of this rank's need box
+  const int* clear_cells;   // clear_mode 2: only these window cells (ascending flat indices) inside the box below
+  long long n_clear_cells;
+  int box_lo[3], box_hi[3];
 };
+
+// Zero the cells of `field` (NC floats per cell) this launch is responsible for: the flat range of clear_range(), or,
+// for a sharded chain, the listed reachable cells inside this rank's need box -- nothing else is ever written there.
+template <int NC>
+__device__ __forceinline__ void clear_field(const MdfParams& p, float* field, int org_x, int which, long long gthread,
+                                            long long nthreads);
 
 // Flat range [begin, end) of window cells to clear in a field: force field (which = 0) or work field (which = 1).
 __device__ __forceinline__ void clear_range(const MdfParams& p, int org_x, int which, long long& begin, long long& end) {
   const long long plane = (long long)p.wsize[1] * (p.wsize[2] > 0 ? p.wsize[2] : 1);   // 2-D: wsize[2] unused
   int lo = 0, hi = p.wsize[0];
   if (p.clear_mode) {
-    lo = which ? p.need_x[0] : p.slab_x[0] - org_x - 2;
-    hi = which ? p.need_x[1] : p.slab_x[1] - org_x + 2;
+    // sharded chain: all fields of a rank's copy are accumulated inside its need box only
+    lo = p.need_x[0];
+    hi = p.need_x[1];
     lo = lo < 0 ? 0 : lo;
     hi = hi > p.wsize[0] ? p.wsize[0] : hi;
     if (hi < lo) hi = lo;
@@ -78,6 +87,26 @@ __device__ __forceinline__ void shard_add(const ShardDev& sh, int org_x, int nx,
                                   nz >= sh.lo[r][2] && nz < sh.hi[r][2]);
     if (in) atomicAdd(reinterpret_cast<VecF*>(sh.dst[r]) + idx, v);
   }
+}
+
+template <int NC>
+__device__ __forceinline__ void clear_field(const MdfParams& p, float* field, int org_x, int which, long long gthread,
+                                            long long nthreads) {
+  if (p.clear_mode == 2) {
+    const int w1 = p.wsize[1], w2 = p.wsize[2] > 0 ? p.wsize[2] : 1;
+    for (long long i = gthread; i < p.n_clear_cells; i += nthreads) {
+      const int cell = __ldg(p.clear_cells + i);
+      const int z = cell % w2, y = (cell / w2) % w1, x = cell / (w2 * w1);
+      if (x >= p.box_lo[0] && x < p.box_hi[0] && y >= p.box_lo[1] && y < p.box_hi[1] && z >= p.box_lo[2] && z < p.box_hi[2]) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) field[(long long)cell * NC + c] = 0.f;
+      }
+    }
+    return;
+  }
+  long long cb, ce;
+  clear_range(p, org_x, which, cb, ce);
+  for (long long i = NC * cb + gthread; i < NC * ce; i += nthreads) field[i] = 0.f;
 }
 
 // Position, target velocity and lever arm of marker m for the body state in p.body (dyn.py:69-120):

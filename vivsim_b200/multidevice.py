@@ -18,6 +18,8 @@ The exchange is written on torch tensors, so the same code runs on CPU tensors o
 CUDA tensors over NCCL (production).  There is no data-path collective besides the neighbour exchange.
 """
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -178,7 +180,32 @@ class LocalHalo:
         return False
 
 
-def plan_ib_shards(markers, window, world, dense, moving_in_window=False, margin=2):
+# Cost model behind the marker shares (measured on B200 with BASELINE config 5, profiles/r02_summary.md): one marker costs a
+# rank about 0.4 ns per MDF iteration; a rank whose slab holds reachable window cells also computes their velocity and
+# collides them after the chain, about 0.2 ns per cell.
+COST_PER_MARKER_ITER = 0.4e-9
+COST_PER_WINDOW_CELL = 0.2e-9
+
+
+def balance_marker_shares(n_markers, n_iter, cells_per_rank):
+    """Fractions of the markers per rank that equalise (window work of the rank) + (marker work of the rank): ranks
+    whose slabs hold the body's window get fewer markers, down to none (water filling).  Host logic."""
+    extra = np.asarray(cells_per_rank, dtype=np.float64) * COST_PER_WINDOW_CELL
+    total = float(n_markers) * n_iter * COST_PER_MARKER_ITER
+    world = extra.size
+    if total <= 0:
+        return np.full(world, 1.0 / world)
+    order = np.argsort(extra)
+    level = 0.0
+    for k in range(world, 0, -1):            # the k ranks with the least window work share the markers
+        level = (total + extra[order[:k]].sum()) / k
+        if level >= extra[order[k - 1]]:
+            break
+    share = np.maximum(level - extra, 0.0)
+    return share / share.sum()
+
+
+def plan_ib_shards(markers, window, world, dense, moving_in_window=False, margin=2, shares=None):
     """Divide the markers of one immersed body among `world` ranks (host logic, NumPy only).
 
     The ranks share the multi-direct-forcing chain (csrc/vsb_ibshard.cu): rank r handles a contiguous range of the
@@ -190,9 +217,9 @@ def plan_ib_shards(markers, window, world, dense, moving_in_window=False, margin
     dense: the tiled kernel is used -- within each group the markers are ordered and cut into chunks by
     stepper.cut_marker_chunks.  moving_in_window: the body moves relative to the window (follow = 0, or it rotates),
     so every rank needs the whole window; otherwise the window follows the body and `margin` cells cover the
-    sub-cell drift.
+    sub-cell drift.  shares: fraction of the markers per rank (default: equal).
     Returns dict(perm, marker_ranges (world, 2), chunk_offsets | None, chunk_ranges (world, 2), need_lo, need_hi
-    (world, dim) window-local [lo, hi), axis)."""
+    (world, dim) window-local [lo, hi), axis, cells: ascending flat window indices of the cells a stencil can reach)."""
     from .stepper import cut_marker_chunks
     markers = np.asarray(markers, dtype=np.float32)
     n, dim = markers.shape
@@ -201,7 +228,12 @@ def plan_ib_shards(markers, window, world, dense, moving_in_window=False, margin
     size = np.asarray(size, dtype=np.int64)
     axis = int(np.argmax(markers.max(axis=0) - markers.min(axis=0))) if n else 0
     order = np.argsort(markers[:, axis], kind="stable")
-    bounds = [(n * r) // world for r in range(world + 1)]
+    if shares is None:
+        bounds = [(n * r) // world for r in range(world + 1)]
+    else:                                     # uneven shares (balance_marker_shares)
+        cum = np.concatenate([[0.0], np.cumsum(np.asarray(shares, dtype=np.float64))])
+        bounds = [int(round(n * c / cum[-1])) for c in cum]
+        bounds[0], bounds[-1] = 0, n
     perm_parts, marker_ranges, chunk_ranges, offsets = [], [], [], [0]
     pos = 0
     for r in range(world):
@@ -229,7 +261,28 @@ def plan_ib_shards(markers, window, world, dense, moving_in_window=False, margin
         base = np.floor(markers[perm[b:e]].astype(np.float64) - origin).astype(np.int64)
         need_lo[r] = np.clip(base.min(axis=0) - 1 - margin, 0, size)
         need_hi[r] = np.clip(base.max(axis=0) + 3 + margin, 0, size)
-    return dict(perm=perm, marker_ranges=np.asarray(marker_ranges, dtype=np.int64),
+    # window cells some marker's stencil can reach: base - 1 .. base + 2, and the base itself drifts by at most one cell
+    # either way while the window follows the body
+    if moving_in_window or n == 0:
+        cells = np.arange(int(np.prod(size)), dtype=np.int32)
+    else:
+        vol = np.zeros(tuple(int(k) for k in size), dtype=bool)
+        base = np.floor(markers.astype(np.float64) - origin).astype(np.int64)
+        base = np.clip(base, 0, size - 1)
+        vol[tuple(base[:, d] for d in range(dim))] = True
+        for ax in range(dim):
+            acc = np.zeros_like(vol)
+            for sft in range(-2, 4):
+                src = [slice(None)] * dim
+                dst = [slice(None)] * dim
+                if sft >= 0:
+                    src[ax], dst[ax] = slice(0, vol.shape[ax] - sft), slice(sft, vol.shape[ax])
+                else:
+                    src[ax], dst[ax] = slice(-sft, vol.shape[ax]), slice(0, vol.shape[ax] + sft)
+                acc[tuple(dst)] |= vol[tuple(src)]
+            vol = acc
+        cells = np.flatnonzero(vol).astype(np.int32)
+    return dict(perm=perm, marker_ranges=np.asarray(marker_ranges, dtype=np.int64), cells=cells,
                 chunk_offsets=np.asarray(offsets, dtype=np.int32) if dense else None,
                 chunk_ranges=np.asarray(chunk_ranges, dtype=np.int64), need_lo=need_lo, need_hi=need_hi, axis=axis)
 
@@ -251,7 +304,12 @@ class IbShard:
         markers = np.asarray(ib["markers"], dtype=np.float32)
         wcells = int(np.prod(self.win_size))
         dense = dim == 3 and markers.shape[0] * 4 ** dim > 2 * wcells and markers.shape[0] > 480
-        self.plan = plan_ib_shards(markers, ib["window"], slab.world, dense, moving_in_window)
+        # first pass: which window cells are reachable, and how many of them lie in each slab -> marker shares
+        probe = plan_ib_shards(markers, ib["window"], 1, False, moving_in_window)
+        cx = probe["cells"].astype(np.int64) // int(np.prod(self.win_size[1:])) + int(np.floor(origin[0]))
+        per_rank = np.bincount(np.clip(cx // slab.nx_local, 0, slab.world - 1), minlength=slab.world)
+        self.shares = balance_marker_shares(markers.shape[0], n_iter, per_rank)
+        self.plan = plan_ib_shards(markers, ib["window"], slab.world, dense, moving_in_window, shares=self.shares)
         nc = 2 if dim == 2 else 4
         self.fields = symm.empty((2, n_iter + 1) + self.win_size + (nc,), dtype=torch.float32, device=dev)
         self.fields.zero_()
@@ -259,14 +317,19 @@ class IbShard:
         self.flags.zero_()
         self.sums = symm.empty((L.MAX_RANKS * 4,), dtype=torch.float32, device=dev)
         self.sums.zero_()
-        handles = [symm.rendezvous(t, group) for t in (self.fields, self.flags, self.sums)]
+        # staging slots [source rank] for the force field, and the local field the fluid kernels read
+        self.staging = symm.empty((slab.world,) + self.win_size + (nc,), dtype=torch.float32, device=dev)
+        self.staging.zero_()
+        self.force_field = torch.zeros(self.win_size + (nc,), dtype=torch.float32, device=dev)
+        self.cells = torch.as_tensor(self.plan["cells"], device=dev)
+        handles = [symm.rendezvous(t, group) for t in (self.fields, self.flags, self.sums, self.staging)]
         torch.cuda.synchronize()
         dist.barrier(group)
         self.counter = torch.zeros(4, dtype=torch.int32, device=dev)
         sh = L.VsbIbShard()
         sh.n_ranks, sh.rank = slab.world, slab.rank
         for r in range(slab.world):
-            sh.fields[r], sh.flags[r], sh.sums[r] = (h.buffer_ptrs[r] for h in handles)
+            sh.fields[r], sh.flags[r], sh.sums[r], sh.staging[r] = (h.buffer_ptrs[r] for h in handles)
             for d in range(dim):
                 sh.need_lo[r][d] = int(self.plan["need_lo"][r][d])
                 sh.need_hi[r][d] = int(self.plan["need_hi"][r][d])
@@ -275,6 +338,15 @@ class IbShard:
         sh.marker_begin, sh.marker_end = (int(x) for x in self.plan["marker_ranges"][slab.rank])
         sh.chunk_begin, sh.chunk_end = (int(x) for x in self.plan["chunk_ranges"][slab.rank])
         sh.counter = self.counter.data_ptr()
+        sh.force_field = self.force_field.data_ptr()
+        sh.cells, sh.n_cells = self.cells.data_ptr(), int(self.cells.numel())
+        self.ev_window_done = torch.cuda.Event()
+        self.ev_window_done.record()              # materialise the cudaEvent_t handle
+        sh.ev_window_done = self.ev_window_done.cuda_event
+        self.trace = None
+        if os.environ.get("VSB_SHARD_TRACE"):       # timing aid: %globaltimer at entry / exit of every flag barrier
+            self.trace = torch.zeros(8192, dtype=torch.int64, device=dev)
+            sh.trace = self.trace.data_ptr()
         self.args = sh
         self.slab = slab
         self._handles = handles

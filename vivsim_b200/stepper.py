@@ -283,7 +283,7 @@ class Stepper:
         else:
             self._ib_buf = torch.zeros((2, self.n_iter) + self.win_size + (nc,), device=dev)
             self._u_win = torch.zeros(self.win_size + (nc,), device=dev) if self._use_uwin else None
-        self._g_win = self._ib_buf[0, 0]
+        self._g_win = self._ib_buf[0, 0] if self._shard is None else self._shard.force_field
         self._marker_u = torch.zeros((self.n_markers, dim), device=dev)
         self._marker_force = torch.zeros((self.n_markers, dim), device=dev)   # +F; reaction on the body is -F
         tgt = ib.get("u_target")
@@ -463,7 +463,7 @@ class Stepper:
                 n += 1                                    # second launch of the fused kernel (window x-range)
             n += 1 if (self.ib_fused or self._mdf_one_launch) else self.n_iter
             n += 1 if (self._use_uwin and not self.ib_fused) else 0
-            n += (self.n_iter + 1) if self._shard is not None else 0      # flag barriers of the shared chain
+            n += (self.n_iter + 3) if self._shard is not None else 0      # flag barriers, force push and reduce of the shared chain
         return n
 
     def attach_halo(self, halo):
@@ -624,7 +624,7 @@ class Stepper:
         a.do_stream, a.do_collide = do_stream, do_collide
         a.parity = self._parity
         if self.ib is not None and do_collide:     # force field of this step (double-buffered by parity)
-            self._g_win = self._ib_buf[self._parity, 0]
+            self._g_win = self._ib_buf[self._parity, 0] if self._shard is None else self._shard.force_field
             a.g_win = self._g_win.data_ptr()
         lib = L.lib()
         has_ops = a.n_post > 0 and do_stream
@@ -675,6 +675,10 @@ class Stepper:
             L.check(lib.vsb_step(ref, st_ib))
             if not host_body:
                 a.band = 1                                     # everything but the window's x-range
+                if self._shard is not None:
+                    # shared chain: its first kernel (window velocity; a no-op on ranks whose slab holds no window cell)
+                    # gets the memory system to itself -- every other rank waits for it at the first flag barrier
+                    main.wait_event(self._shard.ev_window_done)
                 L.check(lib.vsb_step(ref, st_main))
             main.wait_stream(s_ib)
             a.band = 0
