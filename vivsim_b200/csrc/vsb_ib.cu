@@ -280,7 +280,6 @@ __global__ void __launch_bounds__(kBlock, DIM == 3 ? 5 : 8) k_mdf_stage(const St
       }
     }
   }
-  if constexpr (SHARD) __threadfence_system();   // this thread's reductions into peer memory are performed before the kernel ends
 }
 
 
@@ -532,7 +531,6 @@ __global__ void __launch_bounds__(kTiledChunk, 3) k_mdf_stage_tiled(const MdfPar
       }
     }
   }
-  if constexpr (SHARD) __threadfence_system();
 }
 
 // body update by one thread (see body_update in vsb_step.cuh)

@@ -131,7 +131,8 @@ __global__ void __launch_bounds__(128) k_shard_window_moments(const StepParams<D
   if constexpr (DIM == 3) { v.z = u[2]; v.w = 0.f; }
   for (int k = 0; k < w.n_ranks; ++k)
     if (in_box(rel, w.lo[k], w.hi[k], DIM)) reinterpret_cast<VecF*>(w.dst[k])[cell] = v;
-  __threadfence_system();
+  // no fence here: the flag barrier that follows on the stream fences at system scope before it publishes, and fences
+  // are cumulative over everything ordered before them (the end of this kernel)
 }
 
 // The force field accumulated by my markers (my copy) -> staging slot [me] of the rank whose slab contains the cell.
@@ -162,7 +163,6 @@ __global__ void __launch_bounds__(256) k_shard_push_force(const ForcePush f, con
   for (int r = 0; r < f.n_ranks; ++r)
     if (gx >= f.x_lo[r] && gx < f.x_hi[r])
       reinterpret_cast<VecF*>(f.staging[r] + (long long)f.rank * f.field)[cell] = v;
-  __threadfence_system();
 }
 
 // Staging slots -> the force field my fluid kernels read: the cells of my slab, summed over the ranks whose need box
