@@ -15,7 +15,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 tail -3 $OUT/launches_bench_$TAG.csv | cut -c1-300
 for cfg in c3 c5; do
   echo "== ncu --set full $cfg"
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_step -s 4 -c 2 -o $OUT/ncu_full_${cfg}_$TAG -f \
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_step -s 4 -c 4 -o $OUT/ncu_full_${cfg}_$TAG -f \
     python scripts/profile_kernels.py $cfg 3 > $OUT/ncu_full_${cfg}_$TAG.log 2>&1
   tail -2 $OUT/ncu_full_${cfg}_$TAG.log
 done

@@ -15,12 +15,14 @@ elif name == "c3":
     spec, body = configs.sphere_3d()
 elif name == "c4":
     spec, body = configs.viv_cylinder_2d_large(n=8192)
-elif name == "c5":   # one slab of the 1024 x 512 x 512 MRT case (1/8 of the domain), periodic, Guo body force
+elif name == "c5":   # the C5 recipe (MRT + Guo-MRT, NEBB / equilibrium faces, moving finite cylinder, tiled MDF) at 256^3
+    spec, body = configs.oscillating_cylinder_3d(nx=256, ny=256, nz=256)
+elif name == "c5slab":   # one slab of the 1024 x 512 x 512 MRT case (1/8 of the domain), periodic, uniform Guo body force
     spec, body = dict(dim=3, shape=(128, 512, 512), collision="mrt", omega=1.7, forcing="guo", g=(1e-6, 0.0, 0.0),
                       post=[], u0=0.05), None
 else:
     raise SystemExit("unknown workload")
-st = Stepper(spec, body=body, dyn_mode="device") if body else Stepper(spec)
+st = Stepper(spec, body=body, dyn_mode="device", follow=2 if name == "c5" else 1) if body else Stepper(spec)
 st.set_f(configs.uniform_state(spec, noise=1e-3))
 st.step(steps)
 torch.cuda.synchronize()
