@@ -20,7 +20,7 @@ for line in txt.splitlines():
 for fn, ins in funcs.items():
     if "k_step" not in fn: continue
     dem = subprocess.run(["c++filt", fn], capture_output=True, text=True).stdout.strip()
-    m = re.search(r"k_step<\(int\)(\d), \(int\)(\d), \(int\)(\d)>", dem)
+    m = re.search(r"k_step<\(int\)(\d), \(int\)(\d+), \(int\)(\d)>", dem)
     tag = "k_step<%s,%s,%s>" % m.groups() if m else dem[:40]
     if flt and flt not in tag: continue
     start = 0

@@ -65,3 +65,48 @@ def test_baseline_workload_generators():
         # every 4-point stencil lies inside the window (the reference leaves out-of-range indices undefined)
         assert np.floor(mk[:, 0]).min() - 1 >= ox and np.floor(mk[:, 0]).max() + 2 < ox + sx
         assert np.floor(mk[:, 1]).min() - 1 >= oy and np.floor(mk[:, 1]).max() + 2 < oy + sy
+
+
+def _moment_harness():
+    """vivsim_b200/csrc/vsb_mrt_moment.cuh is host + device code: g++ compiles it into a small shared library."""
+    import ctypes as C
+    import os
+    import subprocess
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "harness")
+    out = os.path.join(here, "build", "libmrt_moment_harness.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    src = os.path.join(here, "mrt_moment_harness.cpp")
+    hdr = os.path.join(here, "..", "..", "vivsim_b200", "csrc", "vsb_mrt_moment.cuh")
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-I/usr/local/cuda/include", "-o", out, src], check=True)
+    return C.CDLL(out)
+
+
+def test_d3q19_mrt_in_moment_space_equals_the_reference_operator(golden):
+    """The moment-space evaluation the fused D3Q19 MRT kernel uses (no matrix) against the dense product with the
+    reference's own operators (lbm3d/collision/mrt.py:74-98): the rates are recovered from the matrix, A x agrees to
+    fp32 rounding, the Guo operator must be I - A/2, and anything else is refused (-> matrix kernels)."""
+    import ctypes as C
+    lib = _moment_harness()
+    fp = C.POINTER(C.c_float)
+    P = lambda a: a.ctypes.data_as(fp)
+    g = golden["lattice"]
+    rng = np.random.default_rng(0)
+    for om in ("0.8", "1.7"):
+        A = np.ascontiguousarray(g[f"d3q19_mrt_op_{om}"], dtype=np.float32)
+        B = np.ascontiguousarray(g[f"d3q19_mrt_fop_{om}"], dtype=np.float32)
+        s = np.zeros(19, np.float32)
+        assert lib.mm_make(P(A), P(B), P(s)) == 1
+        want = [0, 0, 0, 0, 1.1] + [float(om)] * 5 + [1.2] * 6 + [1.4] * 3      # lbm3d/collision/mrt.py:50-72
+        np.testing.assert_allclose(s, want, rtol=0, atol=2e-6)
+        for _ in range(100):
+            x = rng.standard_normal(19).astype(np.float32)
+            y = np.zeros(19, np.float32)
+            lib.mm_apply(P(s), P(x), P(y))
+            ref = A.astype(np.float64) @ x.astype(np.float64)
+            assert np.abs(y - ref).max() <= 2e-6 * np.abs(ref).max()
+        bad = A.copy(); bad[3, 5] += 0.01
+        assert lib.mm_make(P(bad), None, P(s)) == 0                    # not diagonal in the moment basis
+        assert lib.mm_make(P(A), P(A), P(s)) == 0                      # source operator is not I - A/2
+        cons = (A + 0.1 * np.eye(19, dtype=np.float32)).astype(np.float32)
+        assert lib.mm_make(P(cons), None, P(s)) == 0                   # conserved moments relaxed

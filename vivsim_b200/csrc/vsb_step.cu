@@ -41,31 +41,32 @@ __device__ __forceinline__ void store_vec(float* __restrict__ p, const float (&v
 }
 
 template <int DIM, int COLL>
-__device__ __forceinline__ void edge_block(const StepParams<DIM>& p, const MrtMats<DIM, is_mrt(COLL)>& mm);
+__device__ __forceinline__ void edge_block(const StepParams<DIM>& p, const MrtMats<DIM, mats_kind(COLL)>& mm);
 
 // Block size and register budget per lattice and collision model, measured on B200 (scripts/tune_variants.py,
 // profiles/r01_summary.md section 4):
-//   D3Q19: 128 registers either way; BGK / KBC / regularised run best as 4 CTAs of 128 threads with 2 cells per thread,
-//          MRT as 2 CTAs of 256 threads with 4 cells per thread.
+//   D3Q19: 128 registers either way; BGK / KBC / regularised and MRT in moment space run best as 4 CTAs of 128 threads
+//          with 2 cells per thread, MRT in matrix form as 2 CTAs of 256 threads with 4 cells per thread.
 //   D2Q9:  256 threads, 4 cells per thread; 64 registers (4 CTAs) for BGK / regularised, 80 (3 CTAs) for KBC / MRT.
 // VSB_STEP3D_THREADS / VSB_STEP3D_CTAS override the D3Q19 choice for the tuning builds.
+__host__ __device__ constexpr bool is_matrix_mrt(int coll) { return coll == VSB_COLL_MRT || coll == VSB_COLL_MRT_SPLIT; }
 template <int DIM, int COLL> constexpr int step_max_threads() {
 #ifdef VSB_STEP3D_THREADS
   return DIM == 3 ? VSB_STEP3D_THREADS : 256;
 #else
-  return (DIM == 3 && !is_mrt(COLL)) ? 128 : 256;
+  return (DIM == 3 && !is_matrix_mrt(COLL)) ? 128 : 256;
 #endif
 }
 template <int DIM, int COLL> constexpr int step_min_ctas() {
 #ifdef VSB_STEP3D_CTAS
   if (DIM == 3) return VSB_STEP3D_CTAS;
 #endif
-  return DIM == 3 ? (is_mrt(COLL) ? 2 : 4) : ((COLL == VSB_COLL_KBC || is_mrt(COLL)) ? 3 : 4);
+  return DIM == 3 ? (is_matrix_mrt(COLL) ? 2 : 4) : ((COLL == VSB_COLL_KBC || is_mrt(COLL)) ? 3 : 4);
 }
-template <int DIM, int COLL> constexpr int step_default_vec() { return (DIM == 3 && !is_mrt(COLL)) ? 2 : 4; }
+template <int DIM, int COLL> constexpr int step_default_vec() { return (DIM == 3 && !is_matrix_mrt(COLL)) ? 2 : 4; }
 
 template <int DIM, int COLL, int VEC>
-__global__ void __launch_bounds__(step_max_threads<DIM, COLL>(), step_min_ctas<DIM, COLL>()) k_step(const StepParams<DIM> p, const MrtMats<DIM, is_mrt(COLL)> mm) {
+__global__ void __launch_bounds__(step_max_threads<DIM, COLL>(), step_min_ctas<DIM, COLL>()) k_step(const StepParams<DIM> p, const MrtMats<DIM, mats_kind(COLL)> mm) {
   using L = Lat<DIM>;
   constexpr int Q = L::Q;
   if (blockIdx.x >= p.nb_bulk) {   // blocks appended after the bulk: wall layers of the face operations (edges = 2)
@@ -281,7 +282,7 @@ __global__ void k_lines_mask(const StepParams<DIM> p, const LineSet ls, const ui
 }
 
 template <int DIM, int COLL>
-__global__ void k_lines_collide(const StepParams<DIM> p, const MrtMats<DIM, is_mrt(COLL)> mm, const LineSet ls) {
+__global__ void k_lines_collide(const StepParams<DIM> p, const MrtMats<DIM, mats_kind(COLL)> mm, const LineSet ls) {
   using L = Lat<DIM>;
   int c[3];
   if (!line_cell<DIM>(p, ls, blockIdx.y, (long long)blockIdx.x * blockDim.x + threadIdx.x, c)) return;
@@ -329,7 +330,7 @@ __global__ void k_window_moments(const StepParams<DIM> p, float* __restrict__ u_
 // One wall cell: pull, face operation, (mask), collide, store.  Face operations handled this way are independent of
 // each other (see vsb_edge_fused_supported), so no ordering between them is needed.
 template <int DIM, int COLL, int LOC>
-__device__ __forceinline__ void edge_cell(const StepParams<DIM>& p, const MrtMats<DIM, is_mrt(COLL)>& mm, int wall_layer,
+__device__ __forceinline__ void edge_cell(const StepParams<DIM>& p, const MrtMats<DIM, mats_kind(COLL)>& mm, int wall_layer,
                                           int kind, int wrap_kind, const WallVals& w, int mask_before, long long k) {
   using L = Lat<DIM>;
   using G = FaceGeom<DIM, LOC>;
@@ -388,13 +389,13 @@ __device__ __forceinline__ void edge_cell(const StepParams<DIM>& p, const MrtMat
 
 // Wall layer of one face as a kernel of its own (vsb_edge_fused).
 template <int DIM, int COLL, int LOC>
-__global__ void k_edge_fused(const StepParams<DIM> p, const MrtMats<DIM, is_mrt(COLL)> mm, int wall_layer, int kind,
+__global__ void k_edge_fused(const StepParams<DIM> p, const MrtMats<DIM, mats_kind(COLL)> mm, int wall_layer, int kind,
                              int wrap_kind, WallVals w, int mask_before) {
   edge_cell<DIM, COLL, LOC>(p, mm, wall_layer, kind, wrap_kind, w, mask_before, (long long)blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 template <int DIM, int COLL>
-__device__ __forceinline__ void edge_block(const StepParams<DIM>& p, const MrtMats<DIM, is_mrt(COLL)>& mm) {
+__device__ __forceinline__ void edge_block(const StepParams<DIM>& p, const MrtMats<DIM, mats_kind(COLL)>& mm) {
   unsigned b = blockIdx.x - p.nb_bulk;
   int e = 0;
   if (p.n_wall > 1 && b >= p.wall_blocks0) { e = 1; b -= p.wall_blocks0; }
@@ -458,8 +459,13 @@ template int fill_params<3>(const VsbStepArgs&, StepParams<3>&);
 #endif
 
 template <int DIM, int COLL>
-static void fill_mats(const VsbStepArgs& a, MrtMats<DIM, is_mrt(COLL)>& mm) {
-  if constexpr (is_mrt(COLL)) {
+static void fill_mats(const VsbStepArgs& a, MrtMats<DIM, mats_kind(COLL)>& mm) {
+  if constexpr (COLL == VSB_COLL_MRT_MOMENT) {
+    int c[19][3];
+    for (int q = 0; q < 19; ++q)
+      for (int d = 0; d < 3; ++d) c[q][d] = Lat<3>::c(q, d);
+    make_moment_op3(a.mrt_op_host, a.forcing == VSB_FORCE_GUO ? a.mrt_fop_host : nullptr, c, mm.mo);   // checked by mrt_is_moment
+  } else if constexpr (is_mrt(COLL)) {
     constexpr int Q = Lat<DIM>::Q;
     for (int i = 0; i < Q * Q; ++i) {
       mm.A.a[i] = a.mrt_op_host ? a.mrt_op_host[i] : 0.f;
@@ -476,12 +482,28 @@ static void fill_mats(const VsbStepArgs& a, MrtMats<DIM, is_mrt(COLL)>& mm) {
 template <int DIM>
 static bool mrt_is_split(const VsbStepArgs& a) {
   constexpr int Q = Lat<DIM>::Q;
-  if (!a.mrt_op_host) return false;
+  static const bool allowed = [] { const char* e = getenv("VSB_MRT_FORM"); return !e || e[0] != 'd'; }();
+  if (!allowed || !a.mrt_op_host) return false;
   SplitOp<DIM> tmp;
   if (!make_split_op<DIM>(a.mrt_op_host, tmp)) return false;
   if (a.mrt_fop_host) return make_split_op<DIM>(a.mrt_fop_host, tmp);
   float zero[Q * Q] = {};
   return make_split_op<DIM>(zero, tmp);
+}
+
+// True when the D3Q19 operators of this call are diagonal in the reference's moment basis (see vsb_mrt_moment.cuh);
+// VSB_MRT_FORM=split|dense in the environment keeps the matrix kernels (tuning / A-B comparisons).
+template <int DIM>
+static bool mrt_is_moment(const VsbStepArgs& a) {
+  if constexpr (DIM != 3) return false;
+  static const bool allowed = [] { const char* e = getenv("VSB_MRT_FORM"); return !e || e[0] == 'm'; }();
+  if (!allowed || !a.mrt_op_host) return false;
+  if (a.forcing == VSB_FORCE_GUO && !a.mrt_fop_host) return false;
+  int c[19][3];
+  for (int q = 0; q < 19; ++q)
+    for (int d = 0; d < 3; ++d) c[q][d] = Lat<3>::c(q, d);
+  MomentOp3 tmp;
+  return make_moment_op3(a.mrt_op_host, a.forcing == VSB_FORCE_GUO ? a.mrt_fop_host : nullptr, c, tmp);
 }
 
 static int check_mrt(const VsbStepArgs& a) {
@@ -532,7 +554,7 @@ static bool edges_independent(const VsbStepArgs& a, const StepParams<DIM>& p, in
 }
 
 template <int DIM, int COLL, int LOC>
-static int launch_edge(const StepParams<DIM>& p, const MrtMats<DIM, is_mrt(COLL)>& mm, const VsbPostOp& op,
+static int launch_edge(const StepParams<DIM>& p, const MrtMats<DIM, mats_kind(COLL)>& mm, const VsbPostOp& op,
                        int mask_before, cudaStream_t s) {
   using G = FaceGeom<DIM, LOC>;
   const int n[3] = {p.n0, p.n1, p.n2};
@@ -557,7 +579,7 @@ int edge_impl(const VsbStepArgs& a, cudaStream_t s, bool query_only, int* suppor
   if (query_only) return VSB_OK;
   VSB_REQUIRE(ok, "vsb_edge_fused: the face operations are not independent; use the ordered fix-up (edges = 0)");
   if (int rc = check_mrt(a)) return rc;
-  MrtMats<DIM, is_mrt(COLL)> mm;
+  MrtMats<DIM, mats_kind(COLL)> mm;
   fill_mats<DIM, COLL>(a, mm);
   for (int i = 0; i < a.n_post; ++i) {
     const VsbPostOp& op = a.post[i];
@@ -583,7 +605,7 @@ int step_impl(const VsbStepArgs& a, cudaStream_t s) {
   StepParams<DIM> p;
   if (int rc = fill_params<DIM>(a, p)) return rc;
   if (int rc = check_mrt(a)) return rc;
-  MrtMats<DIM, is_mrt(COLL)> mm;
+  MrtMats<DIM, mats_kind(COLL)> mm;
   fill_mats<DIM, COLL>(a, mm);
   const bool have_ops = a.n_post > 0 && a.do_stream;
   if ((a.edges == 1 || a.edges == 2) && have_ops) {
@@ -726,7 +748,7 @@ int step_impl(const VsbStepArgs& a, cudaStream_t s) {
 VSB_STEP_EXTERN(2, VSB_COLL_BGK) VSB_STEP_EXTERN(2, VSB_COLL_REG) VSB_STEP_EXTERN(2, VSB_COLL_KBC)
 VSB_STEP_EXTERN(2, VSB_COLL_MRT) VSB_STEP_EXTERN(2, VSB_COLL_MRT_SPLIT)
 VSB_STEP_EXTERN(3, VSB_COLL_BGK) VSB_STEP_EXTERN(3, VSB_COLL_REG) VSB_STEP_EXTERN(3, VSB_COLL_KBC)
-VSB_STEP_EXTERN(3, VSB_COLL_MRT) VSB_STEP_EXTERN(3, VSB_COLL_MRT_SPLIT)
+VSB_STEP_EXTERN(3, VSB_COLL_MRT) VSB_STEP_EXTERN(3, VSB_COLL_MRT_SPLIT) VSB_STEP_EXTERN(3, VSB_COLL_MRT_MOMENT)
 #undef VSB_STEP_EXTERN
 
 template <int DIM>
@@ -735,6 +757,10 @@ static int step_dispatch(const VsbStepArgs& a, cudaStream_t s, int what, int* su
   switch (a.collision) {
     case VSB_COLL_BGK: return what ? edge_impl<DIM, VSB_COLL_BGK>(a, s, what == 2, supported) : step_impl<DIM, VSB_COLL_BGK>(a, s);
     case VSB_COLL_MRT:
+      if constexpr (DIM == 3) {
+        if (mrt_is_moment<DIM>(a))
+          return what ? edge_impl<3, VSB_COLL_MRT_MOMENT>(a, s, what == 2, supported) : step_impl<3, VSB_COLL_MRT_MOMENT>(a, s);
+      }
       if (mrt_is_split<DIM>(a))
         return what ? edge_impl<DIM, VSB_COLL_MRT_SPLIT>(a, s, what == 2, supported) : step_impl<DIM, VSB_COLL_MRT_SPLIT>(a, s);
       return what ? edge_impl<DIM, VSB_COLL_MRT>(a, s, what == 2, supported) : step_impl<DIM, VSB_COLL_MRT>(a, s);

@@ -5,6 +5,7 @@
 
 #include "vsb_bc.cuh"
 #include "vsb_internal.h"
+#include "vsb_mrt_moment.cuh"
 
 namespace vsb {
 
@@ -73,14 +74,27 @@ template <int DIM> struct StepParams {
 // MRT operators: collision A and Guo source B (lbm/collision/mrt.py:88, lbm/forcing/guo.py:60-75) as dense matrices
 // and in parity-split form.  Operators that commute with the reflection c -> -c (every M^-1 S M does) run the
 // kernels instantiated for VSB_COLL_MRT_SPLIT, which use only As / Bs; any other matrix runs the dense kernels.
-constexpr int VSB_COLL_MRT_SPLIT = 100;   // internal collision id, never crosses the ABI
-__host__ __device__ constexpr bool is_mrt(int coll) { return coll == VSB_COLL_MRT || coll == VSB_COLL_MRT_SPLIT; }
+// D3Q19 operators that are diagonal in the reference's moment basis with zero rates for the conserved moments (what
+// get_mrt_collision_operator builds) run the kernels instantiated for VSB_COLL_MRT_MOMENT: no matrix at all
+// (vsb_mrt_moment.cuh), and the Guo source operator I - A/2 folded into the same application.
+constexpr int VSB_COLL_MRT_SPLIT = 100;   // internal collision ids, never cross the ABI
+constexpr int VSB_COLL_MRT_MOMENT = 101;
+__host__ __device__ constexpr bool is_mrt(int coll) {
+  return coll == VSB_COLL_MRT || coll == VSB_COLL_MRT_SPLIT || coll == VSB_COLL_MRT_MOMENT;
+}
+// what a kernel instantiated for `coll` receives next to StepParams: 0 nothing, 1 the matrices, 2 the moment rates
+__host__ __device__ constexpr int mats_kind(int coll) {
+  return coll == VSB_COLL_MRT_MOMENT ? 2 : ((coll == VSB_COLL_MRT || coll == VSB_COLL_MRT_SPLIT) ? 1 : 0);
+}
 
-template <int DIM, bool USED> struct MrtMats {
+template <int DIM, int KIND> struct MrtMats {};
+template <int DIM> struct MrtMats<DIM, 1> {
   Matrix<Lat<DIM>::Q> A, B;
   SplitOp<DIM> As, Bs;
 };
-template <int DIM> struct MrtMats<DIM, false> {};
+template <int DIM> struct MrtMats<DIM, 2> {
+  MomentOp3 mo;
+};
 
 __device__ __forceinline__ int wrap(int i, int n) {
   i += (i < 0) ? n : 0;
@@ -281,7 +295,7 @@ template <int DIM> struct WinVec { static constexpr int NC = (DIM == 2) ? 2 : 4;
 // Guo shifts u by g/(2 rho) before the equilibrium).
 template <int DIM, int COLL>
 __device__ __forceinline__ void collide_cell(float (&f)[Lat<DIM>::Q], const float (&g)[Lat<DIM>::D], int forcing,
-                                             const Relax& rx, const MrtMats<DIM, is_mrt(COLL)>& mm) {
+                                             const Relax& rx, const MrtMats<DIM, mats_kind(COLL)>& mm) {
   using L = Lat<DIM>;
   float rho, u[L::D];
   [[maybe_unused]] float feq[L::Q];
@@ -299,6 +313,39 @@ __device__ __forceinline__ void collide_cell(float (&f)[Lat<DIM>::Q], const floa
     float feq0, A[Pairs<DIM>::NP], B[Pairs<DIM>::NP];
     equilibrium_pairs<DIM>(rho, u, feq0, A, B);
     collide_kbc_pairs<DIM>(f, feq0, A, B, rx);
+  } else if constexpr (COLL == VSB_COLL_MRT_MOMENT) {
+    // f + A (feq - f) [+ B G with B = I - A/2]  =  f [+ G] + A (feq - f [- G/2]),  A applied in moment space
+    using P = Pairs<DIM>;
+    float feq0, A[P::NP], B[P::NP], xb[P::NP], xa[P::NP];
+    equilibrium_pairs<DIM>(rho, u, feq0, A, B);
+#pragma unroll
+    for (int k = 0; k < P::NP; ++k) {
+      const int q = P::q(k), o = L::opp(q);
+      xb[k] = 2.0f * A[k] - (f[q] + f[o]);
+      xa[k] = 2.0f * B[k] - (f[q] - f[o]);
+    }
+    if (forcing != VSB_FORCE_NONE) {
+      float G0, Hs[P::NP], Ha[P::NP];
+      guo_term_pairs<DIM>(g, u, G0, Hs, Ha);
+      f[0] += G0;
+#pragma unroll
+      for (int k = 0; k < P::NP; ++k) {
+        const int q = P::q(k), o = L::opp(q);
+        f[q] += Hs[k] + Ha[k];
+        f[o] += Hs[k] - Ha[k];
+        if (forcing == VSB_FORCE_GUO) { xb[k] -= Hs[k]; xa[k] -= Ha[k]; }   // half of G_q + G_opp, half of G_q - G_opp
+      }
+    }
+    float y0, yb[P::NP], ya[P::NP];
+    moment_op3_apply(mm.mo, xb, xa, y0, yb, ya);
+    f[0] += y0;
+#pragma unroll
+    for (int k = 0; k < P::NP; ++k) {
+      const int q = P::q(k), o = L::opp(q);
+      f[q] += yb[k] + ya[k];
+      f[o] += yb[k] - ya[k];
+    }
+    return;
   } else if constexpr (COLL == VSB_COLL_MRT_SPLIT) {
     float feq0, A[Pairs<DIM>::NP], B[Pairs<DIM>::NP];
     equilibrium_pairs<DIM>(rho, u, feq0, A, B);

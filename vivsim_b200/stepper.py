@@ -155,8 +155,15 @@ class Stepper:
         g = spec.get("g")
         self._g_field = None
         if g is not None and a.forcing:
-            if isinstance(g, torch.Tensor) and g.ndim == self.dim + 1:
-                self._g_field = L.dev(g, name="g")
+            if getattr(g, "ndim", 1) == self.dim + 1:
+                # a force field (dim, *shape): stored like the IB force window, cell-major with the components packed
+                # (float2 in 2-D, float4 in 3-D), the window being the whole grid
+                gt = L.dev(torch.as_tensor(np.asarray(g)).to(self.device) if not isinstance(g, torch.Tensor) else g, name="g")
+                if tuple(gt.shape) != (self.dim,) + tuple(self.shape):
+                    raise ValueError(f"g must have shape {(self.dim,) + tuple(self.shape)}, got {tuple(gt.shape)}")
+                packed = torch.zeros(tuple(self.shape) + (2 if self.dim == 2 else 4,), device=self.device, dtype=torch.float32)
+                packed[..., :self.dim] = gt.movedim(0, -1)
+                self._g_field = packed.contiguous()
             else:
                 gv = [float(x) for x in np.asarray(g, dtype=np.float64).reshape(-1)]
                 if len(gv) != self.dim:
