@@ -26,7 +26,7 @@ extern "C" {
 
 typedef void* vsb_stream_t; /* cudaStream_t */
 
-enum { VSB_OK = 0, VSB_ERR_INVALID = -1, VSB_ERR_CUDA = -2 };
+enum { VSB_OK = 0, VSB_ERR_INVALID = -1, VSB_ERR_CUDA = -2, VSB_ERR_TIMEOUT = -3 };
 enum { VSB_COLL_BGK = 0, VSB_COLL_MRT = 1, VSB_COLL_KBC = 2, VSB_COLL_REG = 3 };
 enum { VSB_FORCE_NONE = 0, VSB_FORCE_EDM = 1, VSB_FORCE_GUO = 2 };
 enum { VSB_BC_NEE = 0, VSB_BC_NEBB = 1, VSB_BC_EQUILIBRIUM = 2, VSB_BC_BOUNCE_BACK = 3, VSB_BC_SPECULAR = 4,
@@ -284,6 +284,10 @@ typedef struct {
   int win_shift[3];           /* added to body->origin2[parity] by the fluid kernels: the body state of a slab-decomposed
                                  run carries GLOBAL coordinates (identical on every rank) while `grid` is the local
                                  slab with its ghost layer: win_shift[0] = 1 - x0 of the slab */
+  int early_launch;           /* 1: the fused kernel may start while the kernel enqueued before it on `stream` is still
+                                 running (programmatic dependent launch; that kernel must not produce anything this
+                                 launch reads).  Used to put a body's short IB chain on the SMs FIRST and let the bulk
+                                 pass (band = 1) fill the rest of the device behind it */
 } VsbStepArgs;
 
 int vsb_step(const VsbStepArgs* args, vsb_stream_t stream);
@@ -344,6 +348,20 @@ int vsb_step_host_ode(VsbStepArgs* args, const VsbMdfArgs* mdf, const VsbBodyPar
 int vsb_run_host_ode(VsbStepArgs* args, VsbMdfArgs* mdf, const VsbBodyParams* params, VsbBodyState* pinned,
                      const VsbHostPlan* plan, int n_steps);
 
+/* NON-BLOCKING variant of vsb_run_host_ode: the n_steps steps are only ENQUEUED and the call returns at once -- nothing
+ * is polled or synchronised on the calling thread, so it can sit inside a host-language custom call (an XLA FFI
+ * handler must not block its stream's thread).  Per step, on `ib`: the MDF chain posts the total force into
+ * mdf->host_mail, a host function (cudaLaunchHostFunc) that the driver runs once the chain has finished advances
+ * (a, v, d) on the CPU (dyn.py:5-51, `pinned` is the master copy), one asynchronous 92-byte host->device copy sends the
+ * state back; bulk rows on `main`, window x-range on `ib` before the host function, joined into `main`.  args / mdf as
+ * for vsb_run_host_ode, advanced in place.  `pinned`, *params, mdf->host_mail and the device buffers must stay valid
+ * until the work enqueued on `main` has completed.  A step pays the driver's host-function latency (tens of
+ * microseconds) instead of the mailbox poll's few: prefer vsb_run_host_ode[_multi] where blocking is acceptable.
+ * Not capturable into a CUDA graph (the per-call context is released by the last host function); synchronise `main`
+ * before using vsb_run_host_ode / vsb_step_host_ode on the same body (they read `pinned` on the calling thread). */
+int vsb_enqueue_host_ode(VsbStepArgs* args, VsbMdfArgs* mdf, const VsbBodyParams* params, VsbBodyState* pinned,
+                         const VsbHostPlan* plan, int n_steps);
+
 /* The same for n_domains (1..64) INDEPENDENT simulations on one GPU (an ensemble: e.g. the reduced-velocity sweep of a
  * VIV study, each case being one run of examples/2d/vortex_induced_vibration.py), n_steps each, in one call.  Every
  * domain brings its own argument blocks, body state, mailbox and streams (plans[i]->main / ib must differ between
@@ -387,6 +405,13 @@ int vsb_halo_push(const VsbHaloArgs* args, vsb_stream_t stream);
  * second stream.  vsb_halo_push == send followed by wait. */
 int vsb_halo_send(const VsbHaloArgs* args, vsb_stream_t stream);
 int vsb_halo_wait(const VsbHaloArgs* args, vsb_stream_t stream);
+
+/* The cross-GPU waits above (and the flag barriers of vsb_ibshard_chain) never hang: after 10 s without an answer they
+ * give up, set word [2] of their `counter` and let the stream run on with stale ghost data.  vsb_sync_status makes that
+ * visible to the host: it waits for `stream` (the ONE synchronising call of this group -- call it where the host reads
+ * results anyway), returns VSB_ERR_TIMEOUT with the step number in vsb_last_error() if the indicator is set, else VSB_OK.
+ * `counter` is VsbHaloArgs.counter or VsbIbShard.counter. */
+int vsb_sync_status(const uint32_t* counter, vsb_stream_t stream);
 
 /* ---- multi-GPU: immersed-boundary chain shared by all ranks over peer memory --------------------------------- *
  * The slab decomposition cuts the fluid along x; an immersed body is compact, so "owner computes" would leave its

@@ -11,10 +11,10 @@ cells = bench.cells_of(spec)
 f0 = configs.uniform_state(spec, noise=1e-3)
 sync = torch.cuda.synchronize
 for n_dom in (1, 8):
-    for chain in ("cluster", "barrier", "launches"):
+    for chain, first in (("cluster", False), ("cluster", True), ("barrier", False), ("barrier", True), ("launches", False)):
         sts = []
         for _ in range(n_dom):
-            st = Stepper(spec, body=dict(body), dyn_mode="device", ib_chain=chain)
+            st = Stepper(spec, body=dict(body), dyn_mode="device", ib_chain=chain, chain_first=first)
             st.set_f(f0); st.step(1)
             sts.append(st)
         loop = bench.GraphLoop(sts, 10)
@@ -23,7 +23,7 @@ for n_dom in (1, 8):
         dt, _, _ = bench.timed(lambda: loop.run(n), sync)
         us = dt / (n * 10 * n_dom) * 1e6
         d, v, a, h = sts[0].body_state()
-        print(f"domains {n_dom} chain {chain:9s}: {us:7.2f} us per lattice step per domain, {cells / us / 1e3:8.1f} GLUPS, "
+        print(f"domains {n_dom} chain {chain:9s} chain_first {int(first)}: {us:7.2f} us per lattice step per domain, {cells / us / 1e3:8.1f} GLUPS, "
               f"d = {d}, h = {h}", flush=True)
         del loop, sts
         torch.cuda.empty_cache()

@@ -17,6 +17,11 @@ def run(tag, spec, bpc, vecs=(1, 2, 4), steps=20):
         print(f"{tag:28s} vec={vec} {ms*1e3:9.1f} us/step  {cells/ms/1e3:9.0f} MLUPS  {cells*bpc/ms/1e6/6452.8:5.3f} of HBM")
         del st
 
+if "quick3d" in sys.argv:
+    for coll in ("bgk", "kbc", "mrt"):
+        run(f"D3Q19 {coll} 256^3", dict(dim=3, shape=(256, 256, 256), collision=coll, omega=1.7, forcing=None, post=[], u0=0.05), 152, vecs=(2, 4))
+    run("D3Q19 mrt+guo(uniform) 256^3", dict(dim=3, shape=(256, 256, 256), collision="mrt", omega=1.7, forcing="guo", g=(1e-6, 0.0, 0.0), post=[], u0=0.05), 152, vecs=(2, 4))
+    sys.exit(0)
 if "quick" in sys.argv:
     for coll in ("bgk", "kbc", "mrt"):
         run(f"D3Q19 {coll} 256^3", dict(dim=3, shape=(256, 256, 256), collision=coll, omega=1.7, forcing=None, post=[], u0=0.05), 152, vecs=(2, 4))

@@ -356,8 +356,8 @@ def test_body_history_matches_reference_scan(golden):
     spec, body, f0, (d, v, a), n = cases.viv(g)
     from vivsim_b200 import Stepper
     ref = g["viv_dvah"]                         # columns d(2) v(2) a(2) h(2) per step
-    for kw in (dict(dyn_mode="host"), dict(dyn_mode="device"), dict(dyn_mode="device", use_graph=True),
-               dict(dyn_mode="device", fuse_ib=False, overlap=False)):
+    for kw in (dict(dyn_mode="host"), dict(dyn_mode="host", host_ode="callback"), dict(dyn_mode="device"),
+               dict(dyn_mode="device", use_graph=True), dict(dyn_mode="device", fuse_ib=False, overlap=False)):
         bd = dict(body, d0=d, v0=v, a0=a, n_dof=2, history=64)
         st = Stepper(spec, body=bd, follow=1, **kw).set_f(f0)
         st.step(n)
@@ -379,6 +379,26 @@ def test_body_history_matches_reference_scan(golden):
         st.body_history(9)
     with pytest.raises(Exception):
         Stepper(spec, body=dict(body, n_dof=2), dyn_mode="device").set_f(f0).body_history()
+
+
+def test_non_blocking_host_ode_equals_the_polled_one(golden):
+    """vsb_enqueue_host_ode (Newmark update as a stream-ordered host function, nothing blocks the calling thread)
+    against vsb_run_host_ode (mailbox polled by the caller): same arithmetic in the same order, so the body record is
+    identical; several calls in a row without a synchronisation in between, then the reference's VIV record."""
+    g = golden["recipes"]
+    spec, body, f0, (d, v, a), n = cases.viv(g)
+    from vivsim_b200 import Stepper
+    bd = dict(body, d0=d, v0=v, a0=a, n_dof=2, history=64)
+    polled = Stepper(spec, body=dict(bd), dyn_mode="host", follow=1).set_f(f0)
+    polled.step(n)
+    cb = Stepper(spec, body=dict(bd), dyn_mode="host", host_ode="callback", follow=1).set_f(f0)
+    cb.step(3); cb.step(1); cb.step(n - 4)          # back-to-back enqueues
+    dp, hp = polled.body_history()
+    dc, hc = cb.body_history()
+    assert_close(dc, dp, rtol=1e-6, what="d, callback vs poll")
+    assert_close(hc, hp, rtol=1e-5, what="h, callback vs poll")
+    assert_close(dc, g["viv_dvah"][:, 0:2], rtol=1e-4, what="d vs reference")
+    assert_close(N(cb.get_f()), g["viv_f20"], what="viv f (callback)")
 
 
 def test_host_ode_ensemble_matches_solo_runs(golden):

@@ -33,7 +33,7 @@ EXPORTS = [
     "vsb_body_newmark", "vsb_edge_fused", "vsb_edge_fused_supported", "vsb_ib_fused", "vsb_ib_fused_supported",
     "vsb_halo_push", "vsb_body_newmark_host", "vsb_halo_send", "vsb_halo_wait", "vsb_step_host_ode",
     "vsb_post_field", "vsb_post_mean", "vsb_mg_fine_to_coarse", "vsb_mg_coarse_to_fine", "vsb_run_host_ode",
-    "vsb_run_host_ode_multi", "vsb_ibshard_chain", "vsb_ibshard_barrier",
+    "vsb_run_host_ode_multi", "vsb_ibshard_chain", "vsb_ibshard_barrier", "vsb_enqueue_host_ode", "vsb_sync_status",
 ]
 
 
@@ -93,7 +93,7 @@ class VsbStepArgs(C.Structure):
                 ("win_origin", C.c_int * 3), ("win_size", C.c_int * 3), ("body", C.c_void_p), ("parity", C.c_int),
                 ("n_post", C.c_int), ("post", C.POINTER(VsbPostOp)), ("vec", C.c_int), ("band", C.c_int),
                 ("edges", C.c_int), ("sub_begin", C.c_int), ("sub_end", C.c_int), ("edge_rows_only", C.c_int),
-                ("win_shift", C.c_int * 3)]
+                ("win_shift", C.c_int * 3), ("early_launch", C.c_int)]
 
 
 MAX_RANKS = 8

@@ -125,4 +125,18 @@ int vsb_halo_push(const VsbHaloArgs* a, vsb_stream_t stream) { return halo_launc
 int vsb_halo_send(const VsbHaloArgs* a, vsb_stream_t stream) { return halo_launch(a, 1, stream); }
 int vsb_halo_wait(const VsbHaloArgs* a, vsb_stream_t stream) { return halo_launch(a, 2, stream); }
 
+int vsb_sync_status(const uint32_t* counter, vsb_stream_t stream) {
+  VSB_REQUIRE(counter != nullptr, "vsb_sync_status: null counter");
+  unsigned host[3] = {0u, 0u, 0u};
+  cudaError_t e = cudaMemcpyAsync(host, counter, sizeof(host), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+  if (e != cudaSuccess) return vsb::cuda_fail(e, "vsb_sync_status");
+  if (host[2] != 0u) {
+    vsb::set_error("a cross-GPU wait timed out after 10 s near step %u: a neighbouring rank never published that step "
+                   "(the ranks did not run the same number of steps, or one of them stopped)", host[0]);
+    return VSB_ERR_TIMEOUT;
+  }
+  return VSB_OK;
+}
+
 }  // extern "C"

@@ -119,6 +119,8 @@ __global__ void __launch_bounds__(kBlock, DIM == 3 ? 5 : 8) k_mdf_stage(const St
   constexpr int PPL = NS / G;                // stencil points per lane
   constexpr int NC = WinVec<DIM>::NC;
   using VecF = typename std::conditional<DIM == 2, float2, float4>::type;
+  // a fused step enqueued behind this launch with early_launch = 1 may start as soon as every CTA here is resident
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   __shared__ float s_force[3];
   if (threadIdx.x < 3) s_force[threadIdx.x] = 0.f;
   __syncthreads();
@@ -1007,6 +1009,79 @@ int vsb_run_host_ode(VsbStepArgs* a, VsbMdfArgs* mdf, const VsbBodyParams* bp, V
                      const VsbHostPlan* plan, int n_steps) {
   VSB_REQUIRE(a && mdf && bp && pinned && plan, "vsb_run_host_ode: null argument");
   return vsb_run_host_ode_multi(1, &a, &mdf, &bp, &pinned, &plan, n_steps);
+}
+
+// ---- non-blocking host ODE: the Newmark update runs as a stream-ordered host function
+namespace {
+struct HostOdeCall {            // lives from the enqueue until the last host function of the call has run
+  VsbBodyParams bp;
+  VsbBodyState* pinned;
+  VsbHostMail* mail;
+};
+struct HostOdeTick { HostOdeCall* call; int parity; int last; };
+
+void CUDART_CB host_ode_tick(void* user) {
+  HostOdeTick* t = static_cast<HostOdeTick*>(user);
+  HostOdeCall* c = t->call;
+  for (int k = 0; k < 3; ++k) c->pinned->force_sum[k] = reinterpret_cast<volatile float*>(c->mail->force)[k];
+  host_body_update(c->pinned, &c->bp, t->parity);
+  if (t->last) delete c;
+  delete t;
+}
+}  // namespace
+
+int vsb_enqueue_host_ode(VsbStepArgs* a, VsbMdfArgs* mdf, const VsbBodyParams* bp, VsbBodyState* pinned,
+                         const VsbHostPlan* plan, int n_steps) {
+  VSB_REQUIRE(a && mdf && bp && pinned && plan, "vsb_enqueue_host_ode: null argument");
+  VSB_REQUIRE(mdf->body != nullptr && mdf->host_mail != nullptr, "vsb_enqueue_host_ode: needs a body state and a host mailbox");
+  VSB_REQUIRE(bp->n_dof >= 1 && bp->n_dof <= 3, "n_dof must be 1..3, got %d", bp->n_dof);
+  VSB_REQUIRE(a->do_stream && a->do_collide, "vsb_enqueue_host_ode: full steps only");
+  HostOdeDomain d;
+  d.a = a; d.mdf = mdf; d.bp = bp; d.pinned = pinned;
+  d.main = (cudaStream_t)plan->main; d.ib = (cudaStream_t)plan->ib; d.edge = (cudaStream_t)plan->edge;
+  d.fork = (cudaEvent_t)plan->ev_fork; d.ib_done = (cudaEvent_t)plan->ev_ib; d.edge_done = (cudaEvent_t)plan->ev_edge;
+  VSB_REQUIRE(d.ib && d.fork && d.ib_done, "vsb_enqueue_host_ode: plan needs the ib stream and the fork / ib events");
+  d.has_edges = a->edges == 1 && a->n_post > 0;
+  if (d.has_edges) VSB_REQUIRE(d.edge && d.edge_done, "vsb_enqueue_host_ode: plan needs the edge stream / event");
+  d.want = 0; d.steps_done = 0; d.in_flight = 0;
+  d.graph[0] = d.graph[1] = nullptr;
+  if (n_steps <= 0) return VSB_OK;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (d.main != nullptr && d.main != cudaStreamLegacy) cudaStreamIsCapturing(d.main, &cap);
+  VSB_REQUIRE(cap == cudaStreamCaptureStatusNone, "vsb_enqueue_host_ode: cannot be captured into a CUDA graph");
+  HostOdeCall* call = new HostOdeCall{*bp, pinned, mdf->host_mail};
+  const int saved_seq = mdf->mail_seq;
+  const int seq0 = mdf->host_mail->next;
+  int rc = VSB_OK;
+  cudaError_t e = cudaSuccess;
+  int enqueued = 0;
+  for (int k = 0; k < n_steps && rc == VSB_OK; ++k) {
+    mdf->mail_seq = seq0 + k;                  // nobody polls it here; kept monotonic for a later vsb_run_host_ode
+    if ((rc = host_ode_kernels(d, false))) break;
+    HostOdeTick* tick = new HostOdeTick{call, mdf->parity & 1, k == n_steps - 1};
+    if ((e = cudaLaunchHostFunc(d.ib, host_ode_tick, tick)) != cudaSuccess) {
+      delete tick;
+      rc = cuda_fail(e, "vsb_enqueue_host_ode (host function)");
+      break;
+    }
+    ++enqueued;
+    if ((e = cudaMemcpyAsync(mdf->body, pinned, sizeof(VsbBodyState), cudaMemcpyHostToDevice, d.ib)) != cudaSuccess ||
+        (e = cudaEventRecord(d.ib_done, d.ib)) != cudaSuccess || (e = cudaStreamWaitEvent(d.main, d.ib_done, 0)) != cudaSuccess ||
+        (d.has_edges && (e = cudaStreamWaitEvent(d.main, d.edge_done, 0)) != cudaSuccess)) {
+      rc = cuda_fail(e, "vsb_enqueue_host_ode (state copy / join)");
+      break;
+    }
+    host_ode_flip(d);
+  }
+  mdf->mail_seq = saved_seq;
+  if (rc != VSB_OK) {
+    // ticks already enqueued still reference `call`: let them run, then release it (none of them is marked last)
+    if (enqueued > 0) cudaStreamSynchronize(d.ib);
+    delete call;
+  } else {
+    mdf->host_mail->next = seq0 + n_steps;
+  }
+  return rc;
 }
 
 int vsb_step_host_ode(VsbStepArgs* a, const VsbMdfArgs* mdf, const VsbBodyParams* bp, VsbBodyState* pinned,

@@ -70,6 +70,8 @@ k_mdf_cluster2d(const StepParams<2> sp, const MdfParams p, const BodyUpdate bu, 
   const int m0 = rank * kRows;
   const int n_mark = (int)p.n_markers;
 
+  // a fused step enqueued behind this launch with early_launch = 1 may start as soon as every CTA here is resident
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (debug_stop == 5) return;                      // timing aid: the launch alone
   int org[3] = {p.origin0[0], p.origin0[1], 0};
   if (p.body) { org[0] = p.body->origin2[p.parity][0]; org[1] = p.body->origin2[p.parity][1]; }

@@ -683,7 +683,23 @@ int step_impl(const VsbStepArgs& a, cudaStream_t s) {
       if (e == 0) p.wall_blocks0 = nbw;
       extra += nbw;
     }
-    kernel<<<p.nb_bulk + extra, best_bs, 0, s>>>(p, mm);
+    if (a.early_launch) {
+      // programmatic dependent launch: begin as soon as every CTA of the preceding kernel on this stream has started
+      // (they call griddepcontrol.launch_dependents first thing) -- that kernel keeps the SMs it already holds
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(p.nb_bulk + extra);
+      cfg.blockDim = dim3(best_bs);
+      cfg.dynamicSmemBytes = 0;
+      cfg.stream = s;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      cudaLaunchKernelEx(&cfg, kernel, p, mm);
+    } else {
+      kernel<<<p.nb_bulk + extra, best_bs, 0, s>>>(p, mm);
+    }
   };
   if (vec == 4) launch(k_step<DIM, COLL, 4>);
   else if (vec == 2) launch(k_step<DIM, COLL, 2>);

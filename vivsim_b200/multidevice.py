@@ -150,6 +150,11 @@ class PeerHalo:
     def timed_out(self):
         return bool(self.counter[2].item())
 
+    def check(self):
+        """Synchronise and raise VsbError if a wait for a neighbour gave up (vsb_sync_status)."""
+        L, C = self._L, self._C
+        L.check(L.lib().vsb_sync_status(C.c_void_p(self.counter.data_ptr()), L.stream()))
+
 
 class LocalHalo:
     """Single-rank stand-in for PeerHalo: the "neighbours" are the slab itself (periodic wrap), so `send` copies the
@@ -178,6 +183,9 @@ class LocalHalo:
 
     def timed_out(self):
         return False
+
+    def check(self):
+        pass
 
 
 # Cost model behind the marker shares (measured on B200 with BASELINE config 5, profiles/r02_summary.md): one marker costs a
@@ -354,6 +362,12 @@ class IbShard:
     def timed_out(self):
         return bool(self.counter[2].item())
 
+    def check(self):
+        """Synchronise and raise VsbError if a flag barrier of the shared chain gave up (vsb_sync_status)."""
+        import ctypes as C
+        from . import _lib as L
+        L.check(L.lib().vsb_sync_status(C.c_void_p(self.counter.data_ptr()), L.stream()))
+
 
 def localize_spec(spec, slab, local_ib=None, ib_mode="owner"):
     """Per-rank step description: local extent with ghost layers, x-face operations only on the owning rank,
@@ -480,7 +494,16 @@ class SlabStepper:
         """Physical rows of F_n on this rank, shape (Q, nx_local, ...)."""
         if self.peer is not None and self.stepper._kind == "S":
             self.peer.wait()                      # the neighbours' last sends into this rank's ghost layers
+        self.check()
         return self.stepper.get_f()[:, 1:-1].contiguous()
+
+    def check(self):
+        """Raise VsbError if any cross-GPU wait of the steps taken so far timed out (synchronises this rank's stream).
+        Called by every method that hands results to the host."""
+        if self.peer is not None:
+            self.peer.check()
+        if self.ib_shard is not None:
+            self.ib_shard.check()
 
     def gather_f(self):
         """Global F_n on every rank (all-gather along x) -- for tests and I/O."""
@@ -495,6 +518,7 @@ class SlabStepper:
         """Sum over all bodies / ranks of the hydrodynamic force on the bodies (small all-reduce)."""
         st = self.stepper
         dim = st.dim
+        self.check()
         # sharded chain: every rank holds the forces of its share of the markers (the rest are zero)
         h = (-st.marker_force.sum(dim=0)) if self.owns_body else torch.zeros(dim, device=st.device)
         if self.slab.world > 1:

@@ -77,7 +77,8 @@ def cut_marker_chunks(markers):
 
 class Stepper:
     def __init__(self, spec, device="cuda", rows=None, vec=0, body=None, dyn_mode="host", follow=1, use_graph=False,
-                 fuse_ib=True, fuse_edges=True, overlap=True, buffers=None, ib_chain="auto", ib_shard=None):
+                 fuse_ib=True, fuse_edges=True, overlap=True, buffers=None, ib_chain="auto", ib_shard=None,
+                 chain_first=None, host_ode="poll"):
         """rows: (begin, end) range of the slowest axis that is physical domain (ghost layers outside; slab
         decomposition).  body: dict(m, k, c, added_mass, n_dof=2, d0, v0, a0) for a moving rigid body coupled by
         Newmark-beta; m, k, c scalars (dyn.py:44-46) or (n_dof, n_dof) matrices / length-n_dof diagonals
@@ -88,6 +89,13 @@ class Stepper:
         ib_chain: how a small body's MDF iterations are chained in one launch -- "auto", "barrier" (grid barriers,
         cooperative launch), "cluster" (one thread-block cluster, work fields in distributed shared memory; 2-D,
         <= 512 markers) or "launches" (one launch per iteration).
+        chain_first: put a one-launch IB chain on the SMs BEFORE the bulk pass -- the bulk is enqueued behind it as a
+        programmatic dependent launch and fills the rest of the device, the window band follows the chain on a second
+        stream (None: on when the chain is one launch and the body's ODE is not on the host).
+        host_ode: with dyn_mode="host", how the host learns that a step's force has arrived -- "poll" (the calling
+        thread polls a page-locked mailbox inside vsb_run_host_ode: lowest latency, blocks until the steps are done) or
+        "callback" (vsb_enqueue_host_ode: the Newmark update runs as a stream-ordered host function, step() returns
+        at once).
         ib_shard: multidevice.IbShard -- this stepper is one slab of a decomposed run and shares the IB chain with the
         other ranks (spec['ib'] and the body then carry GLOBAL coordinates).
         fuse_ib / fuse_edges / overlap: use the single-kernel IB path, the single-kernel wall path and concurrent
@@ -125,6 +133,10 @@ class Stepper:
         if ib_chain not in L.CHAIN:
             raise ValueError(f"ib_chain must be one of {sorted(L.CHAIN)}, got {ib_chain!r}")
         self._ib_chain = ib_chain
+        self._chain_first_want = chain_first
+        if host_ode not in ("poll", "callback"):
+            raise ValueError(f"host_ode must be 'poll' or 'callback', got {host_ode!r}")
+        self._host_ode = host_ode
         self._shard = ib_shard
         # extent the IB window and the body live in: the whole decomposed grid when the chain is shared
         self._gshape = tuple(ib_shard.slab.global_shape) if ib_shard is not None else self.shape
@@ -678,6 +690,23 @@ class Stepper:
             self._ib_part(st_ib)                               # IB chain (its few CTAs should not queue behind
             if pipelined and self._shard is not None:          # the bulk), then the window's x-range
                 self._chain_done.record(s_ib)
+            if self._chain_first() and not host_body and not pipelined:
+                # The chain is ONE small launch: let it take its SMs first.  The bulk follows on the same stream as a
+                # programmatic dependent launch (it starts once every CTA of the chain is resident, not when the
+                # chain ends) and the band waits for the chain on the main stream.  Enqueued the other way round, the
+                # bulk's ~1200 CTAs occupy every SM first and the chain's CTAs trickle in as slots free up.
+                self._chain_ev.record(s_ib)
+                a.band, a.early_launch = 1, 1
+                L.check(lib.vsb_step(ref, st_ib))
+                a.early_launch = 0
+                main.wait_event(self._chain_ev)
+                a.band = 2
+                L.check(lib.vsb_step(ref, st_main))
+                main.wait_stream(s_ib)
+                a.band = 0
+                if with_ib:
+                    self._parity ^= 1
+                return
             a.band = 2
             L.check(lib.vsb_step(ref, st_ib))
             if not host_body:
@@ -707,6 +736,16 @@ class Stepper:
             halo.push(dst_index, st_main)
         if with_ib:
             self._parity ^= 1
+
+    def _chain_first(self):
+        if getattr(self, "_chain_first_on", None) is None:
+            want = self._chain_first_want
+            if want is None:
+                want = os.environ.get("VSB_CHAIN_FIRST", "0") == "1"
+            self._chain_first_on = bool(want and self.ib is not None and self._mdf_one_launch and not self._use_uwin
+                                        and not self.ib_fused and self._shard is None and self.halo is None)
+            self._chain_ev = torch.cuda.Event()
+        return self._chain_first_on
 
     def _host_ode_step(self, main):
         """One pass with the rigid-body ODE on the host through vsb_step_host_ode (fork / join in C)."""
@@ -770,8 +809,9 @@ class Stepper:
         """n whole steps with the rigid-body ODE on the host in one C call (vsb_run_host_ode): the host loop, the
         mailbox polling and the Newmark update all happen in C; Python only flips its buffer / parity bookkeeping."""
         self._host_ode_prepare(torch.cuda.current_stream())
-        L.check(L.lib().vsb_run_host_ode(C.byref(self._args), C.byref(self._mdf), C.byref(self._hparams),
-                                         C.c_void_p(self._body_pin.data_ptr()), C.byref(self._plan), int(n)))
+        fn = L.lib().vsb_enqueue_host_ode if self._host_ode == "callback" else L.lib().vsb_run_host_ode
+        L.check(fn(C.byref(self._args), C.byref(self._mdf), C.byref(self._hparams),
+                   C.c_void_p(self._body_pin.data_ptr()), C.byref(self._plan), int(n)))
         self._host_ode_finish(n)
 
     def _ib_part(self, st):
