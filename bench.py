@@ -46,9 +46,11 @@ CHUNK = 500          # lattice time steps per domain per bench step (reference C
 GRAPH_STEPS = 10     # lattice time steps per domain per CUDA-graph replay (even: the buffers ping-pong)
 # ensemble members: overlap the IB chain with the bulk inside each domain (the domains overlap each other either way)
 ENSEMBLE_OVERLAP = os.environ.get("VSB_BENCH_OVERLAP", "1") != "0"
-# how the MDF iterations of an ensemble member are chained: with other domains' kernels to fill the gaps, one plain
-# launch per iteration beats the single-launch chains (measured: launches 76.2, cluster 73.6, barrier 68.6 GLUPS)
-ENSEMBLE_CHAIN = os.environ.get("VSB_BENCH_CHAIN", "launches")
+# how the MDF iterations of an ensemble member are chained (profiles/r02_chain_modes_*.txt, 8 domains, two visits): all
+# iterations in one cooperative launch with grid barriers 77.2 / 78.6 GLUPS, one launch per iteration 75.7 / 78.1, the
+# marker-space cluster kernel 73.5 / 76.5; enqueuing the chain before the bulk (chain_first) is within the noise
+ENSEMBLE_CHAIN = os.environ.get("VSB_BENCH_CHAIN", "barrier")
+CHAIN_FIRST = os.environ.get("VSB_BENCH_CHAIN_FIRST", "0") != "0"
 
 
 def peaks():
@@ -387,7 +389,8 @@ def run_ours(args):
     replays_per_step = CHUNK // GRAPH_STEPS
     if world == 1:
         for i in range(n_rep):
-            st = Stepper(spec, body=dict(body), dyn_mode="device", overlap=ENSEMBLE_OVERLAP, ib_chain=ENSEMBLE_CHAIN)
+            st = Stepper(spec, body=dict(body), dyn_mode="device", overlap=ENSEMBLE_OVERLAP, ib_chain=ENSEMBLE_CHAIN,
+                         chain_first=CHAIN_FIRST)
             st.set_f(f0)
             st.step(1)     # prologue: internal state is now S_0
             steppers.append(st)
@@ -637,7 +640,7 @@ def run_ours(args):
                                          + (" on every GPU" if world > 1 else "")
                                          + " (reference update_chunk, vortex_induced_vibration.py:28,150-157)",
                            "lattice_steps_per_bench_step": CHUNK, "cells_per_lattice_step": cells,
-                           "ensemble_domains": n_rep, "ib_chain": ENSEMBLE_CHAIN,
+                           "ensemble_domains": n_rep, "ib_chain": ENSEMBLE_CHAIN, "chain_first": CHAIN_FIRST,
                            "graph_replays": timed_replays, "eager_steps": 0,
                            "lattice_steps_per_graph_replay": GRAPH_STEPS,
                            "us_per_lattice_step": dt / (lattice_steps * n_rep) * 1e6,

@@ -44,13 +44,17 @@ for chain in chains:
                 continue
         for what in combos:
             skip.clear(); skip.update(what)
-            st = Stepper(spec, body=dict(body), dyn_mode="device", ib_chain=chain, chain_first=first)
-            st.set_f(f0); st.step(1)
-            loop = bench.GraphLoop([st], 10)
+            n_dom = int(os.environ.get("VSB_PARTS_DOMAINS", "1"))
+            sts = []
+            for _ in range(n_dom):
+                st = Stepper(spec, body=dict(body), dyn_mode="device", ib_chain=chain, chain_first=first)
+                st.set_f(f0); st.step(1)
+                sts.append(st)
+            loop = bench.GraphLoop(sts, 10)
             loop.run(20)
             n = 200
             dt, _, _ = bench.timed(lambda: loop.run(n), sync)
-            us = dt / (n * 10) * 1e6
+            us = dt / (n * 10 * n_dom) * 1e6
             ran = [p for p in ("chain", "band", "bulk") if p not in skip]
-            print(f"chain {chain:8s} chain_first {int(first)}  runs {'+'.join(ran):16s}: {us:6.2f} us per step", flush=True)
-            del loop, st
+            print(f"domains {n_dom} chain {chain:8s} chain_first {int(first)}  runs {'+'.join(ran):16s}: {us:6.2f} us per step", flush=True)
+            del loop, st, sts

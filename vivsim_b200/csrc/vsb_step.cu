@@ -76,32 +76,44 @@ __global__ void __launch_bounds__(step_max_threads<DIM, COLL>(), step_min_ctas<D
   const int nv = p.n2 / VEC;
   int worg[3];
   window_origin<DIM>(p, worg);
-  // rows of the slowest axis handled by this launch: all of [r_begin, r_end), or only / all but the x-range of
-  // the force window (band), so that the bulk can run while the IB kernels still produce the window's force
+  // rows of the slowest axis handled by this launch: all of [r_begin, r_end), or only / all but the band of the force
+  // window, so that the bulk can run while the IB kernels still produce the window's force.
   const int band_lo = max(p.s_begin, worg[0]), band_hi = min(p.s_end, worg[0] + p.wsz[0]);
-  // In 3-D the band is the window's (x, y) footprint over all z: band 2 enumerates wsz[1] lines per x plane.
+  // The band is the window's (x, y) footprint over all z in 3-D (band 2 enumerates wsz[1] lines per x plane) and, in
+  // 2-D, the window's x rows restricted to the vector groups that overlap its y-range (band 2 enumerates p.nvb groups
+  // per row, a launch constant that covers any alignment of the moving window).
   const bool box = DIM == 3 && p.band == 2;
+  const bool box2 = DIM == 2 && p.band == 2;
+  const int jb_lo = (DIM == 2) ? worg[1] / VEC : 0;                               // vector groups of the window's y-range
+  const int jb_hi = (DIM == 2) ? (worg[1] + p.wsz[1] - 1) / VEC : 0;              // (inclusive)
   const int row0 = (p.band == 2) ? band_lo : p.s_begin;
   const int nrow = p.edge_rows ? 2 : ((p.band == 2) ? max(band_hi - band_lo, 0) : p.s_end - p.s_begin);
   const int lines = box ? p.wsz[1] : p.n1;            // z lines per x plane handled by this launch
-  const unsigned total = (unsigned)((DIM == 2) ? nrow : nrow * lines) * (unsigned)nv;   // < 2^31, checked by the host
+  const int nvr = box2 ? p.nvb : nv;                  // vector groups per row enumerated by this launch
+  const unsigned total = (unsigned)((DIM == 2) ? nrow : nrow * lines) * (unsigned)nvr;   // < 2^31, checked by the host
   unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
-  bool active = gid < total;
-  if (!active) gid = 0;          // the lane stays in the shuffles; it loads and stores nothing
-  const unsigned row = fast_div(gid, p.div_nv);
-  const int j = (int)(gid - row * (unsigned)nv);
+  bool valid = gid < total;      // the lane addresses cells of the grid (it loads them, so that its neighbours' shuffles
+  if (!valid) gid = 0;           // are right); `active` below: it also computes and stores them
+  const unsigned row = fast_div(gid, box2 ? p.div_nvb : p.div_nv);
+  const int jr = (int)(gid - row * (unsigned)nvr);    // group counter within the enumerated part of the row
+  const int j = box2 ? jb_lo + jr : jr;
+  if (box2 && j >= nv) valid = false;
   const int rx = (DIM == 2) ? (int)row : (int)fast_div(row, box ? p.div_w1 : p.div_n1);   // row counter along the slowest axis
   const int ix0 = p.edge_rows ? (rx == 0 ? p.r_begin : p.r_end - 1) : row0 + rx;
   const int i0 = (DIM == 2) ? 0 : ix0;
   const int i1 = (DIM == 2) ? ix0 : (int)row - rx * lines + (box ? worg[1] : 0);
-  const int i2 = j * VEC;
+  const int i2 = (valid ? j : 0) * VEC;
   const int lane = threadIdx.x & 31;
   const int n12 = p.n1 * p.n2;
   const long long ncell = (long long)p.n0 * n12;
   const long long cell = (long long)i0 * n12 + (i1 * p.n2 + i2);
+  bool active = valid;
   {
     const int ix = (DIM == 2) ? i1 : i0;
-    if (p.band == 1 && ix >= band_lo && ix < band_hi && (DIM == 2 || (unsigned)(i1 - worg[1]) < (unsigned)p.wsz[1])) active = false;
+    const bool in_band = ix >= band_lo && ix < band_hi &&
+                         (DIM == 2 ? (j >= jb_lo && j <= jb_hi) : ((unsigned)(i1 - worg[1]) < (unsigned)p.wsz[1]));
+    if (p.band == 1 && in_band) active = false;
+    if (box2 && !in_band) active = false;             // padding groups of the enumeration
     // wall layers owned by the fused wall kernel (at most two)
     if (p.n_skip > 0 && (p.skip_axis[0] ? i1 : i0) == p.skip_layer[0]) active = false;
     if (p.n_skip > 1 && (p.skip_axis[1] ? i1 : i0) == p.skip_layer[1]) active = false;
@@ -111,6 +123,9 @@ __global__ void __launch_bounds__(step_max_threads<DIM, COLL>(), step_min_ctas<D
   // read (and L2-prefetch) the same few cache lines, which serialises in one L2 slice (measured: +45 % on the bulk
   // launch of the 256^3 sphere case).
   if (__all_sync(0xffffffffu, !active)) return;
+  // In 3-D (and for whole rows in 2-D) activity is uniform along a row, so an inactive lane never feeds an active
+  // one.  The 2-D window box cuts rows: there an inactive lane next to an active one must still hold its real cells.
+  const bool loads = (DIM == 2) ? valid : active;
 
   float f[VEC][Q];
   if (p.do_stream) {
@@ -125,7 +140,7 @@ __global__ void __launch_bounds__(step_max_threads<DIM, COLL>(), step_min_ctas<D
       d0[2] = (i0 == p.n0 - 1 ? 1 - p.n0 : 1) * n12;
     }
     const float* __restrict__ own = p.fin + cell;
-    if (!active) {   // idle lanes still take part in the shuffles: they all read the first cells of each plane (cached)
+    if (!loads) {   // idle lanes still take part in the shuffles: they all read the first cells of each plane (cached)
       own = p.fin;
 #pragma unroll
       for (int k = 0; k < 3; ++k) { d0[k] = 0; d1[k] = 0; }
@@ -138,7 +153,7 @@ __global__ void __launch_bounds__(step_max_threads<DIM, COLL>(), step_min_ctas<D
       // The block that will follow this one on the SM is about one resident grid ahead; its cells lie (nearly always)
       // at the same relative offsets.  Asking L2 for them now turns its DRAM latency into L2 latency.
       const unsigned ahead = (unsigned)p.prefetch_blocks * blockDim.x;
-      if (gid + ahead < total) {
+      if (active && gid + ahead < total) {
         const float* __restrict__ nxt = own + (long long)ahead * VEC;
         static_for<Q>([&](auto qc) {
           constexpr int q = decltype(qc)::value;
@@ -151,14 +166,15 @@ __global__ void __launch_bounds__(step_max_threads<DIM, COLL>(), step_min_ctas<D
         constexpr int q = decltype(qc)::value;
         constexpr int c2 = L::c(q, 2);
         const int sh = (c2 > 0) ? (i2 == 0 ? p.n2 - 1 : -1) : ((c2 < 0) ? (i2 == p.n2 - 1 ? 1 - p.n2 : 1) : 0);
-        f[0][q] = __ldg(source(qc) + (active ? sh : 0));
+        f[0][q] = __ldg(source(qc) + (loads ? sh : 0));
       });
     } else {
       // all aligned vector loads first (one predicated block), then the one-element shifts of the populations that
       // move along the contiguous axis
       float v[Q][VEC];
       static_for<Q>([&](auto qc) { load_vec<VEC>(source(qc), v[decltype(qc)::value]); });
-      const bool first = active && (lane == 0 || j == 0), last = active && (lane == 31 || j == nv - 1);
+      // the neighbouring lane holds the neighbouring cells only inside one enumerated row
+      const bool first = active && (lane == 0 || jr == 0), last = active && (lane == 31 || jr == nvr - 1 || j == nv - 1);
       static_for<Q>([&](auto qc) {
         constexpr int q = decltype(qc)::value;
         constexpr int c2 = L::c(q, 2);
@@ -635,12 +651,15 @@ int step_impl(const VsbStepArgs& a, cudaStream_t s) {
   const int nrow = p.edge_rows ? 2 : ((p.band == 2) ? std::min(p.wsz[0], p.s_end - p.s_begin) : p.s_end - p.s_begin);
   const bool box = DIM == 3 && p.band == 2;            // 3-D band 2: only the window's y-range of every x plane
   const long long rows = (DIM == 2) ? (long long)nrow : (long long)nrow * (box ? p.wsz[1] : p.n1);
-  const long long total = rows * (p.n2 / vec);
+  const bool box2 = DIM == 2 && p.band == 2;           // 2-D band 2: only the vector groups over the window's y-range
+  p.nvb = std::min(p.n2 / vec, p.wsz[1] / vec + 2);    // any alignment of a window of wsz[1] cells touches <= this many
+  const long long total = rows * (box2 ? p.nvb : p.n2 / vec);
   VSB_REQUIRE(total < (1ll << 31) && (long long)p.n0 * p.n1 * p.n2 < (1ll << 31),
               "vsb_step: more than 2^31 cells in one launch; split the rows (sub_begin / sub_end)");
   p.div_nv = make_fast_div((unsigned)(p.n2 / vec));
   p.div_n1 = make_fast_div((unsigned)p.n1);
   p.div_w1 = make_fast_div((unsigned)std::max(p.wsz[1], 1));
+  p.div_nvb = make_fast_div((unsigned)std::max(p.nvb, 1));
   // Block size: for grids of only a few waves (e.g. 1024^2 = 1.73 waves of 256-thread blocks) the partly filled last
   // wave costs up to a whole wave; choose the multiple of 32 in [128, 256] that fills the last wave best.
   auto launch = [&](auto kernel) {
@@ -673,7 +692,7 @@ int step_impl(const VsbStepArgs& a, cudaStream_t s) {
       // lattices, scripts/prefetch_sweep.py; beyond ~2x that the lines are evicted again before use)
       static const double pf_bytes = [] { const char* e = getenv("VSB_PREFETCH_KB"); return (e ? atof(e) : 5632.0) * 1024.0; }();
       const double block_bytes = (double)best_bs * vec * Lat<DIM>::Q * 4.0;
-      p.prefetch_blocks = (pf_bytes > 0 && !box) ? std::max(1, (int)(pf_bytes / block_bytes + 0.5)) : 0;   // (box rows are not contiguous)
+      p.prefetch_blocks = (pf_bytes > 0 && !box && !box2) ? std::max(1, (int)(pf_bytes / block_bytes + 0.5)) : 0;   // (box rows are not contiguous)
     }
     unsigned extra = 0;
     for (int e = 0; e < p.n_wall; ++e) {

@@ -59,8 +59,8 @@ template <int DIM> struct StepParams {
   const VsbBodyState* body;
   int parity;
   const uint8_t* mask;
-  int band;             // 0 all rows, 1 skip the window's band, 2 only the band.  Band = the window's x-range
-                        // (2-D) or its (x, y) footprint over all z (3-D)
+  int band;             // 0 all rows, 1 skip the window's band, 2 only the band.  Band = the window's box, rounded out
+                        // to whole vector groups along y (2-D), or its (x, y) footprint over all z (3-D)
   int n_skip;           // wall layers (normal to a non-contiguous axis) left to the fused wall kernel
   int skip_axis[2], skip_layer[2];
   int n_wall;           // face operations executed by the blocks appended to this launch (edges = 2)
@@ -68,6 +68,8 @@ template <int DIM> struct StepParams {
   WallOpDev wall[2];
   FastDiv div_nv, div_n1;   // thread index -> (row, vector column), row -> (i0, i1)
   FastDiv div_w1;           // 3-D band 2: row -> (x plane of the window, y line of the window)
+  FastDiv div_nvb;          // 2-D band 2: thread index -> (row, vector group of the window's y-range)
+  int nvb;                  // 2-D band 2: vector groups enumerated per row
   int prefetch_blocks;      // > 0: pull the lines of the block that many blocks ahead into L2
 };
 
