@@ -241,6 +241,11 @@ typedef struct {
                       markers whose 4 x 4 stencil can overlap that of marker m under any rigid motion of the body (m
                       itself included), padded with 0xffff; nbr_stride a multiple of 4, <= 48.  NULL: no cluster kernel */
   int nbr_stride;
+  const int32_t* reach_cells;      /* optional: ascending flat window indices of the cells a marker stencil can EVER reach
+                      (window following the body: the stencils at rest plus one cell of drift either way).  The call then
+                      clears only those cells of g_win_next / scratch_next -- for a finely meshed surface that is a thin
+                      shell of the window (BASELINE config 5: 1 / 8 of it).  NULL: the whole window */
+  int64_t n_reach_cells;
 } VsbMdfArgs;
 
 /* ---- fused time step ------------------------------------------------------------------- *
@@ -306,6 +311,10 @@ int vsb_edge_fused(const VsbStepArgs* args, vsb_stream_t stream);
  * do_stream, win_origin / body + parity, win_size and the mask of `args`.  The window must not contain cells of a
  * face that carries a boundary operation. */
 int vsb_ib_window_moments(const VsbStepArgs* args, float* u_win, vsb_stream_t stream);
+/* The same on a list of window cells only (VsbMdfArgs.reach_cells): the other cells of u_win are left untouched and are
+ * never multiplied by a non-zero stencil weight. */
+int vsb_ib_window_moments_cells(const VsbStepArgs* args, float* u_win, const int32_t* cells, int64_t n_cells,
+                                vsb_stream_t stream);
 
 /* Body update on the device: h = -force_sum + a*added_mass; (a,v,d) <- newmark(a,v,d,h,m,k,c); force_sum <- 0;
  * origin2[parity ^ 1] <- window origin for the next step.  `parity` is the parity of the step being completed. */

@@ -110,3 +110,44 @@ def test_d3q19_mrt_in_moment_space_equals_the_reference_operator(golden):
         assert lib.mm_make(P(A), P(A), P(s)) == 0                      # source operator is not I - A/2
         cons = (A + 0.1 * np.eye(19, dtype=np.float32)).astype(np.float32)
         assert lib.mm_make(P(cons), None, P(s)) == 0                   # conserved moments relaxed
+
+
+def test_reachable_window_cells_cover_every_stencil_of_a_following_window():
+    """The cell list that lets the dense-body path skip most of the IB window: for any displacement of the body, with
+    the window origin following it by floor() (examples/3d/oscillating_cylinder.py:241-243) or truncation
+    (examples/2d/vortex_induced_vibration.py:104-105), every node of every marker's 4-point stencil is on the list."""
+    from vivsim_b200.stepper import reachable_window_cells
+    rng = np.random.default_rng(1)
+    spec, _ = configs.oscillating_cylinder_3d(nx=128, ny=64, nz=64)
+    markers = np.asarray(spec["ib"]["markers"], dtype=np.float32)
+    origin, size = spec["ib"]["window"]
+    cells = reachable_window_cells(markers, origin, size)
+    assert cells.dtype == np.int32 and (np.diff(cells) > 0).all()
+    assert cells.size < 0.6 * np.prod(size)                           # a shell, not the whole window
+    listed = np.zeros(int(np.prod(size)), dtype=bool)
+    listed[cells] = True
+    for _ in range(20):
+        d = rng.uniform(-3.0, 3.0, size=3).astype(np.float32)
+        org = np.floor(np.asarray(origin, dtype=np.float32) + d).astype(np.int64)
+        base = np.floor(markers + d - org.astype(np.float32)).astype(np.int64)
+        for jx in range(-1, 3):
+            for jy in range(-1, 3):
+                for jz in range(-1, 3):
+                    n = base + np.array([jx, jy, jz])
+                    inside = ((n >= 0) & (n < np.asarray(size))).all(axis=1)
+                    flat = (n[:, 0] * size[1] + n[:, 1]) * size[2] + n[:, 2]
+                    assert listed[flat[inside]].all()
+    # 2-D, truncation rule
+    spec2, _ = configs.viv_cylinder_2d(nx=256, ny=128, n_marker=400, radius=20.0)
+    m2 = np.asarray(spec2["ib"]["markers"], dtype=np.float32)
+    (ox, oy), (sx, sy) = spec2["ib"]["window"]
+    c2 = reachable_window_cells(m2, (ox, oy), (sx, sy))
+    l2 = np.zeros(sx * sy, dtype=bool); l2[c2] = True
+    for _ in range(20):
+        d = rng.uniform(0.0, 2.0, size=2).astype(np.float32)
+        org = (np.asarray((ox, oy), dtype=np.float32) + d).astype(np.int64)
+        base = np.floor(m2 + d - org.astype(np.float32)).astype(np.int64)
+        for jx in range(-1, 3):
+            for jy in range(-1, 3):
+                n = base + np.array([jx, jy])
+                assert l2[n[:, 0] * sy + n[:, 1]].all()

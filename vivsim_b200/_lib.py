@@ -33,7 +33,7 @@ EXPORTS = [
     "vsb_body_newmark", "vsb_edge_fused", "vsb_edge_fused_supported", "vsb_ib_fused", "vsb_ib_fused_supported",
     "vsb_halo_push", "vsb_body_newmark_host", "vsb_halo_send", "vsb_halo_wait", "vsb_step_host_ode",
     "vsb_post_field", "vsb_post_mean", "vsb_mg_fine_to_coarse", "vsb_mg_coarse_to_fine", "vsb_run_host_ode",
-    "vsb_run_host_ode_multi", "vsb_ibshard_chain", "vsb_ibshard_barrier", "vsb_enqueue_host_ode", "vsb_sync_status",
+    "vsb_run_host_ode_multi", "vsb_ibshard_chain", "vsb_ibshard_barrier", "vsb_enqueue_host_ode", "vsb_sync_status", "vsb_ib_window_moments_cells",
 ]
 
 
@@ -82,7 +82,8 @@ class VsbMdfArgs(C.Structure):
                 ("marker_force", C.c_void_p), ("body", C.c_void_p), ("barrier", C.c_void_p),
                 ("host_mail", C.c_void_p), ("mail_seq", C.c_int), ("chunk_offsets", C.c_void_p), ("n_chunks", C.c_int),
                 ("rotation", C.c_int), ("center", C.c_float * 2), ("chain_mode", C.c_int),
-                ("nbr_list", C.c_void_p), ("nbr_stride", C.c_int)]
+                ("nbr_list", C.c_void_p), ("nbr_stride", C.c_int), ("reach_cells", C.c_void_p),
+                ("n_reach_cells", C.c_int64)]
 
 
 class VsbStepArgs(C.Structure):

@@ -558,6 +558,11 @@ static int mdf_impl(const VsbStepArgs& sa, const VsbMdfArgs& a, const VsbBodyPar
   p.mail_seq = a.mail_seq;
   p.chunk_offsets = nullptr;
   p.m_begin = 0; p.m_end = a.n_markers; p.chunk_begin = 0; p.clear_mode = 0;
+  if (a.reach_cells && a.n_reach_cells > 0) {   // clear only the cells a stencil can reach (the rest is never written)
+    p.clear_mode = 2;
+    p.clear_cells = a.reach_cells; p.n_clear_cells = a.n_reach_cells;
+    for (int d = 0; d < 3; ++d) { p.box_lo[d] = 0; p.box_hi[d] = d < DIM ? a.win_size[d] : 1; }
+  }
   p.nbr_list = a.nbr_list; p.nbr_stride = a.nbr_stride;
   p.rotation = (DIM == 2 && a.rotation) ? 1 : 0;
   p.center[0] = a.center[0]; p.center[1] = a.center[1];

@@ -343,6 +343,29 @@ __global__ void k_window_moments(const StepParams<DIM> p, float* __restrict__ u_
   for (int d = 0; d < L::D; ++d) u_win[t * WinVec<DIM>::NC + d] = u[d];
 }
 
+// The same on a list of window cells (ascending flat window indices).
+template <int DIM>
+__global__ void k_window_moments_cells(const StepParams<DIM> p, float* __restrict__ u_win, const int* __restrict__ cells,
+                                       const long long n_cells) {
+  using L = Lat<DIM>;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_cells) return;
+  int org[3];
+  window_origin<DIM>(p, org);
+  const int flat = __ldg(cells + t);
+  int rel[3] = {0, 0, 0}, r = flat;
+#pragma unroll
+  for (int d = L::D - 1; d >= 0; --d) { rel[d] = r % p.wsz[d]; r /= p.wsz[d]; }
+  int c[3] = {0, 0, 0};
+#pragma unroll
+  for (int d = 0; d < L::D; ++d) c[d + L::A0] = org[d] + rel[d];
+  float f[L::Q], rho, u[L::D];
+  pull_cell<DIM>(p, c[0], c[1], c[2], f, true);
+  moments<DIM>(f, rho, u);
+#pragma unroll
+  for (int d = 0; d < L::D; ++d) u_win[(long long)flat * WinVec<DIM>::NC + d] = u[d];
+}
+
 // One wall cell: pull, face operation, (mask), collide, store.  Face operations handled this way are independent of
 // each other (see vsb_edge_fused_supported), so no ordering between them is needed.
 template <int DIM, int COLL, int LOC>
@@ -806,7 +829,7 @@ static int step_dispatch(const VsbStepArgs& a, cudaStream_t s, int what, int* su
 }
 
 template <int DIM>
-static int window_impl(const VsbStepArgs& a, float* u_win, cudaStream_t s) {
+static int window_impl(const VsbStepArgs& a, float* u_win, cudaStream_t s, const int32_t* cells = nullptr, long long n_cells = 0) {
   StepParams<DIM> p;
   VsbStepArgs b = a;
   if (!b.f_out) b.f_out = u_win;  // unused by this kernel; only has to differ from f_in
@@ -817,7 +840,12 @@ static int window_impl(const VsbStepArgs& a, float* u_win, cudaStream_t s) {
     VSB_REQUIRE(a.win_size[d] > 0, "vsb_ib_window_moments: empty window");
     wcells *= a.win_size[d];
   }
-  k_window_moments<DIM><<<blocks_for(wcells, 128), 128, 0, s>>>(p, u_win);
+  if (cells) {
+    VSB_REQUIRE(n_cells >= 0 && n_cells <= wcells, "vsb_ib_window_moments_cells: %lld cells listed, the window has %lld", n_cells, wcells);
+    if (n_cells > 0) k_window_moments_cells<DIM><<<blocks_for(n_cells, 128), 128, 0, s>>>(p, u_win, cells, n_cells);
+  } else {
+    k_window_moments<DIM><<<blocks_for(wcells, 128), 128, 0, s>>>(p, u_win);
+  }
   VSB_LAUNCH_CHECK("vsb_ib_window_moments");
   return VSB_OK;
 }
@@ -861,6 +889,13 @@ int vsb_ib_window_moments(const VsbStepArgs* args, float* u_win, vsb_stream_t st
   VSB_REQUIRE(args && u_win, "vsb_ib_window_moments: null argument");
   VSB_REQUIRE(args->grid.dim == 2 || args->grid.dim == 3, "dim must be 2 or 3, got %d", args->grid.dim);
   return args->grid.dim == 2 ? window_impl<2>(*args, u_win, (cudaStream_t)stream) : window_impl<3>(*args, u_win, (cudaStream_t)stream);
+}
+
+int vsb_ib_window_moments_cells(const VsbStepArgs* args, float* u_win, const int32_t* cells, int64_t n_cells, vsb_stream_t stream) {
+  VSB_REQUIRE(args && u_win && cells, "vsb_ib_window_moments_cells: null argument");
+  VSB_REQUIRE(args->grid.dim == 2 || args->grid.dim == 3, "dim must be 2 or 3, got %d", args->grid.dim);
+  return args->grid.dim == 2 ? window_impl<2>(*args, u_win, (cudaStream_t)stream, cells, n_cells)
+                             : window_impl<3>(*args, u_win, (cudaStream_t)stream, cells, n_cells);
 }
 
 }  // extern "C"

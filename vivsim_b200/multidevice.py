@@ -274,22 +274,8 @@ def plan_ib_shards(markers, window, world, dense, moving_in_window=False, margin
     if moving_in_window or n == 0:
         cells = np.arange(int(np.prod(size)), dtype=np.int32)
     else:
-        vol = np.zeros(tuple(int(k) for k in size), dtype=bool)
-        base = np.floor(markers.astype(np.float64) - origin).astype(np.int64)
-        base = np.clip(base, 0, size - 1)
-        vol[tuple(base[:, d] for d in range(dim))] = True
-        for ax in range(dim):
-            acc = np.zeros_like(vol)
-            for sft in range(-2, 4):
-                src = [slice(None)] * dim
-                dst = [slice(None)] * dim
-                if sft >= 0:
-                    src[ax], dst[ax] = slice(0, vol.shape[ax] - sft), slice(sft, vol.shape[ax])
-                else:
-                    src[ax], dst[ax] = slice(-sft, vol.shape[ax]), slice(0, vol.shape[ax] + sft)
-                acc[tuple(dst)] |= vol[tuple(src)]
-            vol = acc
-        cells = np.flatnonzero(vol).astype(np.int32)
+        from .stepper import reachable_window_cells
+        cells = reachable_window_cells(markers, origin, size)
     return dict(perm=perm, marker_ranges=np.asarray(marker_ranges, dtype=np.int64), cells=cells,
                 chunk_offsets=np.asarray(offsets, dtype=np.int32) if dense else None,
                 chunk_ranges=np.asarray(chunk_ranges, dtype=np.int64), need_lo=need_lo, need_hi=need_hi, axis=axis)

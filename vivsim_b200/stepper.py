@@ -45,6 +45,34 @@ TILE_CELLS = 2304         # cells of its shared-memory box (kTileCells)
 TILE_COLUMN = 4           # markers of one chunk share a TILE_COLUMN x TILE_COLUMN column of cells in (x, y)
 
 
+def reachable_window_cells(markers, window_origin, window_size):
+    """Ascending flat indices (int32) of the IB-window cells a 4-point stencil of some marker can ever touch while the
+    window follows the body: the stencil nodes base - 1 .. base + 2 of every marker at rest, with the base allowed to
+    drift by one cell either way (the window origin is an integer, the body's displacement is not).  Host logic,
+    NumPy only.  For a finely meshed surface this is a thin shell of the window -- the only cells whose velocity has to
+    be computed and whose force / work fields are ever written."""
+    markers = np.asarray(markers, dtype=np.float64)
+    dim = markers.shape[1]
+    origin = np.floor(np.asarray(window_origin, dtype=np.float64)[:dim]).astype(np.int64)
+    size = np.asarray(window_size, dtype=np.int64)[:dim]
+    vol = np.zeros(tuple(int(k) for k in size), dtype=bool)
+    if markers.shape[0]:
+        base = np.clip(np.floor(markers - origin).astype(np.int64), 0, size - 1)
+        vol[tuple(base[:, d] for d in range(dim))] = True
+    for ax in range(dim):
+        acc = np.zeros_like(vol)
+        for sft in range(-2, 4):
+            src = [slice(None)] * dim
+            dst = [slice(None)] * dim
+            if sft >= 0:
+                src[ax], dst[ax] = slice(0, vol.shape[ax] - sft), slice(sft, vol.shape[ax])
+            else:
+                src[ax], dst[ax] = slice(-sft, vol.shape[ax]), slice(0, vol.shape[ax] + sft)
+            acc[tuple(dst)] |= vol[tuple(src)]
+        vol = acc
+    return np.flatnonzero(vol).astype(np.int32)
+
+
 def cut_marker_chunks(markers):
     """Storage order and chunk boundaries of a dense 3-D marker set for the tiled MDF kernel (host logic, NumPy only).
 
@@ -357,6 +385,15 @@ class Stepper:
                     nbr[:js.size, i] = js
                 self._nbr = torch.as_tensor(nbr.view(np.int16), device=dev)
                 m.nbr_list, m.nbr_stride = self._nbr.data_ptr(), stride
+        # Dense body in a window that follows it: only a thin shell of the window is ever within reach of a stencil.
+        # Its cell list lets the window-velocity kernel and the per-step clearing skip the rest (C5: 7.1 M -> 0.9 M cells).
+        self._reach = None
+        rigid_in_window = body is None or (int(follow) in (1, 2) and not bool(body.get("rotation", False)))
+        if self._use_uwin and self._shard is None and rigid_in_window and ib.get("reach_list", True):
+            cells = reachable_window_cells(markers, self.win_origin0, self.win_size)
+            if cells.size < 0.5 * wcells:
+                self._reach = torch.as_tensor(cells, device=dev)
+                m.reach_cells, m.n_reach_cells = self._reach.data_ptr(), int(cells.size)
         m.chain_mode = L.CHAIN[chain]
         self._mdf_one_launch = ((self.n_markers * lanes + 127) // 128 <= 120 and self._ib_chain != "launches"
                                 and self._shard is None)
@@ -832,7 +869,11 @@ class Stepper:
         else:
             m.u_win = None
             if self._use_uwin:
-                L.check(lib.vsb_ib_window_moments(C.byref(a), L.ptr(self._u_win), st))
+                if self._reach is not None:
+                    L.check(lib.vsb_ib_window_moments_cells(C.byref(a), L.ptr(self._u_win), L.ptr(self._reach),
+                                                            C.c_int64(self._reach.numel()), st))
+                else:
+                    L.check(lib.vsb_ib_window_moments(C.byref(a), L.ptr(self._u_win), st))
                 m.u_win = self._u_win.data_ptr()
             L.check(lib.vsb_ib_mdf(C.byref(a), C.byref(m), bp, st))
         if self.body is not None and self.dyn_mode == "host":
