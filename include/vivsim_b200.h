@@ -137,6 +137,15 @@ int vsb_ib_interpolate(int n_comp, int64_t n_cells, const float* grid, int64_t n
 /* spread: ib/stencil.py:81-110.  grid (C, n_cells) += scatter of values (M, C); atomics. */
 int vsb_ib_spread(int n_comp, int64_t n_cells, float* grid, int64_t n_markers, int n_stencil,
                   const float* values, const float* weights, const int32_t* indices, vsb_stream_t stream);
+/* The same scatter-add with a DETERMINISTIC summation order: every cell receives its contributions in the order of
+ * the flattened (marker, stencil point) index, products and sums rounded separately -- reproducible run to run and
+ * bit-identical to a sequential scatter (NumPy add.at, XLA's CPU scatter).  One stable radix sort of the M * NS cell
+ * indices, then one thread per run of equal indices.  `workspace`: device memory of at least
+ * vsb_ib_spread_ordered_workspace(n_markers, n_stencil) bytes (a host-side size query; < 0: too many entries). */
+int64_t vsb_ib_spread_ordered_workspace(int64_t n_markers, int n_stencil);
+int vsb_ib_spread_ordered(int n_comp, int64_t n_cells, float* grid, int64_t n_markers, int n_stencil, const float* values,
+                          const float* weights, const int32_t* indices, void* workspace, int64_t workspace_bytes,
+                          vsb_stream_t stream);
 
 /* ---- rigid body state (device resident) ------------------------------------------------ *
  * The IB window follows a moving body.  Its integer origin for the step with parity p (0/1, alternating every

@@ -23,7 +23,7 @@ def lib():
 
 def declared_symbols():
     src = open(HEADER).read()
-    return sorted(set(re.findall(r"^(?:int|const char\*)\s+(vsb_\w+)\s*\(", src, flags=re.M)))
+    return sorted(set(re.findall(r"^(?:int|int64_t|const char\*)\s+(vsb_\w+)\s*\(", src, flags=re.M)))
 
 
 def test_header_symbols_exported(lib):

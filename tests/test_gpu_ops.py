@@ -155,3 +155,44 @@ def test_empty_inputs():
     r, u = lbm.get_macroscopic(torch.zeros((9, 0), device="cuda"))
     assert r.shape == (0,) and u.shape == (2, 0)
     assert lbm.get_equilibrium(torch.zeros((0,), device="cuda"), torch.zeros((2, 0), device="cuda")).shape == (9, 0)
+
+
+def test_ordered_spread_is_bit_exact_and_reproducible(golden):
+    """vsb_ib_spread_ordered: contributions reach every cell in flattened (marker, stencil point) order,
+    products and sums rounded separately -- bit-identical to the sequential scatter of the oracle (np.add.at,
+    ib/stencil.py:104-110), and the same bits on every run; the atomic spread agrees to rounding only."""
+    from vivsim_b200 import ib, ib3d
+    import oracle.ib
+    g = golden["ib"]
+    # reference fixtures: 2-D and 3-D
+    mx, my, u = T(g["mx"]), T(g["my"]), T(g["u2"])
+    w, idx = ib.get_ib_stencil(mx, my, int(g["shape2"][1]))
+    got = N(ib.spread(T(g["vals2"]), u, w, idx, ordered=True))
+    assert_bitexact(got, oracle.ib.spread(g["vals2"], g["u2"], N(w), N(idx)), "ordered spread vs oracle (2-D fixture)")
+    assert_close(got, g["spread2"], what="ordered spread vs reference fixture")
+    verts, u3 = T(g["verts"]), T(g["u3"])
+    w3, idx3 = ib3d.get_ib_stencil(verts, tuple(int(x) for x in g["shape3"]))
+    got3 = N(ib3d.spread(T(g["vals3"]), u3, w3, idx3, ordered=True))
+    assert_bitexact(got3, oracle.ib.spread(g["vals3"], g["u3"], N(w3), N(idx3)), "ordered spread vs oracle (3-D fixture)")
+    # many markers on few cells (long runs of equal indices), negative and out-of-range indices, three components
+    rng = np.random.default_rng(11)
+    n_m, ns, ncell = 3000, 16, 40 * 25
+    vals = rng.standard_normal((n_m, 3)).astype(np.float32)
+    wts = rng.random((n_m, ns)).astype(np.float32)
+    index = rng.integers(0, ncell, size=(n_m, ns)).astype(np.int32)
+    grid = rng.standard_normal((3, 40, 25)).astype(np.float32)
+    want = oracle.ib.spread(vals, grid, wts, index)
+    runs = [N(ib.spread(T(vals), T(grid), T(wts), T(index), ordered=True)) for _ in range(3)]
+    assert_bitexact(runs[0], want, "ordered spread vs oracle (dense duplicates)")
+    assert_bitexact(runs[1], runs[0], "run to run"); assert_bitexact(runs[2], runs[0], "run to run")
+    assert_close(N(ib.spread(T(vals), T(grid), T(wts), T(index))), want, what="atomic spread")
+    index2 = index.copy()
+    index2[::7, 0] = -1            # wraps once to the last cell
+    index2[::11, 1] = ncell + 5    # dropped
+    a = N(ib.spread(T(vals), T(grid), T(wts), T(index2), ordered=True))
+    b = N(ib.spread(T(vals), T(grid), T(wts), T(index2)))
+    assert_close(a, b, what="ordered vs atomic with wrapped / dropped indices")
+    # empty marker set
+    e = ib.spread(torch.zeros((0, 3), device="cuda"), T(grid), torch.zeros((0, ns), device="cuda"),
+                  torch.zeros((0, ns), dtype=torch.int32, device="cuda"), ordered=True)
+    assert_bitexact(N(e), grid, "no markers")

@@ -33,7 +33,7 @@ EXPORTS = [
     "vsb_body_newmark", "vsb_edge_fused", "vsb_edge_fused_supported", "vsb_ib_fused", "vsb_ib_fused_supported",
     "vsb_halo_push", "vsb_body_newmark_host", "vsb_halo_send", "vsb_halo_wait", "vsb_step_host_ode",
     "vsb_post_field", "vsb_post_mean", "vsb_mg_fine_to_coarse", "vsb_mg_coarse_to_fine", "vsb_run_host_ode",
-    "vsb_run_host_ode_multi", "vsb_ibshard_chain", "vsb_ibshard_barrier", "vsb_enqueue_host_ode", "vsb_sync_status", "vsb_ib_window_moments_cells",
+    "vsb_run_host_ode_multi", "vsb_ibshard_chain", "vsb_ibshard_barrier", "vsb_enqueue_host_ode", "vsb_sync_status", "vsb_ib_window_moments_cells", "vsb_ib_spread_ordered", "vsb_ib_spread_ordered_workspace",
 ]
 
 

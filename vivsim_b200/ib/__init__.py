@@ -69,14 +69,27 @@ def interpolate(grid_values, stencil_weights, stencil_indices):
     return out
 
 
-def spread(marker_values, grid_values, stencil_weights, stencil_indices):
-    """Scatter-add marker values onto a copy of grid_values   (ib/stencil.py:81-110)."""
+def spread(marker_values, grid_values, stencil_weights, stencil_indices, ordered=False):
+    """Scatter-add marker values onto a copy of grid_values   (ib/stencil.py:81-110).
+    ordered=True: deterministic summation order (flattened (marker, stencil point) order per cell, as a sequential
+    scatter applies it): reproducible run to run and bit-identical to the CPU oracle; ordered=False: fp32 atomics."""
     v = L.dev(marker_values, name="marker_values")
     g = L.dev(grid_values, name="grid_values").clone()
     w = L.dev(stencil_weights, name="stencil_weights")
     idx = L.dev(stencil_indices, torch.int32, name="stencil_indices")
     if v.shape != (w.shape[0], g.shape[0]):
         raise ValueError(f"marker_values must have shape ({w.shape[0]}, {g.shape[0]}), got {tuple(v.shape)}")
+    if ordered:
+        lib = L.lib()
+        lib.vsb_ib_spread_ordered_workspace.restype = C.c_int64
+        need = int(lib.vsb_ib_spread_ordered_workspace(C.c_int64(w.shape[0]), int(w.shape[1])))
+        if need < 0:
+            raise ValueError("ordered spread: more than 2^31 stencil entries")
+        ws = torch.empty(max(need, 1), dtype=torch.uint8, device=g.device)
+        L.check(lib.vsb_ib_spread_ordered(int(g.shape[0]), C.c_int64(g[0].numel()), L.ptr(g), C.c_int64(w.shape[0]),
+                                          int(w.shape[1]), L.ptr(v), L.ptr(w), L.ptr(idx), L.ptr(ws), C.c_int64(need),
+                                          L.stream()))
+        return g
     L.check(L.lib().vsb_ib_spread(int(g.shape[0]), C.c_int64(g[0].numel()), L.ptr(g), C.c_int64(w.shape[0]),
                                   int(w.shape[1]), L.ptr(v), L.ptr(w), L.ptr(idx), L.stream()))
     return g
