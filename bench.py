@@ -415,9 +415,15 @@ def run_ours(args):
             steppers.append(st)
         multi = {"decomposition": f"{world} slabs of {nxl} x {spec['shape'][1]} along x per ensemble member",
                  "exchange": ("peer-mapped symmetric memory over NVLink, inside the step's CUDA graph, no NCCL on the data "
+                              "path: interior rows start at once; on a second stream ONE launch of the fused kernel waits "
+                              "for the neighbours' flag words, updates the two edge rows, stores the 3 crossing "
+                              "populations (4 KB each per side) into the neighbours' ghost rows from its epilogue and "
+                              "publishes the step (VsbStepArgs.halo)" if steppers[0].stepper.halo_fused else
+                              "peer-mapped symmetric memory over NVLink, inside the step's CUDA graph, no NCCL on the data "
                               "path: interior rows start at once; a second stream waits for the neighbours' flag words "
                               "(vsb_halo_wait), updates the two edge rows and stores the 3 crossing populations' edge rows "
                               "(4 KB each) into the neighbours' ghost rows (vsb_halo_send)"),
+                 "halo_fused": bool(steppers[0].stepper.halo_fused),
                  "halo_bytes_per_step_per_rank": steppers[0].slab.halo_bytes_per_step()}
     loop = GraphLoop(steppers, GRAPH_STEPS)
     loop.run(W * replays_per_step)

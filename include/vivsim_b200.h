@@ -298,6 +298,13 @@ typedef struct {
   int win_shift[3];           /* added to body->origin2[parity] by the fluid kernels: the body state of a slab-decomposed
                                  run carries GLOBAL coordinates (identical on every rank) while `grid` is the local
                                  slab with its ghost layer: win_shift[0] = 1 - x0 of the slab */
+  const struct VsbHaloArgs* halo;  /* optional, with edge_rows_only = 1 on a slab of a decomposed run: the launch itself does the
+                                 halo hand-shake that vsb_halo_wait / vsb_halo_send would do around it (halo->state must
+                                 be f_out): halo_mode bit 0 -- every CTA first waits until both neighbours have published
+                                 the current step; bit 1 -- the populations crossing a cut are ALSO stored into the
+                                 neighbours' ghost rows from the kernel's epilogue and the last CTA publishes the step.
+                                 One launch instead of three per step */
+  int halo_mode;
   int early_launch;           /* 1: the fused kernel may start while the kernel enqueued before it on `stream` is still
                                  running (programmatic dependent launch; that kernel must not produce anything this
                                  launch reads).  Used to put a body's short IB chain on the SMs FIRST and let the bulk
@@ -403,7 +410,7 @@ int vsb_run_host_ode_multi(int n_domains, VsbStepArgs* const* args, VsbMdfArgs* 
  *   my_flags (2 words)         [0] written by the left neighbour, [1] by the right neighbour
  *   left_flags / right_flags   the neighbours' flag words, peer-mapped
  *   counter (3 words, local)   step number, CTA ticket, timeout indicator (set to 1 if a neighbour never arrived) */
-typedef struct {
+typedef struct VsbHaloArgs {
   VsbGrid grid;
   const float* state;
   float* left_state;

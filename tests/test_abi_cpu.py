@@ -43,6 +43,37 @@ def test_struct_layouts_match_header(lib):
     assert ctypes.sizeof(_lib.VsbWallValue) == 16
 
 
+def test_every_ctypes_struct_matches_the_header_field_by_field(tmp_path):
+    """A C program compiled against include/vivsim_b200.h prints sizeof / offsetof of every structure and field the
+    ctypes binding declares (a field the header does not have fails the compilation): both sides must agree."""
+    import subprocess
+    from vivsim_b200 import _lib
+    structs = [v for k, v in vars(_lib).items()
+               if k.startswith("Vsb") and isinstance(v, type) and issubclass(v, ctypes.Structure)]
+    assert len(structs) >= 11
+    src = ["#include <stdio.h>", "#include <stddef.h>", '#include "vivsim_b200.h"', "int main(void) {"]
+    for st in structs:
+        src.append(f'printf("{st.__name__} %zu\\n", sizeof({st.__name__}));')
+        for name, *_ in st._fields_:
+            src.append(f'printf("{st.__name__}.{name} %zu\\n", offsetof({st.__name__}, {name}));')
+    src.append("return 0; }")
+    (tmp_path / "layout.c").write_text("\n".join(src))
+    exe = str(tmp_path / "layout")
+    r = subprocess.run(["gcc", "-I", os.path.dirname(HEADER), str(tmp_path / "layout.c"), "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()
+    seen = 0
+    for key, val in zip(out[::2], out[1::2]):
+        if "." in key:
+            st, field = key.split(".")
+            expect = getattr(getattr(_lib, st), field).offset
+        else:
+            expect = ctypes.sizeof(getattr(_lib, key))
+        assert int(val) == expect, f"{key}: header {val}, ctypes {expect}"
+        seen += 1
+    assert seen == sum(1 + len(st._fields_) for st in structs)
+
+
 def test_validation_errors_without_gpu(lib):
     from vivsim_b200 import _lib
     g = _lib.VsbGrid(5, 4, 4, 1)

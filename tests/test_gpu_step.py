@@ -326,10 +326,13 @@ def test_dense_marker_path_matches_sparse_path(golden):
             assert_close(N(st.get_f()), g[key], what=f"{name} dense={dense}")
 
 
+@pytest.mark.parametrize("halo", ["pipelined-local", "fused-local"])
 @pytest.mark.parametrize("dim", [2, 3])
-def test_pipelined_halo_pass_on_one_gpu(dim):
+def test_pipelined_halo_pass_on_one_gpu(dim, halo):
     """The multi-GPU pass (interior rows first; wait, the two edge rows with the x walls, send on a second stream) run
-    on one GPU with a local periodic halo: must equal the plain stepper bit for bit (no body) / to rounding (body)."""
+    on one GPU with a local periodic halo: must equal the plain stepper bit for bit (no body) / to rounding (body).
+    "fused-local": the edge-row launch waits, stores the crossing populations into the (own) ghost rows and publishes
+    the step itself (VsbStepArgs.halo), eagerly and from a CUDA graph."""
     from vivsim_b200 import Stepper, configs
     from vivsim_b200.multidevice import SlabStepper
     if dim == 2:
@@ -340,9 +343,20 @@ def test_pipelined_halo_pass_on_one_gpu(dim):
     for with_body in (False, True):
         sp = spec if with_body else dict(spec, ib=None)
         a = Stepper(sp).set_f(f0); a.step(9)
-        b = SlabStepper(sp, rank=0, world=1, halo="pipelined-local").set_f_global(f0)
-        assert b.stepper.halo_pipelined
-        b.step(9)
+        b = SlabStepper(sp, rank=0, world=1, halo=halo).set_f_global(f0)
+        assert b.stepper.halo_pipelined and b.stepper.halo_fused == (halo == "fused-local")
+        if halo == "fused-local":
+            b.step(3)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                b.advance_raw(2)
+            for _ in range(3):
+                graph.replay()
+            b.check()
+            assert int(b.peer.counter[0]) >= 8 and not b.peer.timed_out()   # one publish per collide pass
+        else:
+            b.step(9)
         if with_body:
             assert_close(N(b.gather_f()), N(a.get_f()), what="pipelined pass with body")
         else:

@@ -94,7 +94,7 @@ class VsbStepArgs(C.Structure):
                 ("win_origin", C.c_int * 3), ("win_size", C.c_int * 3), ("body", C.c_void_p), ("parity", C.c_int),
                 ("n_post", C.c_int), ("post", C.POINTER(VsbPostOp)), ("vec", C.c_int), ("band", C.c_int),
                 ("edges", C.c_int), ("sub_begin", C.c_int), ("sub_end", C.c_int), ("edge_rows_only", C.c_int),
-                ("win_shift", C.c_int * 3), ("early_launch", C.c_int)]
+                ("win_shift", C.c_int * 3), ("halo", C.c_void_p), ("halo_mode", C.c_int), ("early_launch", C.c_int)]
 
 
 MAX_RANKS = 8

@@ -40,7 +40,7 @@ __device__ __forceinline__ void store_vec(float* __restrict__ p, const float (&v
   *reinterpret_cast<T*>(p) = t;
 }
 
-template <int DIM, int COLL>
+template <int DIM, int COLL, bool HALO = false>
 __device__ __forceinline__ void edge_block(const StepParams<DIM>& p, const MrtMats<DIM, mats_kind(COLL)>& mm);
 
 // Block size and register budget per lattice and collision model, measured on B200 (scripts/tune_variants.py,
@@ -65,12 +65,23 @@ template <int DIM, int COLL> constexpr int step_min_ctas() {
 }
 template <int DIM, int COLL> constexpr int step_default_vec() { return (DIM == 3 && !is_matrix_mrt(COLL)) ? 2 : 4; }
 
-template <int DIM, int COLL, int VEC>
-__global__ void __launch_bounds__(step_max_threads<DIM, COLL>(), step_min_ctas<DIM, COLL>()) k_step(const StepParams<DIM> p, const MrtMats<DIM, mats_kind(COLL)> mm) {
+// Populations of one cell (or VEC cells) that cross the cut next to an edge row go to the neighbour's ghost row as
+// well (fused halo send, StepParams::halo): row r_begin sends its c = -1 populations to the LEFT neighbour's ghost row
+// r_end, row r_end - 1 its c = +1 populations to the RIGHT neighbour's ghost row r_begin - 1.
+template <int DIM>
+__device__ __forceinline__ bool halo_target(const StepParams<DIM>& p, int i_slow, int dir, float*& base, long long& shift) {
+  const long long rowstride = (DIM == 2) ? (long long)p.n2 : (long long)p.n1 * p.n2;
+  if (dir < 0 && i_slow == p.r_begin) { base = p.halo.left_state; shift = (long long)(p.r_end - p.r_begin) * rowstride; return true; }
+  if (dir > 0 && i_slow == p.r_end - 1) { base = p.halo.right_state; shift = -(long long)(p.r_end - p.r_begin) * rowstride; return true; }
+  return false;
+}
+
+template <int DIM, int COLL, int VEC, bool HALO>
+__device__ __forceinline__ void step_body(const StepParams<DIM>& p, const MrtMats<DIM, mats_kind(COLL)>& mm) {
   using L = Lat<DIM>;
   constexpr int Q = L::Q;
   if (blockIdx.x >= p.nb_bulk) {   // blocks appended after the bulk: wall layers of the face operations (edges = 2)
-    edge_block<DIM, COLL>(p, mm);
+    edge_block<DIM, COLL, HALO>(p, mm);
     return;
   }
   const int nv = p.n2 / VEC;
@@ -232,12 +243,66 @@ __global__ void __launch_bounds__(step_max_threads<DIM, COLL>(), step_min_ctas<D
   }
 
   if (active) {
-#pragma unroll
-    for (int q = 0; q < Q; ++q) {
+    const bool send = HALO && (p.halo.mode & 2) != 0;
+    const int i_slow = (DIM == 2) ? i1 : i0;
+    static_for<Q>([&](auto qc) {
+      constexpr int q = decltype(qc)::value;
       float v[VEC];
 #pragma unroll
       for (int k = 0; k < VEC; ++k) v[k] = f[k][q];
       store_vec<VEC>(p.fout + q * ncell + cell, v);
+      constexpr int cx = L::c(q, L::A0);
+      if constexpr (HALO && cx != 0) {
+        float* base;
+        long long shift;
+        if (send && halo_target<DIM>(p, i_slow, cx, base, shift)) store_vec<VEC>(base + q * ncell + cell + shift, v);
+      }
+    });
+  }
+}
+
+// HALO = true: the variant launched for the two edge rows of a slab with the fused hand-shake (VsbStepArgs.halo); the
+// bulk kernels carry none of that code (it cost the 3-D kernels, which sit at their 128-register limit, 16-32 bytes
+// of spills).
+template <int DIM, int COLL, int VEC, bool HALO = false>
+__global__ void __launch_bounds__(step_max_threads<DIM, COLL>(), step_min_ctas<DIM, COLL>()) k_step(const StepParams<DIM> p, const MrtMats<DIM, mats_kind(COLL)> mm) {
+  if constexpr (!HALO) {
+    step_body<DIM, COLL, VEC, false>(p, mm);
+    return;
+  }
+  if (p.halo.mode & 1) {
+    // fused halo wait: both neighbours must have published the step this rank is about to take (their sends into my
+    // ghost rows are complete, and they are done reading the buffer I am about to overwrite).  Every CTA waits itself;
+    // counter[0] only changes when the LAST CTA of this launch reaches the epilogue, i.e. after all of them are past here.
+    if (threadIdx.x == 0) {
+      const unsigned step = *reinterpret_cast<volatile unsigned*>(p.halo.counter);
+      unsigned long long t0, t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      while ((int)(p.halo.my_flags[0] - step) < 0 || (int)(p.halo.my_flags[1] - step) < 0) {
+        __nanosleep(64);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 10000000000ull) { p.halo.counter[2] = 1u; break; }   // 10 s: report, do not hang
+      }
+      __threadfence_system();
+    }
+    __syncthreads();
+  }
+  step_body<DIM, COLL, VEC, HALO>(p, mm);
+  if (p.halo.mode & 2) {
+    // fused halo send: the peer stores of this CTA are out; the last CTA to get here publishes the step
+    __threadfence_system();
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&p.halo.counter[1], 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+      __threadfence_system();
+      p.halo.counter[1] = 0;
+      const unsigned step = p.halo.counter[0] + 1;
+      p.halo.counter[0] = step;
+      p.halo.left_flags[1] = step;    // "your right neighbour has delivered step `step`"
+      p.halo.right_flags[0] = step;   // "your left neighbour has delivered step `step`"
+      __threadfence_system();
     }
   }
 }
@@ -368,7 +433,7 @@ __global__ void k_window_moments_cells(const StepParams<DIM> p, float* __restric
 
 // One wall cell: pull, face operation, (mask), collide, store.  Face operations handled this way are independent of
 // each other (see vsb_edge_fused_supported), so no ordering between them is needed.
-template <int DIM, int COLL, int LOC>
+template <int DIM, int COLL, int LOC, bool HALO = false>
 __device__ __forceinline__ void edge_cell(const StepParams<DIM>& p, const MrtMats<DIM, mats_kind(COLL)>& mm, int wall_layer,
                                           int kind, int wrap_kind, const WallVals& w, int mask_before, long long k) {
   using L = Lat<DIM>;
@@ -424,6 +489,17 @@ __device__ __forceinline__ void edge_cell(const StepParams<DIM>& p, const MrtMat
   }
 #pragma unroll
   for (int q = 0; q < Q; ++q) p.fout[q * ncell + cell] = fw[q];
+  if constexpr (HALO) {   // a wall cell on an edge row of the slab: its crossing populations travel too
+    if (p.halo.mode & 2) static_for<Q>([&](auto qc) {
+      constexpr int q = decltype(qc)::value;
+      constexpr int cx = L::c(q, L::A0);
+      if constexpr (cx != 0) {
+        float* base;
+        long long shift;
+        if (halo_target<DIM>(p, c[L::A0], cx, base, shift)) base[q * ncell + cell + shift] = fw[q];
+      }
+    });
+  }
 }
 
 // Wall layer of one face as a kernel of its own (vsb_edge_fused).
@@ -433,7 +509,7 @@ __global__ void k_edge_fused(const StepParams<DIM> p, const MrtMats<DIM, mats_ki
   edge_cell<DIM, COLL, LOC>(p, mm, wall_layer, kind, wrap_kind, w, mask_before, (long long)blockIdx.x * blockDim.x + threadIdx.x);
 }
 
-template <int DIM, int COLL>
+template <int DIM, int COLL, bool HALO>
 __device__ __forceinline__ void edge_block(const StepParams<DIM>& p, const MrtMats<DIM, mats_kind(COLL)>& mm) {
   unsigned b = blockIdx.x - p.nb_bulk;
   int e = 0;
@@ -441,14 +517,14 @@ __device__ __forceinline__ void edge_block(const StepParams<DIM>& p, const MrtMa
   const WallOpDev& op = p.wall[e];
   const long long k = (long long)b * blockDim.x + threadIdx.x;
   if constexpr (DIM == 2) {
-    if (op.loc == 0) edge_cell<2, COLL, 0>(p, mm, op.layer, op.kind, op.wrap, op.w, op.mask_before, k);
-    else edge_cell<2, COLL, 1>(p, mm, op.layer, op.kind, op.wrap, op.w, op.mask_before, k);
+    if (op.loc == 0) edge_cell<2, COLL, 0, HALO>(p, mm, op.layer, op.kind, op.wrap, op.w, op.mask_before, k);
+    else edge_cell<2, COLL, 1, HALO>(p, mm, op.layer, op.kind, op.wrap, op.w, op.mask_before, k);
   } else {
     switch (op.loc) {
-      case 0: edge_cell<3, COLL, 0>(p, mm, op.layer, op.kind, op.wrap, op.w, op.mask_before, k); break;
-      case 1: edge_cell<3, COLL, 1>(p, mm, op.layer, op.kind, op.wrap, op.w, op.mask_before, k); break;
-      case 2: edge_cell<3, COLL, 2>(p, mm, op.layer, op.kind, op.wrap, op.w, op.mask_before, k); break;
-      default: edge_cell<3, COLL, 3>(p, mm, op.layer, op.kind, op.wrap, op.w, op.mask_before, k); break;
+      case 0: edge_cell<3, COLL, 0, HALO>(p, mm, op.layer, op.kind, op.wrap, op.w, op.mask_before, k); break;
+      case 1: edge_cell<3, COLL, 1, HALO>(p, mm, op.layer, op.kind, op.wrap, op.w, op.mask_before, k); break;
+      case 2: edge_cell<3, COLL, 2, HALO>(p, mm, op.layer, op.kind, op.wrap, op.w, op.mask_before, k); break;
+      default: edge_cell<3, COLL, 3, HALO>(p, mm, op.layer, op.kind, op.wrap, op.w, op.mask_before, k); break;
     }
   }
 }
@@ -480,6 +556,21 @@ int fill_params(const VsbStepArgs& a, StepParams<DIM>& p) {
   VSB_REQUIRE(a.band >= 0 && a.band <= 2, "vsb_step: band must be 0, 1 or 2");
   VSB_REQUIRE(a.band == 0 || a.win_size[0] > 0, "vsb_step: band mode needs a force window");
   p.band = a.band;
+  p.halo = HaloDev{};
+  if (a.halo_mode) {
+    VSB_REQUIRE(a.halo_mode > 0 && a.halo_mode <= 3, "vsb_step: halo_mode must be 0..3");
+    VSB_REQUIRE(a.halo && a.edge_rows_only, "vsb_step: the fused halo hand-shake needs halo != NULL and edge_rows_only = 1");
+    const VsbHaloArgs& h = *a.halo;
+    VSB_REQUIRE(h.my_flags && h.left_flags && h.right_flags && h.counter && h.left_state && h.right_state,
+                "vsb_step: incomplete VsbHaloArgs");
+    VSB_REQUIRE(h.state == a.f_out, "vsb_step: halo->state must be the buffer this launch writes (f_out)");
+    VSB_REQUIRE(h.grid.dim == a.grid.dim && h.grid.nx == a.grid.nx && h.grid.ny == a.grid.ny &&
+                (a.grid.dim == 2 || h.grid.nz == a.grid.nz), "vsb_step: halo->grid differs from the step's grid");
+    VSB_REQUIRE(p.r_begin == 1 && p.r_end == nrows - 1, "vsb_step: the fused halo hand-shake expects one ghost layer per side");
+    p.halo.mode = a.halo_mode;
+    p.halo.my_flags = h.my_flags; p.halo.left_flags = h.left_flags; p.halo.right_flags = h.right_flags;
+    p.halo.counter = h.counter; p.halo.left_state = h.left_state; p.halo.right_state = h.right_state;
+  }
   p.n_skip = 0;
   p.prefetch_blocks = 0;
   p.n_wall = 0;
@@ -671,6 +762,7 @@ int step_impl(const VsbStepArgs& a, cudaStream_t s) {
   if (vec == 0) vec = step_default_vec<DIM, COLL>();
   while (vec > 1 && (p.n2 % vec != 0 || ((uintptr_t)a.f_in % (4 * vec)) || ((uintptr_t)a.f_out % (4 * vec)))) vec >>= 1;
   VSB_REQUIRE(vec == 1 || vec == 2 || vec == 4, "vsb_step: vec must be 0, 1, 2 or 4");
+  if (p.halo.mode) vec = 1;   // the hand-shaking edge-row launch exists in the scalar variant only (same arithmetic per cell)
   const int nrow = p.edge_rows ? 2 : ((p.band == 2) ? std::min(p.wsz[0], p.s_end - p.s_begin) : p.s_end - p.s_begin);
   const bool box = DIM == 3 && p.band == 2;            // 3-D band 2: only the window's y-range of every x plane
   const long long rows = (DIM == 2) ? (long long)nrow : (long long)nrow * (box ? p.wsz[1] : p.n1);
@@ -743,7 +835,8 @@ int step_impl(const VsbStepArgs& a, cudaStream_t s) {
       kernel<<<p.nb_bulk + extra, best_bs, 0, s>>>(p, mm);
     }
   };
-  if (vec == 4) launch(k_step<DIM, COLL, 4>);
+  if (p.halo.mode) launch(k_step<DIM, COLL, 1, true>);   // two edge rows: the scalar variant is the only one instantiated
+  else if (vec == 4) launch(k_step<DIM, COLL, 4>);
   else if (vec == 2) launch(k_step<DIM, COLL, 2>);
   else launch(k_step<DIM, COLL, 1>);
   VSB_LAUNCH_CHECK("vsb_step (fused kernel)");

@@ -43,6 +43,17 @@ struct WallOpDev {
   WallVals w;
 };
 
+// Halo hand-shake done by the edge-row launch itself (see VsbStepArgs.halo; the flag protocol is vsb_halo.cu's).
+struct HaloDev {
+  int mode;                        // bit 0: wait for the neighbours first; bit 1: send the crossing populations + publish
+  volatile unsigned* my_flags;     // [0] written by the left neighbour, [1] by the right neighbour
+  volatile unsigned* left_flags;   // left neighbour's flag words: this rank writes [1]
+  volatile unsigned* right_flags;  // right neighbour's flag words: this rank writes [0]
+  unsigned* counter;               // [0] step number, [1] CTA ticket, [2] set to 1 if a wait timed out
+  float* left_state;               // the neighbours' copies of the buffer this launch writes (f_out)
+  float* right_state;
+};
+
 template <int DIM> struct StepParams {
   int n0, n1, n2;
   int r_begin, r_end;   // physical rows of array axis A0 (the slowest real axis); ghost layers lie outside
@@ -71,6 +82,7 @@ template <int DIM> struct StepParams {
   FastDiv div_nvb;          // 2-D band 2: thread index -> (row, vector group of the window's y-range)
   int nvb;                  // 2-D band 2: vector groups enumerated per row
   int prefetch_blocks;      // > 0: pull the lines of the block that many blocks ahead into L2
+  HaloDev halo;
 };
 
 // MRT operators: collision A and Guo source B (lbm/collision/mrt.py:88, lbm/forcing/guo.py:60-75) as dense matrices

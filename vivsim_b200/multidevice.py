@@ -188,6 +188,36 @@ class LocalHalo:
         pass
 
 
+class LocalFusedHalo(LocalHalo):
+    """LocalHalo whose hand-shake runs inside the edge-row launch (VsbStepArgs.halo): the slab is its own left and
+    right neighbour, so the launch's peer stores land in its own ghost layers and its flag words are its own.  Puts
+    the fused wait / send / publish code of k_step under test on one GPU."""
+
+    def __init__(self, slab, buffers):
+        import ctypes as C
+        from . import _lib as L
+        super().__init__(slab, buffers)
+        dev = buffers[0].device
+        self.flags = torch.zeros(16, dtype=torch.int32, device=dev)
+        self.counter = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.args = []
+        for buf in buffers:
+            a = L.VsbHaloArgs()
+            a.grid = L.grid_of(slab.local_shape)
+            a.state = a.left_state = a.right_state = buf.data_ptr()
+            a.my_flags = a.left_flags = a.right_flags = self.flags.data_ptr()
+            a.counter = self.counter.data_ptr()
+            self.args.append(a)
+        self._C, self._L = C, L
+
+    def timed_out(self):
+        return bool(self.counter[2].item())
+
+    def check(self):
+        L, C = self._L, self._C
+        L.check(L.lib().vsb_sync_status(C.c_void_p(self.counter.data_ptr()), L.stream()))
+
+
 # Cost model behind the marker shares (measured on B200 with BASELINE config 5, profiles/r02_summary.md): one marker costs a
 # rank about 0.4 ns per MDF iteration; a rank whose slab holds reachable window cells also computes their velocity and
 # collides them after the chain, about 0.2 ns per cell.
@@ -413,8 +443,11 @@ class SlabStepper:
     NVLink; graph-capturable).  halo = "nccl": torch.distributed send/recv of the edge layers.  "auto": peer when the
     symmetric-memory rendezvous succeeds, else NCCL."""
 
-    def __init__(self, spec, rank=None, world=None, group=None, local_ib=None, body=None, halo="auto", ib="auto", **kw):
-        """ib: how an immersed body of the global spec is distributed -- "owner": the rank whose slab contains the IB
+    def __init__(self, spec, rank=None, world=None, group=None, local_ib=None, body=None, halo="auto", ib="auto",
+                 halo_fused=None, **kw):
+        """halo_fused: None (default: on unless VSB_HALO_FUSED=0) / False -- whether the edge-row launch of the pipelined
+        pass does the neighbour hand-shake itself (one launch) or vsb_halo_wait / vsb_halo_send run around it (three).
+        ib: how an immersed body of the global spec is distributed -- "owner": the rank whose slab contains the IB
         window (>= 2 layers from a cut) computes the whole chain; "shard": the markers are divided among all ranks and
         the window fields are shared through peer memory (a body may sit on or move across a cut; the chain of a
         large body is spread over all GPUs); "auto": "owner" when the window of a fixed body fits one slab, else
@@ -460,11 +493,11 @@ class SlabStepper:
         buffers = self.peer.buffers() if self.peer is not None else None
         self.stepper = Stepper(self.local_spec, rows=self.slab.rows, body=body if has_body else None, buffers=buffers, **kw)
         self.owns_body = has_body
-        if world == 1 and halo == "pipelined-local":   # one rank, but through the same pipelined pass as peer mode
-            self.peer = LocalHalo(self.slab, self.stepper._bufs)
-            self.halo = "pipelined-local"
+        if world == 1 and halo in ("pipelined-local", "fused-local"):   # one rank, but through the same pipelined pass as peer mode
+            self.peer = (LocalHalo if halo == "pipelined-local" else LocalFusedHalo)(self.slab, self.stepper._bufs)
+            self.halo = halo
         if self.peer is not None:
-            self.stepper.attach_halo(self.peer)     # the halo kernels become part of every pass of the stepper
+            self.stepper.attach_halo(self.peer, fused=halo_fused)   # the halo kernels become part of every pass of the stepper
         self.n_launch_per_step = self.stepper.n_launch_per_step
 
     # -- state in / out (reference convention F)

@@ -522,10 +522,12 @@ class Stepper:
             n += (self.n_iter + 3) if self._shard is not None else 0      # flag barriers, force push and reduce of the shared chain
         return n
 
-    def attach_halo(self, halo):
+    def attach_halo(self, halo, fused=None):
         """Multi-GPU slabs: `halo` (multidevice.PeerHalo) exchanges ghost layers inside every collide pass.  When all
         face operations sit on x faces (or there are none) the exchange is pipelined: interior rows start at once,
-        while a second stream waits for the neighbours, updates the two edge rows and sends them on."""
+        while a second stream waits for the neighbours, updates the two edge rows and sends them on.  fused (default:
+        on, VSB_HALO_FUSED=0 turns it off): the edge-row launch does the wait and the send itself (VsbStepArgs.halo)
+        instead of a vsb_halo_wait before and a vsb_halo_send after it."""
         self.halo = halo
         locs = [self._post[i].loc for i in range(self._args.n_post) if self._post[i].kind != L.BC["mask"]]
         x_only = all(loc in (L.LOC["left"], L.LOC["right"]) for loc in locs)
@@ -534,7 +536,10 @@ class Stepper:
             self._side = self._side_streams()
         self._halo_stream = torch.cuda.Stream(device=self.device)
         self._chain_done = torch.cuda.Event()
-        self.n_launch_per_step += 3 if self.halo_pipelined else 1
+        if fused is None:
+            fused = os.environ.get("VSB_HALO_FUSED", "1") != "0"
+        self.halo_fused = bool(fused and self.halo_pipelined and getattr(halo, "args", None) is not None)
+        self.n_launch_per_step += (1 if self.halo_fused else 3) if self.halo_pipelined else 1
 
     # ------------------------------------------------------------------ state access
     def set_f(self, f):
@@ -757,17 +762,26 @@ class Stepper:
             a.band = 0
         if pipelined:
             # second stream: neighbours' ghost layers -> the two edge rows (and the x walls) -> send them on
+            fused = self.halo_fused
+            hmode = 2                                          # the edge-row launch sends; 3: it waits first as well
             if self._shard is not None and with_ib and self.overlap:
                 s_halo.wait_event(self._chain_done)            # a window on a cut: the edge rows read its force field
             elif halo_waited:
                 s_halo.wait_stream(main)                       # chain and interior rows ran on `main`
+            elif fused:
+                hmode = 3
             else:
                 halo.wait(st_halo)
             a.band = 0
             a.sub_begin, a.sub_end, a.edge_rows_only = 0, 0, 1
+            if fused:
+                a.halo, a.halo_mode = C.addressof(halo.args[dst_index]), hmode
             L.check(lib.vsb_step(ref, st_halo))
             a.edge_rows_only = 0
-            halo.send(dst_index, st_halo)
+            if fused:
+                a.halo, a.halo_mode = None, 0
+            else:
+                halo.send(dst_index, st_halo)
             main.wait_stream(s_halo)
         elif halo is not None:
             halo.push(dst_index, st_main)
