@@ -300,17 +300,28 @@ __global__ void __launch_bounds__(kBlock, DIM == 3 ? 5 : 8) k_mdf_stage(const St
 // A finely meshed surface puts ~20 stencil points on every window cell, so ~64 global reductions per marker become
 // ~3 per marker.  Chunks whose bounding box does not fit (markers not stored in a spatially coherent order) fall back
 // to global gathers / reductions, CTA by CTA.
-constexpr int kTiledChunk = 256;      // markers per CTA = threads per CTA
-constexpr int kTileCells = 2304;      // cells of the staged box: 2304 x 16 B = 36 KB
+#ifndef VSB_TILE_CELLS
+#define VSB_TILE_CELLS 2304
+#endif
+#ifndef VSB_TILED_CTAS
+#define VSB_TILED_CTAS 3
+#endif
+constexpr int kTiledChunk = 256;                // markers per CTA = threads per CTA
+constexpr int kTileCells = VSB_TILE_CELLS;      // cells of the staged box: 2304 x 16 B = 36 KB
 
+// Per-marker records of the cell-centric pass, packed so that one visit costs 8 shared-memory loads, all but two of
+// them warp-uniform (broadcast): base and value as one 128-bit word each, the x / y weights side by side, and the z
+// weights ZERO-PADDED on both sides -- the weight of the marker for the cell dz + k of a unit is pz[3 + dz + k] for
+// any -4 < dz < 4, so the inner loop needs no predicates.
 struct TiledShared {
-  int base[kTiledChunk][3];           // first stencil node (floor(x) - 1) per axis
-  float w[kTiledChunk][12];           // delta weights: x nodes 0..3, y nodes 0..3, z nodes 0..3 (0 outside the window)
-  float val[kTiledChunk][3];          // value spread by the marker (dF, or F at the last stage)
+  int4 base[kTiledChunk];             // first stencil node (floor(x) - 1) per axis; .w unused
+  float4 val[kTiledChunk];            // value spread by the marker (dF, or F at the last stage); .w unused
+  float wxy[kTiledChunk][8];          // delta weights: x nodes 0..3, y nodes 0..3 (0 outside the window)
+  float pz[kTiledChunk][12];          // 0 0 0 | z nodes 0..3 | 0 0 0 (+ 2 words of padding)
 };
 
 template <int DIM, bool SHARD>
-__global__ void __launch_bounds__(kTiledChunk, 3) k_mdf_stage_tiled(const MdfParams p, const BodyUpdate bu, const ShardArg<SHARD> sh) {
+__global__ void __launch_bounds__(kTiledChunk, VSB_TILED_CTAS) k_mdf_stage_tiled(const MdfParams p, const BodyUpdate bu, const ShardArg<SHARD> sh) {
   static_assert(DIM == 3, "the tiled stage is instantiated for D3Q19 bodies only");
   constexpr int NC = 4;
   extern __shared__ float4 s_dyn[];
@@ -388,20 +399,23 @@ __global__ void __launch_bounds__(kTiledChunk, 3) k_mdf_stage_tiled(const MdfPar
     for (int d = 0; d < 3; ++d) {
       x[d] = p.markers0[m * 3 + d] + disp[d] - (float)org[d];
       b0[d] = (int)floorf(x[d]) - 1;
-      sm.base[tid][d] = b0[d];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int node = b0[d] + k;
         float wl = delta(p.delta_kind, (float)node - x[d]);
         if (node < 0 || node >= p.wsize[d]) wl = 0.f;     // node outside the window: the reference's stencil skips it
         wgt[d][k] = wl;
-        sm.w[tid][4 * d + k] = wl;
+        if (d < 2) sm.wxy[tid][4 * d + k] = wl;
+        else sm.pz[tid][3 + k] = wl;
       }
     }
+    sm.base[tid] = make_int4(b0[0], b0[1], b0[2], 0);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) sm.pz[tid][k] = sm.pz[tid][7 + k] = 0.f;
     float um[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
     for (int jx = 0; jx < 4; ++jx) {                                // 16 points per trip keeps the register count down
-      const float wx = sm.w[tid][jx];
+      const float wx = sm.wxy[tid][jx];
 #pragma unroll
       for (int jy = 0; jy < 4; ++jy)
 #pragma unroll
@@ -428,8 +442,8 @@ __global__ void __launch_bounds__(kTiledChunk, 3) k_mdf_stage_tiled(const MdfPar
       spread_val[c] = last ? F : dF;
       p.marker_u[m * 3 + c] = u_m;
       p.marker_force[m * 3 + c] = F;
-      sm.val[tid][c] = spread_val[c];
     }
+    sm.val[tid] = make_float4(spread_val[0], spread_val[1], spread_val[2], 0.f);
     if (!tiled) {                                     // box too large for the tile: global vector reductions
 #pragma unroll 1
       for (int jx = 0; jx < 4; ++jx)
@@ -437,7 +451,7 @@ __global__ void __launch_bounds__(kTiledChunk, 3) k_mdf_stage_tiled(const MdfPar
         for (int jy = 0; jy < 4; ++jy)
 #pragma unroll
           for (int jz = 0; jz < 4; ++jz) {
-            const float w = (wgt[2][jz] * wgt[1][jy]) * sm.w[tid][jx];
+            const float w = (wgt[2][jz] * wgt[1][jy]) * sm.wxy[tid][jx];
             if (w != 0.f) {
               const long long ci = ((long long)(b0[0] + jx) * p.wsize[1] + (b0[1] + jy)) * p.wsize[2] + (b0[2] + jz);
               const float4 val = make_float4(spread_val[0] * w, spread_val[1] * w, spread_val[2] * w, 0.f);
@@ -466,8 +480,8 @@ __global__ void __launch_bounds__(kTiledChunk, 3) k_mdf_stage_tiled(const MdfPar
   // warp own different rows of the SAME z group, so the z test is warp-uniform; when the chunk's markers are sorted by
   // z (they are, for chunks cut by the host) each unit only visits the markers whose stencil reaches its z group.
   if (tiled) {
-    const int my_bz = tid < n_here ? sm.base[tid][2] : INT_MAX;
-    const int next_bz = tid + 1 < n_here ? sm.base[tid + 1][2] : INT_MAX;
+    const int my_bz = tid < n_here ? sm.base[tid].z : INT_MAX;
+    const int next_bz = tid + 1 < n_here ? sm.base[tid + 1].z : INT_MAX;
     const bool z_sorted = __syncthreads_and(my_bz <= next_bz) != 0;
     const int zg = (ext[2] + 3) >> 2;
     const int n_rows = ext[0] * ext[1];
@@ -478,30 +492,27 @@ __global__ void __launch_bounds__(kTiledChunk, 3) k_mdf_stage_tiled(const MdfPar
       int m_lo = 0, m_hi = n_here;
       if (z_sorted) {          // markers with cz0 - 3 <= base_z <= cz0 + 3
         int a = 0, b = n_here;
-        while (a < b) { const int mid = (a + b) >> 1; if (sm.base[mid][2] < cz0 - 3) a = mid + 1; else b = mid; }
+        while (a < b) { const int mid = (a + b) >> 1; if (sm.base[mid].z < cz0 - 3) a = mid + 1; else b = mid; }
         m_lo = a;
         b = n_here;
-        while (a < b) { const int mid = (a + b) >> 1; if (sm.base[mid][2] <= cz0 + 3) a = mid + 1; else b = mid; }
+        while (a < b) { const int mid = (a + b) >> 1; if (sm.base[mid].z <= cz0 + 3) a = mid + 1; else b = mid; }
         m_hi = a;
       }
       float acc[4][3];
 #pragma unroll
       for (int k = 0; k < 4; ++k) acc[k][0] = acc[k][1] = acc[k][2] = 0.f;
       for (int mi = m_lo; mi < m_hi; ++mi) {
-        const int dz = cz0 - sm.base[mi][2];                                                         // broadcast reads
-        if (dz > -4 && dz < 4) {
-          const unsigned jx = (unsigned)(cx - sm.base[mi][0]), jy = (unsigned)(cy - sm.base[mi][1]);
-          if (jx < 4u && jy < 4u) {
-            const float wy = sm.w[mi][4 + jy], wx = sm.w[mi][jx];
-            const float v0 = sm.val[mi][0], v1 = sm.val[mi][1], v2 = sm.val[mi][2];
+        const int4 b = sm.base[mi];                                                                  // broadcast read
+        const int dz = cz0 - b.z;                                                                    // warp-uniform
+        const unsigned jx = (unsigned)(cx - b.x), jy = (unsigned)(cy - b.y);
+        if (dz > -4 && dz < 4 && jx < 4u && jy < 4u) {
+          const float wx = sm.wxy[mi][jx], wy = sm.wxy[mi][4 + jy];
+          const float4 v = sm.val[mi];
+          const float* pz = &sm.pz[mi][3 + dz];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const unsigned jz = (unsigned)(dz + k);
-              if (jz < 4u) {
-                const float w = (sm.w[mi][8 + jz] * wy) * wx;
-                acc[k][0] += v0 * w; acc[k][1] += v1 * w; acc[k][2] += v2 * w;
-              }
-            }
+          for (int k = 0; k < 4; ++k) {
+            const float w = (pz[k] * wy) * wx;                                                       // 0 outside the stencil
+            acc[k][0] += v.x * w; acc[k][1] += v.y * w; acc[k][2] += v.z * w;
           }
         }
       }

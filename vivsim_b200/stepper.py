@@ -41,8 +41,8 @@ def _parse_bc(name):
 
 
 TILE_CHUNK = 256          # markers per CTA of the tiled MDF kernel (kTiledChunk in csrc/vsb_ib.cu)
-TILE_CELLS = 2304         # cells of its shared-memory box (kTileCells)
-TILE_COLUMN = 4           # markers of one chunk share a TILE_COLUMN x TILE_COLUMN column of cells in (x, y)
+TILE_CELLS = int(os.environ.get("VSB_TILE_CELLS", "2304"))   # cells of its shared-memory box (kTileCells; tuning builds only)
+TILE_COLUMN = int(os.environ.get("VSB_TILE_COLUMN", "4"))    # markers of one chunk share a TILE_COLUMN x TILE_COLUMN column of cells in (x, y)
 
 
 def reachable_window_cells(markers, window_origin, window_size):
