@@ -76,7 +76,34 @@ def test_viv_moving_body_host_and_device(golden):
             assert_close(hist[:, 2 * k:2 * k + 2], ref[:, 2 * k:2 * k + 2], rtol=1e-4, what=f"viv {nm} ({mode})")
 
 
-@pytest.mark.parametrize("chain", ["auto", "barrier", "launches"])
+def test_ib_chain_modes_agree_and_one_cta_chain_is_reproducible():
+    """Every way of chaining the MDF iterations of a small 2-D body -- one launch per iteration, grid barriers, the
+    marker-space cluster kernel, ONE CTA with shared-memory buckets (no floating-point atomics) -- gives the oracle's
+    populations and marker forces; the one-CTA chain sums in a fixed order, so two runs agree bit for bit."""
+    from vivsim_b200 import Stepper
+    spec = recipes.cylinder2d_spec(nx=96, ny=64, n_marker=64, radius=7.5, u0=0.08, nu=0.02, n_iter=5)
+    f0 = recipes.uniform_init(spec, noise=1e-3, seed=3)
+    f_ref, h_ref = recipes.run(spec, f0, 10)
+    runs = {}
+    for chain in ("launches", "barrier", "cluster", "cta", "cta", "auto"):
+        st = Stepper(spec, ib_chain=chain).set_f(f0)
+        st.step(10)
+        f, h = N(st.get_f()), -N(st.marker_force)
+        assert_close(f, f_ref, what=f"chain {chain}: populations")
+        assert_close(h, h_ref, rtol=3e-5, what=f"chain {chain}: marker forces")
+        if chain == "cta" and "cta" in runs:
+            assert_bitexact(f, runs["cta"][0], "one-CTA chain, second run: populations")
+            assert_bitexact(h, runs["cta"][1], "one-CTA chain, second run: marker forces")
+        runs[chain] = (f, h)
+    # dense-window variant (stage 0 interpolates a precomputed window velocity)
+    st = Stepper(spec, ib_chain="cta", fuse_ib=False)
+    st._use_uwin = True
+    st._u_win = torch.zeros(st.win_size + (2,), device="cuda")
+    st.set_f(f0).step(10)
+    assert_close(N(st.get_f()), f_ref, what="chain cta with u_win: populations")
+
+
+@pytest.mark.parametrize("chain", ["auto", "barrier", "launches", "cluster", "cta"])
 def test_viv_rotating_body_host_and_device(golden, chain):
     """Rotational degree of freedom in the fused path (dyn.py:84-154): marker kinematics, per-marker
     target velocity, torque sum and the matrix-form Newmark update, ODE on the host and on the device, against the

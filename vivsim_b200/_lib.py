@@ -20,7 +20,7 @@ BC = {"nee": 0, "nebb": 1, "equilibrium": 2, "bounce_back": 3, "specular_reflect
 WRAP = {"": 0, "velocity": 1, "pressure": 2, "force_corrected": 3}
 LOC = {"left": 0, "right": 1, "bottom": 2, "top": 3, "back": 4, "front": 5}
 DELTA = {"peskin3": 0, "peskin4": 1, "cosine4": 2, "hat2": 3}
-CHAIN = {"auto": 0, "barrier": 1, "cluster": 2, "launches": 3}
+CHAIN = {"auto": 0, "barrier": 1, "cluster": 2, "launches": 3, "cta": 4}
 DIAG = {"velocity_magnitude": 0, "velocity_gradient": 1, "vorticity": 2, "vorticity_magnitude": 3, "divergence": 4,
         "strain_rate": 5, "strain_rate_magnitude": 6, "kinetic_energy": 7, "pressure": 8, "enstrophy": 9,
         "q_criterion": 10}

@@ -586,6 +586,18 @@ static int mdf_impl(const VsbStepArgs& sa, const VsbMdfArgs& a, const VsbBodyPar
   const int mode = a.chain_mode;
   bool use_cluster = false;
   if constexpr (DIM == 2) {
+    // Small 2-D bodies, on request (chain_mode 4; VSB_MDF_CTA=1 makes it the automatic choice): the whole chain in ONE
+    // CTA, work field in shared memory, spread as a gather over per-cell buckets (vsb_mdf_cta.cu) -- no floating-point
+    // atomics, bit-reproducible.  Measured on C2: 60 us against 14-18 us for the grid-barrier chain (one SM is not
+    // enough for 8192 stencil points x 5 iterations), so it is not the default.
+    static const bool cta_auto = [] { const char* e = getenv("VSB_MDF_CTA"); return e && e[0] == '1'; }();
+    const bool use_cta = (mode == 4 || (mode == 0 && cta_auto)) && mdf_cta2d_supported(p);
+    if (mode == 4 && !use_cta) {
+      set_error("vsb_ib_mdf: chain_mode 4 (one CTA) needs a 2-D body of at most 512 markers in a window of fewer than "
+                "~19000 cells");
+      return VSB_ERR_INVALID;
+    }
+    if (use_cta) return launch_mdf_cta2d(sp, p, bu, stream);
     // Small 2-D bodies: the whole chain in one thread-block cluster, work fields in distributed shared memory,
     // hardware cluster barriers between the iterations (vsb_mdf_cluster.cu)
     use_cluster = (mode == 0 || mode == 2) && a.u_win == nullptr && mdf_cluster2d_supported(p);
@@ -595,8 +607,8 @@ static int mdf_impl(const VsbStepArgs& sa, const VsbMdfArgs& a, const VsbBodyPar
       return VSB_ERR_INVALID;
     }
     if (use_cluster) return launch_mdf_cluster2d(sp, p, bu, stream);
-  } else if (mode == 2) {
-    set_error("vsb_ib_mdf: chain_mode 2 (cluster) is for 2-D bodies");
+  } else if (mode == 2 || mode == 4) {
+    set_error("vsb_ib_mdf: chain_mode 2 (cluster) and 4 (one CTA) are for 2-D bodies");
     return VSB_ERR_INVALID;
   }
   // Small bodies: every iteration in ONE launch, separated by grid barriers.  The launch is cooperative, so all of its

@@ -172,4 +172,8 @@ int launch_mdf_stage_sharded(int dim, const MdfParams& p, const ShardDev& sh, bo
 bool mdf_cluster2d_supported(const MdfParams& p);
 int launch_mdf_cluster2d(const StepParams<2>& sp, const MdfParams& p, const BodyUpdate& bu, cudaStream_t stream);
 
+// Whole chain of a small 2-D body in one CTA, work field in shared memory, no floating-point atomics (vsb_mdf_cta.cu).
+bool mdf_cta2d_supported(const MdfParams& p);
+int launch_mdf_cta2d(const StepParams<2>& sp, const MdfParams& p, const BodyUpdate& bu, cudaStream_t stream);
+
 }  // namespace vsb

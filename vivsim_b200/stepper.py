@@ -114,8 +114,9 @@ class Stepper:
         rotation=True and center=(cx, cy) adds the rotation about the centre (dyn.py:84-154).
         dyn_mode "host" (reference-faithful, one tiny D2H/H2D per step) or "device"
         (vsb_body_newmark, graph-capturable).  follow: IB window rule for a moving body (1 trunc, 2 clip(floor)).
-        ib_chain: how a small body's MDF iterations are chained in one launch -- "auto", "barrier" (grid barriers,
-        cooperative launch), "cluster" (one thread-block cluster, work fields in distributed shared memory; 2-D,
+        ib_chain: how a small body's MDF iterations are chained in one launch -- "auto", "cta" (ONE CTA, work field in
+        shared memory, spread as a gather over per-cell buckets: no floating-point atomics, bit-reproducible; 2-D,
+        <= 512 markers), "barrier" (grid barriers, cooperative launch), "cluster" (one thread-block cluster, work fields in distributed shared memory; 2-D,
         <= 512 markers) or "launches" (one launch per iteration).
         chain_first: put a one-launch IB chain on the SMs BEFORE the bulk pass -- the bulk is enqueued behind it as a
         programmatic dependent launch and fills the rest of the device, the window band follows the chain on a second
