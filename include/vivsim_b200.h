@@ -244,12 +244,12 @@ typedef struct {
                       torque of +F accumulated into body->force_sum[2]                                        */
   float center[2];
   int chain_mode;                  /* how a small body's iterations are chained inside one launch:
-                      0 auto; 1 grid barriers through `barrier` (cooperative launch); 2 one thread-block cluster that
+                      0 auto (1 for small bodies, else 3); 1 grid barriers through `barrier` (cooperative launch); 2 one thread-block cluster that
                       iterates in marker space (2-D, <= 512 markers, needs nbr_list); 3 one launch per iteration;
                       4 ONE CTA with the work field in shared memory and the spread done as a gather over per-cell
                       buckets -- no floating-point atomics, bit-reproducible (2-D, <= 512 markers, window of fewer than
                       ~19000 cells; measured 3-4x slower than 1 on BASELINE config 2, kept for reproducibility) */
-  const uint16_t* nbr_list;        /* chain_mode 0 / 2: (nbr_stride, 512) device array, neighbour-major: column m lists the
+  const uint16_t* nbr_list;        /* chain_mode 2: (nbr_stride, 512) device array, neighbour-major: column m lists the
                       markers whose 4 x 4 stencil can overlap that of marker m under any rigid motion of the body (m
                       itself included), padded with 0xffff; nbr_stride a multiple of 4, <= 48.  NULL: no cluster kernel */
   int nbr_stride;

@@ -22,7 +22,8 @@ elif name == "c5slab":   # one slab of the 1024 x 512 x 512 MRT case (1/8 of the
                       post=[], u0=0.05), None
 else:
     raise SystemExit("unknown workload")
-st = Stepper(spec, body=body, dyn_mode="device", follow=2 if name == "c5" else 1) if body else Stepper(spec)
+kw = dict(ib_chain=os.environ["VSB_CHAIN"]) if "VSB_CHAIN" in os.environ else {}
+st = Stepper(spec, body=body, dyn_mode="device", follow=2 if name == "c5" else 1, **kw) if body else Stepper(spec, **kw)
 st.set_f(configs.uniform_state(spec, noise=1e-3))
 st.step(steps)
 torch.cuda.synchronize()

@@ -368,24 +368,23 @@ class Stepper:
         m.barrier = self._mdf_barrier.data_ptr()
         lanes = 16 if dim == 2 else 32
         chain = self._ib_chain
-        if chain in ("auto", "cluster") and dim == 2 and self.n_markers <= 512:
+        if chain == "cluster" and (dim != 2 or self.n_markers > 512):
+            raise ValueError("ib_chain='cluster' is for 2-D bodies of at most 512 markers")
+        if chain == "cluster":
             # the cluster kernel keeps, per marker, the markers whose 4 x 4 stencil can overlap its own (within 3 cells
             # per axis, whatever the rigid motion): at most 96.  The marker set is rigid, so check once.
             d2 = ((markers[:, None, :].astype(np.float64) - markers[None, :, :]) ** 2).sum(axis=2)
             near = d2 < (4 * 2 ** 0.5 + 1.5) ** 2            # |base difference| <= 3 per axis => distance < 4 sqrt(2) + 1
             stride = int(near.sum(axis=1).max())
-            if stride > 48 and chain == "cluster":
-                raise ValueError("ib_chain='cluster': more than 48 markers within reach of one marker's stencil")
             if stride > 48:
-                chain = "barrier"
-            else:
-                stride = (stride + 3) // 4 * 4
-                nbr = np.full((stride, 512), 0xFFFF, dtype=np.uint16)      # neighbour-major, one column per marker
-                for i in range(self.n_markers):
-                    js = np.flatnonzero(near[i])
-                    nbr[:js.size, i] = js
-                self._nbr = torch.as_tensor(nbr.view(np.int16), device=dev)
-                m.nbr_list, m.nbr_stride = self._nbr.data_ptr(), stride
+                raise ValueError("ib_chain='cluster': more than 48 markers within reach of one marker's stencil")
+            stride = (stride + 3) // 4 * 4
+            nbr = np.full((stride, 512), 0xFFFF, dtype=np.uint16)      # neighbour-major, one column per marker
+            for i in range(self.n_markers):
+                js = np.flatnonzero(near[i])
+                nbr[:js.size, i] = js
+            self._nbr = torch.as_tensor(nbr.view(np.int16), device=dev)
+            m.nbr_list, m.nbr_stride = self._nbr.data_ptr(), stride
         # Dense body in a window that follows it: only a thin shell of the window is ever within reach of a stencil.
         # Its cell list lets the window-velocity kernel and the per-step clearing skip the rest (C5: 7.1 M -> 0.9 M cells).
         self._reach = None
