@@ -786,7 +786,7 @@ struct HostOdeDomain {
   VsbStepArgs* a; VsbMdfArgs* mdf; const VsbBodyParams* bp; VsbBodyState* pinned;
   cudaStream_t main, ib, edge;
   cudaEvent_t fork, ib_done, edge_done;
-  int has_edges, want, steps_done, in_flight;
+  int has_edges, want, steps_done, in_flight, n_steps;
   cudaGraphExec_t graph[2];    // by step parity; null: launch kernel by kernel
 };
 
@@ -863,8 +863,11 @@ int host_ode_complete(HostOdeDomain& d) {
   for (int c = 0; c < 3; ++c) d.pinned->force_sum[c] = mail->force[c];
   host_body_update(d.pinned, d.bp, par);
   if (d.graph[par]) {
-    // behind the whole step in `main` (the next step needs all of it anyway): two driver calls per step in total
-    if ((e = cudaMemcpyAsync(mdf->body, d.pinned, sizeof(VsbBodyState), cudaMemcpyHostToDevice, d.main)) != cudaSuccess)
+    // The graph of the NEXT step begins with the copy of the body state from this page-locked buffer (a memcpy node,
+    // host_ode_capture), so a step costs the host ONE driver call -- the graph launch; the loop is bound by those
+    // calls, not by the device.  Only the state after the last step of the run is sent explicitly.
+    if (d.steps_done + 1 >= d.n_steps &&
+        (e = cudaMemcpyAsync(mdf->body, d.pinned, sizeof(VsbBodyState), cudaMemcpyHostToDevice, d.main)) != cudaSuccess)
       return cuda_fail(e, "vsb_run_host_ode (host -> device)");
   } else {
     if ((e = cudaMemcpyAsync(mdf->body, d.pinned, sizeof(VsbBodyState), cudaMemcpyHostToDevice, d.ib)) != cudaSuccess)
@@ -895,7 +898,10 @@ int host_ode_capture(HostOdeDomain& d) {
       rc = cuda_fail(e, "vsb_run_host_ode (begin capture)");
       break;
     }
-    rc = host_ode_kernels(d, true);
+    // first node: the body state the host computed from the previous step's force (page-locked memory, read when the
+    // node executes -- the host writes it before it launches the graph and not again until this step's force is back)
+    e = cudaMemcpyAsync(d.mdf->body, d.pinned, sizeof(VsbBodyState), cudaMemcpyHostToDevice, d.main);
+    rc = (e == cudaSuccess) ? host_ode_kernels(d, true) : cuda_fail(e, "vsb_run_host_ode (capture of the state copy)");
     e = cudaStreamEndCapture(d.main, &g);
     if (rc == VSB_OK && e != cudaSuccess) rc = cuda_fail(e, "vsb_run_host_ode (end capture)");
     if (rc == VSB_OK && (e = cudaGraphInstantiate(&d.graph[par], g, 0)) != cudaSuccess) {
@@ -989,7 +995,7 @@ int vsb_run_host_ode_multi(int n_domains, VsbStepArgs* const* args, VsbMdfArgs* 
     for (int j = 0; j < i; ++j)
       VSB_REQUIRE(dom[j].ib != d.ib && (n_domains == 1 || dom[j].main != d.main) && dom[j].mdf->host_mail != d.mdf->host_mail,
                   "vsb_run_host_ode_multi: domains %d and %d share a stream or a mailbox", j, i);
-    d.want = 0; d.steps_done = 0; d.in_flight = 0;
+    d.want = 0; d.steps_done = 0; d.in_flight = 0; d.n_steps = n_steps;
     d.graph[0] = d.graph[1] = nullptr;
   }
   if (n_steps <= 0) return VSB_OK;
