@@ -397,7 +397,10 @@ int vsb_enqueue_host_ode(VsbStepArgs* args, VsbMdfArgs* mdf, const VsbBodyParams
  * advanced (dyn.py:5-51), its state sent back and its next step enqueued, so the device always has other domains'
  * kernels to run while one domain waits for the host -- the per-step host round trip is hidden instead of paid.
  * Runs of >= 32 steps record each domain's step (both parities) as CUDA graphs after two kernel-by-kernel steps and
- * replay them: two driver calls per step (graph launch, 92-byte state copy); VSB_HOST_ODE_GRAPH=0 switches that off,
+ * replay them: ONE driver call per step (the graph's first node is the 92-byte copy of the body state from `pinned`).
+ * The graphs are kept for the next call with the same `plans[i]` and are replayed again as long as every argument a
+ * captured step depends on is unchanged (both argument blocks, face operations, MRT operators, streams, `pinned`,
+ * mailbox -- compared byte by byte), else recorded anew.  VSB_HOST_ODE_GRAPH=0 switches graphs off,
  * VSB_HOST_ODE_THREADS=T serves the domains from T host threads (kernel by kernel). */
 int vsb_run_host_ode_multi(int n_domains, VsbStepArgs* const* args, VsbMdfArgs* const* mdfs,
                            const VsbBodyParams* const* params, VsbBodyState* const* pinned,

@@ -508,6 +508,39 @@ def test_host_ode_ensemble_matches_solo_runs(golden):
         Ensemble([ens.steppers[0], Stepper(spec, body=dict(bodies[0]), dyn_mode="host", follow=1, fuse_ib=False).set_f(f0)]).step(2)
 
 
+def test_host_ode_step_graphs_are_reused_from_chunk_to_chunk(golden):
+    """A driver loop calls the host-ODE runner once per chunk; the two step graphs of a domain are kept between the
+    calls (keyed by everything a captured step depends on).  Chunks of even and odd length (the latter start on the
+    other parity), a change of the step's arguments in between (stale graphs must not be replayed): always the result
+    of the same steps launched kernel by kernel."""
+    g = golden["recipes"]
+    spec, body, f0, (d, v, a), _ = cases.viv(g)
+    from vivsim_b200 import Ensemble, Stepper
+    import os
+    bd = dict(body, d0=d, v0=v, a0=a, n_dof=2, history=256)
+    chunks = (40, 33, 37, 40)
+
+    def run(graph):
+        os.environ["VSB_HOST_ODE_GRAPH"] = "1" if graph else "0"
+        try:
+            ens = Ensemble([Stepper(spec, body=dict(bd), dyn_mode="host", follow=1, fuse_ib=False).set_f(f0) for _ in range(2)])
+            for k, n in enumerate(chunks):
+                if k == 3:      # a different relaxation rate from here on: the cached graphs no longer describe the step
+                    for st in ens.steppers:
+                        st._args.omega = float(st._args.omega) * 0.98
+                ens.step(n)
+            return ens
+        finally:
+            del os.environ["VSB_HOST_ODE_GRAPH"]
+
+    a_, b_ = run(True), run(False)
+    for k in range(2):
+        assert a_.steppers[k].body_steps() == sum(chunks)
+        assert_close(N(a_.steppers[k].get_f()), N(b_.steppers[k].get_f()), what=f"member {k}: populations")
+        for x, y, nm in zip(a_.steppers[k].body_history(), b_.steppers[k].body_history(), ("d", "h")):
+            assert_close(x, y, rtol=1e-4, what=f"member {k}: {nm} history")
+
+
 def test_checkpoint_restore_resumes_identically(golden, tmp_path):
     """Dump after 8 steps, restore into a fresh stepper (through a file), continue: same state as an uninterrupted run.
     Without a body the continuation is bit-identical; with one it agrees to the rounding of the fp32 atomics."""

@@ -8,7 +8,9 @@
 #include <climits>
 #include <cstdlib>
 #include <string>
+#include <mutex>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "vsb_mdf.cuh"
@@ -788,7 +790,92 @@ struct HostOdeDomain {
   cudaEvent_t fork, ib_done, edge_done;
   int has_edges, want, steps_done, in_flight, n_steps;
   cudaGraphExec_t graph[2];    // by step parity; null: launch kernel by kernel
+  const void* plan;            // the caller's VsbHostPlan: key of the graph cache
+  bool graphs_from_cache;
 };
+
+// The two step graphs of a domain are kept from one vsb_run_host_ode[_multi] call to the next (a driver loop calls once
+// per chunk of a few hundred steps; capturing and instantiating 2 graphs per domain and chunk cost ~5 % of such a
+// chunk).  Cached per VsbHostPlan; valid as long as everything a captured step depends on is unchanged -- both argument
+// blocks (normalised to parity 0), the face operations, the MRT operators, streams and the page-locked state buffer.
+struct HostOdeGraphs {
+  std::vector<unsigned char> key;
+  cudaGraphExec_t graph[2];
+};
+std::mutex g_host_ode_mu;
+std::unordered_map<const void*, HostOdeGraphs> g_host_ode_graphs;
+
+void key_bytes(std::vector<unsigned char>& k, const void* p, size_t n) {
+  const unsigned char* b = static_cast<const unsigned char*>(p);
+  k.insert(k.end(), b, b + n);
+}
+
+std::vector<unsigned char> host_ode_key(const HostOdeDomain& d) {
+  VsbStepArgs a = *d.a;
+  VsbMdfArgs m = *d.mdf;
+  if (m.parity & 1) {   // what alternates with the parity, put back to parity 0
+    const float* fi = a.f_in; a.f_in = a.f_out; a.f_out = const_cast<float*>(fi);
+    float* t = m.g_win; m.g_win = m.g_win_next; m.g_win_next = t;
+    t = m.scratch; m.scratch = m.scratch_next; m.scratch_next = t;
+  }
+  m.parity = 0; m.mail_seq = 0; a.parity = 0; a.g_win = m.g_win; a.band = 0;
+  std::vector<unsigned char> k;
+  key_bytes(k, &a, sizeof(a));
+  key_bytes(k, &m, sizeof(m));
+  if (a.n_post > 0 && a.post) key_bytes(k, a.post, sizeof(VsbPostOp) * (size_t)a.n_post);
+  const size_t qq = (a.grid.dim == 2 ? 81 : 361) * sizeof(float);
+  if (a.mrt_op_host) key_bytes(k, a.mrt_op_host, qq);
+  if (a.mrt_fop_host) key_bytes(k, a.mrt_fop_host, qq);
+  const void* handles[5] = {d.main, d.ib, d.edge, d.pinned, d.mdf->host_mail};
+  key_bytes(k, handles, sizeof(handles));
+  return k;
+}
+
+// Graphs of an earlier call with the same plan and an identical step, if any.
+bool host_ode_cached_graphs(HostOdeDomain& d) {
+  const std::vector<unsigned char> key = host_ode_key(d);
+  std::lock_guard<std::mutex> lock(g_host_ode_mu);
+  auto it = g_host_ode_graphs.find(d.plan);
+  if (it == g_host_ode_graphs.end()) return false;
+  if (it->second.key != key) {   // the step changed: those graphs are stale
+    for (int k = 0; k < 2; ++k)
+      if (it->second.graph[k]) cudaGraphExecDestroy(it->second.graph[k]);
+    g_host_ode_graphs.erase(it);
+    return false;
+  }
+  d.graph[0] = it->second.graph[0];
+  d.graph[1] = it->second.graph[1];
+  d.graphs_from_cache = true;
+  return true;
+}
+
+// End of a call: hand the graphs to the cache (or drop them when the domain ended on an error).
+void host_ode_keep_graphs(HostOdeDomain& d, bool ok) {
+  if (!d.graph[0] && !d.graph[1]) return;
+  if (ok && d.graph[0] && d.graph[1] && !d.in_flight) {
+    if (!d.graphs_from_cache) {
+      HostOdeGraphs g;
+      g.key = host_ode_key(d);
+      g.graph[0] = d.graph[0]; g.graph[1] = d.graph[1];
+      std::lock_guard<std::mutex> lock(g_host_ode_mu);
+      auto it = g_host_ode_graphs.find(d.plan);
+      if (it != g_host_ode_graphs.end()) {
+        for (int k = 0; k < 2; ++k)
+          if (it->second.graph[k]) cudaGraphExecDestroy(it->second.graph[k]);
+        g_host_ode_graphs.erase(it);
+      }
+      g_host_ode_graphs.emplace(d.plan, std::move(g));
+    }
+  } else {
+    if (d.graphs_from_cache) {
+      std::lock_guard<std::mutex> lock(g_host_ode_mu);
+      g_host_ode_graphs.erase(d.plan);
+    }
+    for (int k = 0; k < 2; ++k)
+      if (d.graph[k]) cudaGraphExecDestroy(d.graph[k]);
+  }
+  d.graph[0] = d.graph[1] = nullptr;
+}
 
 // The device work of one step: IB chain (posts the force into the mailbox) and window band on `ib`, bulk on `main`,
 // wall layers on `edge`.  join = true (graph capture) also folds the side streams back into `main`.
@@ -887,6 +974,7 @@ int host_ode_complete(HostOdeDomain& d) {
 int host_ode_capture(HostOdeDomain& d) {
   // the legacy default stream cannot be captured: such a domain keeps launching kernel by kernel
   if (d.main == nullptr || d.main == cudaStreamLegacy || d.main == cudaStreamPerThread) return VSB_OK;
+  if (host_ode_cached_graphs(d)) return VSB_OK;
   cudaError_t e;
   const int saved_seq = d.mdf->mail_seq;
   d.mdf->mail_seq = -1;
@@ -997,6 +1085,7 @@ int vsb_run_host_ode_multi(int n_domains, VsbStepArgs* const* args, VsbMdfArgs* 
                   "vsb_run_host_ode_multi: domains %d and %d share a stream or a mailbox", j, i);
     d.want = 0; d.steps_done = 0; d.in_flight = 0; d.n_steps = n_steps;
     d.graph[0] = d.graph[1] = nullptr;
+    d.plan = plan; d.graphs_from_cache = false;
   }
   if (n_steps <= 0) return VSB_OK;
   // Host threads: one thread serves all domains by default.  VSB_HOST_ODE_THREADS = T gives each of T threads a fixed
@@ -1010,14 +1099,12 @@ int vsb_run_host_ode_multi(int n_domains, VsbStepArgs* const* args, VsbMdfArgs* 
   // launch, state copy) instead of about ten.  VSB_HOST_ODE_GRAPH=0 keeps launching kernel by kernel.
   const char* ge = getenv("VSB_HOST_ODE_GRAPH");
   const int graph_after = ((ge ? atoi(ge) != 0 : true) && n_steps >= 32 && n_thr == 1) ? 2 : 0;
-  auto cleanup = [&] {
-    for (int i = 0; i < n_domains; ++i)
-      for (int k = 0; k < 2; ++k)
-        if (dom[i].graph[k]) { cudaGraphExecDestroy(dom[i].graph[k]); dom[i].graph[k] = nullptr; }
+  auto cleanup = [&](bool ok) {
+    for (int i = 0; i < n_domains; ++i) host_ode_keep_graphs(dom[i], ok);
   };
   if (n_thr == 1) {
     const int rc1 = host_ode_serve(dom, n_domains, 1, 0, n_steps, graph_after);
-    cleanup();
+    cleanup(rc1 == VSB_OK);
     return rc1;
   }
   int dev = 0;
@@ -1033,7 +1120,7 @@ int vsb_run_host_ode_multi(int n_domains, VsbStepArgs* const* args, VsbMdfArgs* 
     });
   rcs[0] = host_ode_serve(dom, n_domains, n_thr, 0, n_steps, graph_after);
   for (auto& w : workers) w.join();
-  cleanup();
+  cleanup(false);
   for (int t = 1; t < n_thr; ++t)
     if (rcs[t]) { set_error("%s", msgs[t].c_str()); return rcs[t]; }
   return rcs[0];
